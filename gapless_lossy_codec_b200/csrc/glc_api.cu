@@ -1,0 +1,1446 @@
+// glc_api.cu -- host side of libglc_b200.so: contexts, memory pools, batching, the C ABI of
+// include/glc.h.  Raw CUDA runtime calls only (no PyTorch, no CPU compute fallback: when there is
+// no device every entry point fails with GLC_ERR_NO_DEVICE).
+//
+// Host-side structure of one encode (reference Encoder::encode, src/codec.rs:421-565):
+//   files -> FileDesc table (row/frame numbering across the whole batch)
+//   waves of frames:  H2D of the wave's PCM on the copy stream  ||  mdct_exact + quant_pack of the
+//                     previous wave on the compute stream (events order them)
+//   scan (nnz, raw lengths) -> gather into the compact stream -> D2H into pooled pinned memory.
+// One decode (Decoder::decode, src/codec.rs:595-768):
+//   H2D stream -> dequant (+ per-tile k-chunk masks) -> imdct_exact -> overlap-add/interleave -> D2H,
+//   the gapless trim being an offset/length applied to the D2H copy.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "glc_internal.cuh"
+
+using namespace glc;
+
+// ------------------------------------------------------------------ errors
+
+static thread_local std::string g_last_error;
+
+static glc_status fail(glc_status st, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return st;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(GLC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+#define GLC_TRY(expr)              \
+    do                             \
+    {                              \
+        glc_status _s = (expr);    \
+        if (_s != GLC_OK)          \
+            return _s;             \
+    } while (0)
+
+extern "C" const char *glc_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint32_t glc_abi_version(void) { return GLC_ABI_VERSION; }
+
+extern "C" glc_status glc_device_count(int *count)
+{
+    if (!count)
+        return fail(GLC_ERR_INVALID_ARG, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+    {
+        *count = 0;
+        (void)cudaGetLastError();
+        return fail(GLC_ERR_NO_DEVICE, "no CUDA device available (%s); libglc_b200 has no CPU fallback",
+                    e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    }
+    *count = n;
+    return GLC_OK;
+}
+
+// ----------------------------------------------------------- pinned pool
+
+struct PinnedBlock
+{
+    void *p;
+    size_t cap;
+    bool used;
+};
+
+struct PinnedPool
+{
+    std::vector<PinnedBlock> blocks;
+    std::mutex mu;
+
+    void *alloc(size_t bytes)
+    {
+        if (bytes == 0)
+            bytes = 16;
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (size_t i = 0; i < blocks.size(); ++i)
+            if (!blocks[i].used && blocks[i].cap >= bytes && blocks[i].cap <= bytes * 2 + (1u << 20))
+                if (best < 0 || blocks[i].cap < blocks[best].cap)
+                    best = (int)i;
+        if (best >= 0)
+        {
+            blocks[best].used = true;
+            return blocks[best].p;
+        }
+        size_t cap = (bytes + 4095) & ~(size_t)4095;
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        blocks.push_back({p, cap, true});
+        return p;
+    }
+    bool release(void *p)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &b : blocks)
+            if (b.p == p)
+            {
+                b.used = false;
+                return true;
+            }
+        return false;
+    }
+    void destroy()
+    {
+        for (auto &b : blocks)
+            cudaFreeHost(b.p);
+        blocks.clear();
+    }
+};
+
+// ------------------------------------------------------------------ context
+
+struct TimedLaunch
+{
+    int id;
+    cudaEvent_t a, b;
+};
+
+struct glc_ctx
+{
+    int device;
+    glc_mode mode;
+    cudaStream_t compute, copy;
+    cudaEvent_t t0, t1;
+    HostTables host;
+    float *d_tab_mdct, *d_tab_imdct, *d_window;
+    PinnedPool pool;
+    glc_stats stats;
+    bool timing;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> ev_free;
+    int gemm_variant;
+    uint64_t wave_frames;
+    float *d_flush;
+    size_t flush_floats;
+};
+
+struct glc_encoder
+{
+    glc_ctx *ctx;
+    uint32_t sample_rate;
+    DevPerceptual *d_perc;
+};
+
+struct glc_decoder
+{
+    glc_ctx *ctx;
+    uint32_t channels, sample_rate;
+};
+
+static cudaEvent_t get_event(glc_ctx *c)
+{
+    if (!c->ev_free.empty())
+    {
+        cudaEvent_t e = c->ev_free.back();
+        c->ev_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Brackets one kernel launch for the per-kernel statistics.
+struct LaunchScope
+{
+    glc_ctx *c;
+    int id;
+    cudaStream_t s;
+    cudaEvent_t a;
+    LaunchScope(glc_ctx *ctx, int kid, cudaStream_t st, uint64_t n_launches = 1) : c(ctx), id(kid), s(st), a(nullptr)
+    {
+        c->stats.launches[id] += n_launches;
+        if (c->timing)
+        {
+            a = get_event(c);
+            cudaEventRecord(a, s);
+        }
+    }
+    ~LaunchScope()
+    {
+        if (c->timing)
+        {
+            cudaEvent_t b = get_event(c);
+            cudaEventRecord(b, s);
+            c->timed.push_back({id, a, b});
+        }
+    }
+};
+
+static void drain_timed(glc_ctx *c)
+{
+    for (auto &t : c->timed)
+    {
+        cudaEventSynchronize(t.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess)
+            c->stats.kernel_ms[t.id] += ms;
+        c->ev_free.push_back(t.a);
+        c->ev_free.push_back(t.b);
+    }
+    c->timed.clear();
+}
+
+extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
+{
+    if (!out)
+        return fail(GLC_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    GLC_TRY(glc_device_count(&n));
+    if (device < 0 || device >= n)
+        return fail(GLC_ERR_INVALID_ARG, "device %d out of range (have %d)", device, n);
+    if (mode != GLC_MODE_EXACT)
+        return fail(GLC_ERR_UNSUPPORTED, "only GLC_MODE_EXACT is implemented in this build");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(GLC_ERR_NO_DEVICE, "device %d is sm_%d%d; libglc_b200 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    glc_ctx *c = new (std::nothrow) glc_ctx();
+    if (!c)
+        return fail(GLC_ERR_NO_MEMORY, "out of host memory");
+    c->device = device;
+    c->mode = mode;
+    c->timing = false;
+    memset(&c->stats, 0, sizeof c->stats);
+    c->gemm_variant = 0;
+    if (const char *v = getenv("GLC_GEMM_VARIANT"))
+        c->gemm_variant = atoi(v);
+    c->wave_frames = 8192;
+    if (const char *v = getenv("GLC_WAVE_FRAMES"))
+        c->wave_frames = (uint64_t)atoll(v) > 0 ? (uint64_t)atoll(v) : 8192;
+    c->d_flush = nullptr;
+    c->flush_floats = 0;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->t0));
+    CUDA_TRY(cudaEventCreate(&c->t1));
+    // keep freed stream-ordered allocations cached in the pool (no trimming at sync points)
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess)
+    {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    // tables: host libm -> tiled copies -> device
+    build_host_tables(&c->host);
+    const size_t tab_bytes = sizeof(float) * (size_t)kHop * kFrame;
+    float *tiled = (float *)malloc(tab_bytes);
+    if (!tiled)
+        return fail(GLC_ERR_NO_MEMORY, "out of host memory");
+    CUDA_TRY(cudaMalloc(&c->d_tab_mdct, tab_bytes));
+    CUDA_TRY(cudaMalloc(&c->d_tab_imdct, tab_bytes));
+    CUDA_TRY(cudaMalloc(&c->d_window, sizeof(float) * kFrame));
+    tile_table_for_mdct(c->host.cos_tab, tiled);
+    CUDA_TRY(cudaMemcpy(c->d_tab_mdct, tiled, tab_bytes, cudaMemcpyHostToDevice));
+    tile_table_for_imdct(c->host.cos_tab, tiled);
+    CUDA_TRY(cudaMemcpy(c->d_tab_imdct, tiled, tab_bytes, cudaMemcpyHostToDevice));
+    free(tiled);
+    CUDA_TRY(cudaMemcpy(c->d_window, c->host.window, sizeof(float) * kFrame, cudaMemcpyHostToDevice));
+    *out = c;
+    return GLC_OK;
+}
+
+extern "C" void glc_ctx_destroy(glc_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    drain_timed(c);
+    for (auto e : c->ev_free)
+        cudaEventDestroy(e);
+    cudaFree(c->d_tab_mdct);
+    cudaFree(c->d_tab_imdct);
+    cudaFree(c->d_window);
+    if (c->d_flush)
+        cudaFree(c->d_flush);
+    c->pool.destroy();
+    free_host_tables(&c->host);
+    cudaEventDestroy(c->t0);
+    cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->compute);
+    cudaStreamDestroy(c->copy);
+    delete c;
+}
+
+extern "C" glc_status glc_ctx_set_tuning(glc_ctx *c, int gemm_variant, uint64_t wave_frames)
+{
+    if (!c)
+        return fail(GLC_ERR_INVALID_ARG, "ctx is null");
+    if (gemm_variant >= 0 && gemm_variant <= 2)
+        c->gemm_variant = gemm_variant;
+    if (wave_frames)
+        c->wave_frames = wave_frames;
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_host_alloc(glc_ctx *c, size_t bytes, void **out)
+{
+    if (!c || !out)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    cudaSetDevice(c->device);
+    *out = c->pool.alloc(bytes);
+    if (!*out)
+        return fail(GLC_ERR_NO_MEMORY, "pinned allocation of %zu bytes failed", bytes);
+    return GLC_OK;
+}
+
+extern "C" void glc_host_free(glc_ctx *c, void *p)
+{
+    if (c && p)
+        c->pool.release(p);
+}
+
+extern "C" void glc_free(glc_ctx *c, void *p)
+{
+    if (c && p)
+        if (!c->pool.release(p))
+            free(p);
+}
+
+extern "C" void glc_stats_reset(glc_ctx *c)
+{
+    if (!c)
+        return;
+    drain_timed(c);
+    memset(&c->stats, 0, sizeof c->stats);
+}
+
+extern "C" void glc_stats_get(glc_ctx *c, glc_stats *out)
+{
+    if (!c || !out)
+        return;
+    cudaSetDevice(c->device);
+    drain_timed(c);
+    *out = c->stats;
+}
+
+extern "C" void glc_stats_enable_kernel_timing(glc_ctx *c, int on)
+{
+    if (c)
+    {
+        drain_timed(c);
+        c->timing = on != 0;
+    }
+}
+
+extern "C" glc_status glc_timer_begin(glc_ctx *c)
+{
+    if (!c)
+        return fail(GLC_ERR_INVALID_ARG, "ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->t0, c->compute));
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_timer_end(glc_ctx *c, float *ms)
+{
+    if (!c || !ms)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->t1, c->compute));
+    CUDA_TRY(cudaEventSynchronize(c->t1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->t0, c->t1));
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_ctx_sync(glc_ctx *c)
+{
+    if (!c)
+        return fail(GLC_ERR_INVALID_ARG, "ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->copy));
+    CUDA_TRY(cudaStreamSynchronize(c->compute));
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_flush_l2(glc_ctx *c)
+{
+    if (!c)
+        return fail(GLC_ERR_INVALID_ARG, "ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->d_flush)
+    {
+        c->flush_floats = (size_t)64 << 20; // 256 MiB > 126 MB L2
+        CUDA_TRY(cudaMalloc(&c->d_flush, c->flush_floats * sizeof(float)));
+    }
+    LaunchScope ls(c, GLC_K_MISC, c->compute);
+    CUDA_TRY(launch_fill(c->d_flush, c->flush_floats, 0.0f, c->compute));
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_measure_fp32_issue(glc_ctx *c, int packed, double *tera)
+{
+    if (!c || !tera)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    float *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 64));
+    const int blocks = prop.multiProcessorCount * 8;
+    const int iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep)
+    {
+        CUDA_TRY(cudaEventRecord(c->t0, c->compute));
+        CUDA_TRY(launch_fp32_issue_bench(packed, iters, sink, blocks, c->compute));
+        CUDA_TRY(cudaEventRecord(c->t1, c->compute));
+        CUDA_TRY(cudaEventSynchronize(c->t1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->t0, c->t1));
+        // per thread per iteration: 16 chains x (mul + add) [x2 lanes when packed]
+        const double ops = (double)blocks * 256.0 * iters * 16.0 * 2.0 * (packed ? 2.0 : 1.0);
+        const double t = ops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t > best)
+            best = t;
+    }
+    cudaFree(sink);
+    *tera = best;
+    return GLC_OK;
+}
+
+// ---- plumbing exported to the other translation units ----
+namespace glc
+{
+glc_status set_error(glc_status st, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return st;
+}
+void *pinned_alloc(glc_ctx *ctx, size_t bytes) { return ctx->pool.alloc(bytes); }
+void pinned_release(glc_ctx *ctx, void *p) { ctx->pool.release(p); }
+int ctx_device(glc_ctx *ctx) { return ctx->device; }
+cudaStream_t ctx_compute_stream(glc_ctx *ctx) { return ctx->compute; }
+void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n) { ctx->stats.launches[kernel_id] += n; }
+void ctx_count_bytes(glc_ctx *ctx, uint64_t h2d, uint64_t d2h)
+{
+    ctx->stats.h2d_bytes += h2d;
+    ctx->stats.d2h_bytes += d2h;
+}
+void ctx_time_begin(glc_ctx *ctx, int kernel_id, void **token)
+{
+    *token = nullptr;
+    if (!ctx->timing)
+        return;
+    TimedLaunch *t = new TimedLaunch();
+    t->id = kernel_id;
+    t->a = get_event(ctx);
+    t->b = nullptr;
+    cudaEventRecord(t->a, ctx->compute);
+    *token = t;
+}
+void ctx_time_end(glc_ctx *ctx, void *token)
+{
+    if (!token)
+        return;
+    TimedLaunch *t = (TimedLaunch *)token;
+    t->b = get_event(ctx);
+    cudaEventRecord(t->b, ctx->compute);
+    ctx->timed.push_back(*t);
+    delete t;
+}
+} // namespace glc
+
+// ------------------------------------------------------------ small helpers
+
+template <typename T>
+static cudaError_t dmalloc(T **p, size_t count, cudaStream_t s)
+{
+    *p = nullptr;
+    return cudaMallocAsync((void **)p, std::max<size_t>(count, 1) * sizeof(T), s);
+}
+
+static void dfree(void *p, cudaStream_t s)
+{
+    if (p)
+        cudaFreeAsync(p, s);
+}
+
+static uint64_t padded_len(uint64_t L)
+{
+    uint64_t v = 512 + L; // HOP/2 zeros + data           src/codec.rs:438-439
+    const uint64_t rem = v % kHop;
+    if (rem)
+        v += kHop - rem;  // to a multiple of HOP           :440-444
+    return v + 512;       // + HOP/2 zeros                  :445
+}
+
+static uint64_t frames_for(uint64_t L)
+{
+    return (padded_len(L) - kFrame) / kHop + 1; // src/codec.rs:449-455 (L > 512 guaranteed by caller)
+}
+
+static bool is_device_accessible_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// ------------------------------------------------- device-resident objects
+
+struct glc_dev_pcm
+{
+    glc_ctx *ctx;
+    float *d;          // interleaved samples (for decode output: untrimmed stream)
+    uint64_t n;        // valid interleaved samples after trim
+    uint64_t trim_off; // first valid value (decode output)
+    uint64_t n_alloc;
+    uint16_t channels;
+};
+
+struct glc_dev_encoded
+{
+    glc_ctx *ctx;
+    uint32_t sample_rate;
+    std::vector<FileDesc> files; // one entry per stream in the batch
+    uint64_t n_rows, n_frames;
+    uint8_t *d_is_raw;
+    uint32_t *d_nnz;
+    uint64_t *d_pair_off;
+    glc_pair *d_pairs;
+    float *d_scales;
+    uint64_t *d_raw_off;
+    int16_t *d_raw;
+    uint64_t n_pairs, n_raw;
+};
+
+extern "C" void glc_dev_pcm_free(glc_dev_pcm *p)
+{
+    if (!p)
+        return;
+    cudaSetDevice(p->ctx->device);
+    dfree(p->d, p->ctx->compute);
+    delete p;
+}
+
+extern "C" void glc_dev_encoded_free(glc_dev_encoded *e)
+{
+    if (!e)
+        return;
+    cudaSetDevice(e->ctx->device);
+    cudaStream_t s = e->ctx->compute;
+    dfree(e->d_is_raw, s);
+    dfree(e->d_nnz, s);
+    dfree(e->d_pair_off, s);
+    dfree(e->d_pairs, s);
+    dfree(e->d_scales, s);
+    dfree(e->d_raw_off, s);
+    dfree(e->d_raw, s);
+    delete e;
+}
+
+// ------------------------------------------------------------------ encoder
+
+extern "C" glc_status glc_encoder_new(glc_ctx *c, uint32_t sample_rate, glc_encoder **out)
+{
+    if (!c || !out)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    if (sample_rate == 0)
+        return fail(GLC_ERR_INVALID_ARG, "sample_rate is 0");
+    CUDA_TRY(cudaSetDevice(c->device));
+    HostPerceptual hp;
+    build_host_perceptual(sample_rate, &hp);
+    DevPerceptual *dp = new DevPerceptual();
+    memset(dp, 0, sizeof *dp);
+    memcpy(dp->inv_w, hp.inv_w, sizeof hp.inv_w);
+    memcpy(dp->band_edges, hp.band_edges, sizeof hp.band_edges);
+    memcpy(dp->band_pf, hp.band_pf, sizeof hp.band_pf);
+    memcpy(dp->band_cnt, hp.band_cnt, sizeof hp.band_cnt);
+    for (int b = 0; b + 1 < hp.n_edges; ++b)
+        for (int k = hp.band_edges[b]; k < hp.band_edges[b + 1]; ++k)
+            dp->band_of[k] = (uint8_t)b;
+    dp->n_edges = hp.n_edges;
+    dp->cf = hp.cf;
+    dp->noise_floor_factor = c->host.noise_floor_factor;
+    glc_encoder *e = new glc_encoder();
+    e->ctx = c;
+    e->sample_rate = sample_rate;
+    cudaError_t ce = cudaMalloc(&e->d_perc, sizeof(DevPerceptual));
+    if (ce == cudaSuccess)
+        ce = cudaMemcpy(e->d_perc, dp, sizeof(DevPerceptual), cudaMemcpyHostToDevice);
+    delete dp;
+    if (ce != cudaSuccess)
+    {
+        delete e;
+        return fail(GLC_ERR_CUDA, "encoder table upload failed: %s", cudaGetErrorString(ce));
+    }
+    *out = e;
+    return GLC_OK;
+}
+
+extern "C" void glc_encoder_free(glc_encoder *e)
+{
+    if (!e)
+        return;
+    cudaSetDevice(e->ctx->device);
+    cudaFree(e->d_perc);
+    delete e;
+}
+
+// Builds the batch numbering.  Returns GLC_ERR_TOO_SHORT for inputs the reference panics on.
+static glc_status build_file_table(uint32_t n_files, const uint64_t *n_samples, const uint16_t *channels,
+                                   std::vector<FileDesc> &files, uint64_t *tot_rows, uint64_t *tot_frames,
+                                   uint64_t *tot_pcm)
+{
+    files.resize(n_files);
+    uint64_t rows = 0, frames = 0, pcm = 0;
+    for (uint32_t i = 0; i < n_files; ++i)
+    {
+        const uint32_t ch = channels[i];
+        if (ch == 0)
+            return fail(GLC_ERR_INVALID_ARG, "file %u: channels is 0", i);
+        if (n_samples[i] % ch)
+            return fail(GLC_ERR_INVALID_ARG, "file %u: %llu samples is not a multiple of %u channels", i,
+                        (unsigned long long)n_samples[i], ch);
+        const uint64_t L = n_samples[i] / ch;
+        if (L <= 512)
+            return fail(GLC_ERR_TOO_SHORT,
+                        "file %u: %llu samples per channel; the reference panics for <= 512 "
+                        "(src/codec.rs:449-452,474)",
+                        i, (unsigned long long)L);
+        FileDesc &f = files[i];
+        f.pcm_off = pcm;
+        f.len = L;
+        f.first_row = rows;
+        f.first_frame = frames;
+        f.channels = ch;
+        f.n_frames = (uint32_t)frames_for(L);
+        rows += (uint64_t)f.n_frames * ch;
+        frames += f.n_frames;
+        pcm += n_samples[i];
+        // keep every file's PCM 16-byte aligned in the arena
+        pcm = (pcm + 3) & ~(uint64_t)3;
+    }
+    *tot_rows = rows;
+    *tot_frames = frames;
+    *tot_pcm = pcm;
+    return GLC_OK;
+}
+
+// Core: everything after "PCM is (being put) in the arena".  host_pcm == nullptr means the arena
+// is already fully resident; otherwise the H2D copies are issued here, wave by wave.
+static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &files, uint64_t tot_rows,
+                              uint64_t tot_frames, float *d_arena, const float *const *host_pcm,
+                              const uint64_t *n_samples, glc_dev_encoded **out)
+{
+    glc_ctx *c = enc->ctx;
+    cudaStream_t cs = c->compute;
+    const uint32_t n_files = (uint32_t)files.size();
+
+    FileDesc *d_files = nullptr;
+    CUDA_TRY(dmalloc(&d_files, n_files, cs));
+    CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(FileDesc) * n_files, cudaMemcpyHostToDevice, cs));
+    c->stats.h2d_bytes += sizeof(FileDesc) * n_files;
+
+    glc_dev_encoded *de = new glc_dev_encoded();
+    de->ctx = c;
+    de->sample_rate = enc->sample_rate;
+    de->files = files;
+    de->n_rows = tot_rows;
+    de->n_frames = tot_frames;
+    de->d_pairs = nullptr;
+    de->d_raw = nullptr;
+    glc_pair *d_slots = nullptr;
+    uint32_t *d_raw_len = nullptr;
+    float *d_coefs = nullptr;
+    CUDA_TRY(dmalloc(&de->d_is_raw, tot_frames, cs));
+    CUDA_TRY(dmalloc(&de->d_nnz, tot_rows, cs));
+    CUDA_TRY(dmalloc(&de->d_pair_off, tot_rows + 1, cs));
+    CUDA_TRY(dmalloc(&de->d_scales, tot_rows, cs));
+    CUDA_TRY(dmalloc(&de->d_raw_off, tot_frames + 1, cs));
+    CUDA_TRY(dmalloc(&d_slots, tot_rows * kHop, cs));
+    CUDA_TRY(dmalloc(&d_raw_len, tot_frames, cs));
+
+    // wave plan: contiguous frame ranges; a wave never spans more rows than the coefficient scratch
+    const uint64_t wave_frames = std::max<uint64_t>(c->wave_frames, 1);
+    uint64_t max_wave_rows = 0;
+    struct Wave
+    {
+        uint64_t f0, f1, r0, r1;
+    };
+    std::vector<Wave> waves;
+    {
+        uint32_t fi = 0;
+        uint64_t f = 0;
+        while (f < tot_frames)
+        {
+            const uint64_t f1 = std::min(tot_frames, f + wave_frames);
+            // rows of frames [f, f1)
+            auto row_of_frame = [&](uint64_t fr) -> uint64_t {
+                if (fr >= tot_frames)
+                    return tot_rows;
+                while (fi + 1 < n_files && files[fi + 1].first_frame <= fr)
+                    ++fi;
+                while (fi > 0 && files[fi].first_frame > fr)
+                    --fi;
+                return files[fi].first_row + (fr - files[fi].first_frame) * files[fi].channels;
+            };
+            Wave w{f, f1, row_of_frame(f), row_of_frame(f1)};
+            max_wave_rows = std::max(max_wave_rows, w.r1 - w.r0);
+            waves.push_back(w);
+            f = f1;
+        }
+    }
+    CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
+
+    // H2D plan: file i is needed by the first wave that touches it; copy whole files in order,
+    // splitting big files at wave boundaries so that copy and compute overlap.
+    cudaEvent_t ev_copy = nullptr;
+    if (host_pcm)
+        ev_copy = get_event(c);
+    uint32_t copy_file = 0;      // next file with bytes left to copy
+    uint64_t copy_done = 0;      // interleaved samples of copy_file already enqueued
+    for (size_t wi = 0; wi < waves.size(); ++wi)
+    {
+        const Wave &w = waves[wi];
+        if (host_pcm)
+        {
+            // everything up to the last sample any frame < w.f1 can touch
+            bool issued = false;
+            while (copy_file < n_files)
+            {
+                const FileDesc &fd = files[copy_file];
+                uint64_t need; // interleaved samples of this file needed by frames < w.f1
+                if (fd.first_frame >= w.f1)
+                    break;
+                const uint64_t last_local = std::min<uint64_t>(w.f1 - fd.first_frame, fd.n_frames);
+                const uint64_t last_pos = last_local * kHop + kHop; // exclusive, padded coordinates
+                const uint64_t smp = last_pos > 512 ? std::min<uint64_t>(last_pos - 512, fd.len) : 0;
+                need = smp * fd.channels;
+                if (need > copy_done)
+                {
+                    CUDA_TRY(cudaMemcpyAsync(d_arena + fd.pcm_off + copy_done, host_pcm[copy_file] + copy_done,
+                                             (need - copy_done) * sizeof(float), cudaMemcpyHostToDevice, c->copy));
+                    c->stats.h2d_bytes += (need - copy_done) * sizeof(float);
+                    copy_done = need;
+                    issued = true;
+                }
+                if (copy_done >= n_samples[copy_file])
+                {
+                    ++copy_file;
+                    copy_done = 0;
+                }
+                else
+                    break;
+            }
+            if (issued || wi == 0)
+            {
+                CUDA_TRY(cudaEventRecord(ev_copy, c->copy));
+                CUDA_TRY(cudaStreamWaitEvent(cs, ev_copy, 0));
+            }
+        }
+        {
+            LaunchScope ls(c, GLC_K_MDCT_EXACT, cs);
+            MdctLaunch m{};
+            m.pcm_arena = d_arena;
+            m.files = d_files;
+            m.n_files = n_files;
+            m.row_begin = w.r0;
+            m.row_end = w.r1;
+            m.tab_tiled = c->d_tab_mdct;
+            m.window = c->d_window;
+            m.norm = c->host.norm;
+            m.coefs = d_coefs - w.r0 * kHop; // kernels index coefficients by absolute row
+            m.variant = c->gemm_variant;
+            CUDA_TRY(launch_mdct_exact(m, cs));
+        }
+        {
+            LaunchScope ls(c, GLC_K_QUANT_PACK, cs);
+            QuantPackLaunch q{};
+            q.coefs = d_coefs - w.r0 * kHop;
+            q.files = d_files;
+            q.n_files = n_files;
+            q.frame_begin = w.f0;
+            q.frame_end = w.f1;
+            q.perc = enc->d_perc;
+            q.slots = d_slots;
+            q.nnz = de->d_nnz;
+            q.scales = de->d_scales;
+            q.is_raw = de->d_is_raw;
+            q.raw_len = d_raw_len;
+            CUDA_TRY(launch_quant_pack(q, cs));
+        }
+    }
+    if (ev_copy)
+        c->ev_free.push_back(ev_copy);
+
+    {
+        LaunchScope ls(c, GLC_K_SCAN, cs, 2);
+        CUDA_TRY(launch_scan_u32_u64(de->d_nnz, de->d_pair_off, tot_rows, cs));
+        CUDA_TRY(launch_scan_u32_u64(d_raw_len, de->d_raw_off, tot_frames, cs));
+    }
+    uint64_t totals[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(&totals[0], de->d_pair_off + tot_rows, 8, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync(&totals[1], de->d_raw_off + tot_frames, 8, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    c->stats.d2h_bytes += 16;
+    de->n_pairs = totals[0];
+    de->n_raw = totals[1];
+    CUDA_TRY(dmalloc(&de->d_pairs, de->n_pairs, cs));
+    CUDA_TRY(dmalloc(&de->d_raw, de->n_raw, cs));
+    {
+        LaunchScope ls(c, GLC_K_GATHER, cs, 2);
+        GatherLaunch g{};
+        g.slots = d_slots;
+        g.nnz = de->d_nnz;
+        g.pair_off = de->d_pair_off;
+        g.pairs = de->d_pairs;
+        g.is_raw = de->d_is_raw;
+        g.raw_off = de->d_raw_off;
+        g.raw = de->d_raw;
+        g.pcm_arena = d_arena;
+        g.files = d_files;
+        g.n_files = n_files;
+        g.window = c->d_window;
+        g.n_rows = tot_rows;
+        g.n_frames_total = tot_frames;
+        CUDA_TRY(launch_gather(g, cs));
+    }
+    dfree(d_slots, cs);
+    dfree(d_raw_len, cs);
+    dfree(d_coefs, cs);
+    dfree(d_files, cs);
+    *out = de;
+    return GLC_OK;
+}
+
+static void block_unref(EncodedBlock *b)
+{
+    if (--b->refs > 0)
+        return;
+    for (void *p : b->pinned)
+        b->ctx->pool.release(p);
+    for (void *p : b->heap)
+        free(p);
+    delete b;
+}
+
+extern "C" void glc_encoded_free(glc_ctx *c, glc_encoded *e)
+{
+    (void)c;
+    if (!e)
+        return;
+    EncodedBox *box = reinterpret_cast<EncodedBox *>(e);
+    block_unref(box->blk);
+    delete box;
+}
+
+static glc_status download_encoded(const glc_dev_encoded *de, glc_encoded **out /* [n_files] */)
+{
+    glc_ctx *c = de->ctx;
+    cudaStream_t cs = c->compute;
+    const uint64_t R = de->n_rows, F = de->n_frames;
+    EncodedBlock *blk = new EncodedBlock();
+    blk->ctx = c;
+    blk->refs = 0;
+    auto pin = [&](size_t bytes) -> void * {
+        void *p = c->pool.alloc(bytes);
+        if (p)
+            blk->pinned.push_back(p);
+        return p;
+    };
+    uint8_t *h_is_raw = (uint8_t *)pin(F);
+    uint32_t *h_nnz = (uint32_t *)pin(R * 4);
+    uint64_t *h_pair_off = (uint64_t *)pin((R + 1) * 8);
+    glc_pair *h_pairs = (glc_pair *)pin(de->n_pairs * 4);
+    float *h_scales = (float *)pin(R * 4);
+    uint64_t *h_raw_off = (uint64_t *)pin((F + 1) * 8);
+    int16_t *h_raw = (int16_t *)pin(de->n_raw * 2);
+    if (!h_is_raw || !h_nnz || !h_pair_off || !h_pairs || !h_scales || !h_raw_off || !h_raw)
+    {
+        blk->refs = 1;
+        block_unref(blk);
+        return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_is_raw, de->d_is_raw, F, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync(h_nnz, de->d_nnz, R * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync(h_pair_off, de->d_pair_off, (R + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync(h_scales, de->d_scales, R * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync(h_raw_off, de->d_raw_off, (F + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    if (de->n_pairs)
+        CUDA_TRY(cudaMemcpyAsync(h_pairs, de->d_pairs, de->n_pairs * 4, cudaMemcpyDeviceToHost, cs));
+    if (de->n_raw)
+        CUDA_TRY(cudaMemcpyAsync(h_raw, de->d_raw, de->n_raw * 2, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    c->stats.d2h_bytes += F + R * 4 + (R + 1) * 8 + R * 4 + (F + 1) * 8 + de->n_pairs * 4 + de->n_raw * 2;
+
+    const size_t nf = de->files.size();
+    for (size_t i = 0; i < nf; ++i)
+    {
+        const FileDesc &fd = de->files[i];
+        EncodedBox *box = new EncodedBox();
+        box->blk = blk;
+        blk->refs++;
+        glc_encoded &e = box->pub;
+        memset(&e, 0, sizeof e);
+        const uint64_t rows = (uint64_t)fd.n_frames * fd.channels;
+        e.sample_rate = de->sample_rate;
+        e.channels = (uint16_t)fd.channels;
+        e.total_samples = fd.len * fd.channels;
+        e.encoder_delay = kHop / 2;                                   // src/codec.rs:547
+        e.padding = (uint32_t)(padded_len(fd.len) - fd.len - kHop / 2); // :546
+        e.original_length = e.total_samples;                          // :562
+        e.n_frames = fd.n_frames;
+        e.frame_is_raw = h_is_raw + fd.first_frame;
+        e.nnz = h_nnz + fd.first_row;
+        e.scales = h_scales + fd.first_row;
+        e.pairs = h_pairs + h_pair_off[fd.first_row];
+        e.raw = h_raw + h_raw_off[fd.first_frame];
+        if (nf == 1)
+        {
+            e.pair_offset = h_pair_off;
+            e.raw_offset = h_raw_off;
+        }
+        else
+        {
+            // rebase the exclusive scans so that each file's offsets start at 0
+            uint64_t *po = (uint64_t *)malloc((rows + 1) * 8);
+            uint64_t *ro = (uint64_t *)malloc(((uint64_t)fd.n_frames + 1) * 8);
+            if (!po || !ro)
+                return fail(GLC_ERR_NO_MEMORY, "out of host memory");
+            blk->heap.push_back(po);
+            blk->heap.push_back(ro);
+            const uint64_t pb = h_pair_off[fd.first_row], rb = h_raw_off[fd.first_frame];
+            for (uint64_t r = 0; r <= rows; ++r)
+                po[r] = h_pair_off[fd.first_row + r] - pb;
+            for (uint64_t f = 0; f <= fd.n_frames; ++f)
+                ro[f] = h_raw_off[fd.first_frame + f] - rb;
+            e.pair_offset = po;
+            e.raw_offset = ro;
+        }
+        out[i] = &box->pub;
+    }
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_encode_batch(glc_encoder *enc, uint32_t n_files, const float *const *pcm,
+                                       const uint64_t *n_samples, const uint16_t *channels, glc_encoded **out)
+{
+    if (!enc || !pcm || !n_samples || !channels || !out || n_files == 0)
+        return fail(GLC_ERR_INVALID_ARG, "null/empty argument");
+    glc_ctx *c = enc->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<FileDesc> files;
+    uint64_t rows, frames, tot_pcm;
+    GLC_TRY(build_file_table(n_files, n_samples, channels, files, &rows, &frames, &tot_pcm));
+    for (uint32_t i = 0; i < n_files; ++i)
+        if (!pcm[i])
+            return fail(GLC_ERR_INVALID_ARG, "file %u: pcm is null", i);
+    float *d_arena = nullptr;
+    CUDA_TRY(dmalloc(&d_arena, tot_pcm, c->copy));
+    glc_dev_encoded *de = nullptr;
+    glc_status st = encode_core(enc, files, rows, frames, d_arena, pcm, n_samples, &de);
+    if (st == GLC_OK)
+        st = download_encoded(de, out);
+    if (de)
+        glc_dev_encoded_free(de);
+    cudaStreamSynchronize(c->compute);
+    dfree(d_arena, c->copy);
+    return st;
+}
+
+extern "C" glc_status glc_encode(glc_encoder *enc, const float *pcm, uint64_t n_samples, uint16_t channels,
+                                 glc_encoded **out)
+{
+    if (!out)
+        return fail(GLC_ERR_INVALID_ARG, "out is null");
+    const float *files[1] = {pcm};
+    return glc_encode_batch(enc, 1, files, &n_samples, &channels, out);
+}
+
+extern "C" glc_status glc_dev_upload(glc_ctx *c, const float *pcm, uint64_t n_samples, uint16_t channels,
+                                     glc_dev_pcm **out)
+{
+    if (!c || !pcm || !out || channels == 0)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    glc_dev_pcm *p = new glc_dev_pcm();
+    p->ctx = c;
+    p->n = n_samples;
+    p->trim_off = 0;
+    p->n_alloc = n_samples;
+    p->channels = channels;
+    CUDA_TRY(dmalloc(&p->d, n_samples, c->compute));
+    CUDA_TRY(cudaMemcpyAsync(p->d, pcm, n_samples * sizeof(float), cudaMemcpyHostToDevice, c->compute));
+    CUDA_TRY(cudaStreamSynchronize(c->compute));
+    c->stats.h2d_bytes += n_samples * sizeof(float);
+    *out = p;
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_dev_encode(glc_encoder *enc, const glc_dev_pcm *pcm, glc_dev_encoded **out)
+{
+    if (!enc || !pcm || !out)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    glc_ctx *c = enc->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<FileDesc> files;
+    uint64_t rows, frames, tot_pcm;
+    const uint64_t n = pcm->n;
+    const uint16_t ch = pcm->channels;
+    GLC_TRY(build_file_table(1, &n, &ch, files, &rows, &frames, &tot_pcm));
+    return encode_core(enc, files, rows, frames, pcm->d + pcm->trim_off, nullptr, nullptr, out);
+}
+
+extern "C" glc_status glc_dev_encoded_download(const glc_dev_encoded *de, glc_encoded **out)
+{
+    if (!de || !out)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(de->ctx->device));
+    return download_encoded(de, out);
+}
+
+// ------------------------------------------------------------------ decoder
+
+extern "C" glc_status glc_decoder_new(glc_ctx *c, uint32_t channels, uint32_t sample_rate, glc_decoder **out)
+{
+    if (!c || !out)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    glc_decoder *d = new glc_decoder();
+    d->ctx = c;
+    d->channels = channels;
+    d->sample_rate = sample_rate;
+    *out = d;
+    return GLC_OK;
+}
+
+extern "C" void glc_decoder_free(glc_decoder *d) { delete d; }
+
+static glc_status validate_encoded(const glc_encoded *e, uint32_t idx)
+{
+    if (!e)
+        return fail(GLC_ERR_INVALID_ARG, "stream %u is null", idx);
+    if (e->channels == 0)
+        return fail(GLC_ERR_CORRUPT, "stream %u: 0 channels", idx);
+    if (e->n_frames && (!e->frame_is_raw || !e->nnz || !e->pair_offset || !e->scales || !e->raw_offset))
+        return fail(GLC_ERR_CORRUPT, "stream %u: missing arrays", idx);
+    return GLC_OK;
+}
+
+struct DecodeOut
+{
+    float *d_out;
+    uint64_t total_out;
+    std::vector<DecFileDesc> files;
+};
+
+// Device part of a batched decode.  The stream arrays are already on the device.
+static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files, uint64_t tot_rows,
+                              uint64_t tot_frames, uint64_t total_out, const uint8_t *d_is_raw,
+                              const uint64_t *d_pair_off, const glc_pair *d_pairs, const float *d_scales,
+                              const uint64_t *d_raw_off, const int16_t *d_raw, float **d_out_ret)
+{
+    cudaStream_t cs = c->compute;
+    const uint32_t n_files = (uint32_t)files.size();
+    DecFileDesc *d_files = nullptr;
+    float *d_coefs = nullptr, *d_blocks = nullptr, *d_out = nullptr;
+    uint32_t *d_mask = nullptr;
+    const uint64_t n_tiles = (tot_rows + kBM - 1) / kBM;
+    CUDA_TRY(dmalloc(&d_files, n_files, cs));
+    CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(DecFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
+    c->stats.h2d_bytes += sizeof(DecFileDesc) * n_files;
+    CUDA_TRY(dmalloc(&d_coefs, tot_rows * kHop, cs));
+    CUDA_TRY(dmalloc(&d_blocks, tot_rows * kFrame, cs));
+    CUDA_TRY(dmalloc(&d_mask, n_tiles, cs));
+    CUDA_TRY(dmalloc(&d_out, total_out, cs));
+    CUDA_TRY(cudaMemsetAsync(d_mask, 0, std::max<uint64_t>(n_tiles, 1) * 4, cs));
+    {
+        LaunchScope ls(c, GLC_K_DEQUANT, cs);
+        DequantLaunch q{};
+        q.pairs = d_pairs;
+        q.pair_off = d_pair_off;
+        q.scales = d_scales;
+        q.n_rows = tot_rows;
+        q.coefs = d_coefs;
+        q.stage_mask = d_mask;
+        CUDA_TRY(launch_dequant(q, cs));
+    }
+    {
+        LaunchScope ls(c, GLC_K_IMDCT_EXACT, cs);
+        ImdctLaunch m{};
+        m.coefs = d_coefs;
+        m.stage_mask = d_mask;
+        m.row_begin = 0;
+        m.row_end = tot_rows;
+        m.tab_tiled = c->d_tab_imdct;
+        m.window = c->d_window;
+        m.norm = c->host.norm;
+        m.blocks = d_blocks;
+        m.variant = c->gemm_variant;
+        CUDA_TRY(launch_imdct_exact(m, cs));
+    }
+    {
+        LaunchScope ls(c, GLC_K_OLA, cs);
+        OlaLaunch o{};
+        o.blocks = d_blocks;
+        o.is_raw = d_is_raw;
+        o.raw_off = d_raw_off;
+        o.raw = d_raw;
+        o.files = d_files;
+        o.n_files = n_files;
+        o.total_out = total_out;
+        o.out = d_out;
+        CUDA_TRY(launch_ola(o, cs));
+    }
+    dfree(d_coefs, cs);
+    dfree(d_blocks, cs);
+    dfree(d_mask, cs);
+    dfree(d_files, cs);
+    (void)tot_frames;
+    *d_out_ret = d_out;
+    return GLC_OK;
+}
+
+// Trim rule of Decoder::decode, src/codec.rs:755-765
+static void trim_window(uint64_t untrimmed, uint32_t delay, uint64_t original_length, uint64_t *off, uint64_t *len)
+{
+    uint64_t o = 0, n = untrimmed;
+    if (n > delay)
+    {
+        o = delay;
+        n -= delay;
+    }
+    if (n > original_length)
+        n = original_length;
+    *off = o;
+    *len = n;
+}
+
+static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc, bool trim,
+                                    float **pcm, uint64_t *n_out)
+{
+    if (!dec || !enc || !pcm || !n_out || n_files == 0)
+        return fail(GLC_ERR_INVALID_ARG, "null/empty argument");
+    glc_ctx *c = dec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t cs = c->compute;
+    std::vector<DecFileDesc> files(n_files);
+    uint64_t rows = 0, frames = 0, outv = 0, npairs = 0, nraw = 0;
+    for (uint32_t i = 0; i < n_files; ++i)
+    {
+        GLC_TRY(validate_encoded(enc[i], i));
+        const glc_encoded *e = enc[i];
+        DecFileDesc &f = files[i];
+        f.first_row = rows;
+        f.first_frame = frames;
+        f.out_off = outv;
+        f.n_frames = e->n_frames;
+        f.channels = e->channels;
+        f.pad = 0;
+        const uint64_t r = e->n_frames * e->channels;
+        rows += r;
+        frames += e->n_frames;
+        outv += (e->n_frames + 1) * kHop * e->channels;
+        npairs += e->n_frames ? e->pair_offset[r] : 0;
+        nraw += e->n_frames ? e->raw_offset[e->n_frames] : 0;
+    }
+    // ---- stage the streams: concatenate into pinned buffers, then one H2D each ----
+    uint8_t *h_is_raw = (uint8_t *)c->pool.alloc(frames);
+    uint64_t *h_pair_off = (uint64_t *)c->pool.alloc((rows + 1) * 8);
+    float *h_scales = (float *)c->pool.alloc(rows * 4);
+    uint64_t *h_raw_off = (uint64_t *)c->pool.alloc((frames + 1) * 8);
+    if (!h_is_raw || !h_pair_off || !h_scales || !h_raw_off)
+        return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+    uint8_t *d_is_raw = nullptr;
+    uint64_t *d_pair_off = nullptr, *d_raw_off = nullptr;
+    glc_pair *d_pairs = nullptr;
+    float *d_scales = nullptr;
+    int16_t *d_raw = nullptr;
+    CUDA_TRY(dmalloc(&d_is_raw, frames, cs));
+    CUDA_TRY(dmalloc(&d_pair_off, rows + 1, cs));
+    CUDA_TRY(dmalloc(&d_scales, rows, cs));
+    CUDA_TRY(dmalloc(&d_raw_off, frames + 1, cs));
+    CUDA_TRY(dmalloc(&d_pairs, npairs, cs));
+    CUDA_TRY(dmalloc(&d_raw, nraw, cs));
+    {
+        uint64_t pb = 0, rb = 0;
+        for (uint32_t i = 0; i < n_files; ++i)
+        {
+            const glc_encoded *e = enc[i];
+            const DecFileDesc &f = files[i];
+            const uint64_t r = e->n_frames * e->channels;
+            if (e->n_frames == 0)
+                continue;
+            memcpy(h_is_raw + f.first_frame, e->frame_is_raw, e->n_frames);
+            memcpy(h_scales + f.first_row, e->scales, r * 4);
+            for (uint64_t k = 0; k < r; ++k)
+            {
+                // nnz is authoritative for the per-row count (pair_offset may come from a foreign producer)
+                h_pair_off[f.first_row + k] = pb + e->pair_offset[k];
+                if (e->pair_offset[k + 1] < e->pair_offset[k] ||
+                    e->pair_offset[k + 1] - e->pair_offset[k] != e->nnz[k])
+                    return fail(GLC_ERR_CORRUPT, "stream %u: pair_offset/nnz mismatch at row %llu", i,
+                                (unsigned long long)k);
+            }
+            for (uint64_t k = 0; k < e->n_frames; ++k)
+            {
+                h_raw_off[f.first_frame + k] = rb + e->raw_offset[k];
+                if (e->raw_offset[k + 1] < e->raw_offset[k])
+                    return fail(GLC_ERR_CORRUPT, "stream %u: raw_offset not monotone", i);
+                const uint64_t rl = e->raw_offset[k + 1] - e->raw_offset[k];
+                if ((e->frame_is_raw[k] != 0) != (rl != 0))
+                    return fail(GLC_ERR_CORRUPT, "stream %u: frame %llu raw flag/length mismatch", i,
+                                (unsigned long long)k);
+            }
+            const uint64_t np = e->pair_offset[r], nr = e->raw_offset[e->n_frames];
+            // payloads go straight from the caller's arrays (pinned when they came from glc_encode)
+            if (np)
+                CUDA_TRY(cudaMemcpyAsync(d_pairs + pb, e->pairs, np * 4, cudaMemcpyHostToDevice, cs));
+            if (nr)
+                CUDA_TRY(cudaMemcpyAsync(d_raw + rb, e->raw, nr * 2, cudaMemcpyHostToDevice, cs));
+            pb += np;
+            rb += nr;
+        }
+        h_pair_off[rows] = pb;
+        h_raw_off[frames] = rb;
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_is_raw, h_is_raw, frames, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpyAsync(d_pair_off, h_pair_off, (rows + 1) * 8, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpyAsync(d_scales, h_scales, rows * 4, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpyAsync(d_raw_off, h_raw_off, (frames + 1) * 8, cudaMemcpyHostToDevice, cs));
+    c->stats.h2d_bytes += frames + (rows + 1) * 8 + rows * 4 + (frames + 1) * 8 + npairs * 4 + nraw * 2;
+
+    float *d_out = nullptr;
+    glc_status st = decode_core(c, files, rows, frames, outv, d_is_raw, d_pair_off, d_pairs, d_scales, d_raw_off,
+                                d_raw, &d_out);
+    if (st == GLC_OK)
+    {
+        // D2H with the gapless trim folded into the copy window
+        for (uint32_t i = 0; i < n_files && st == GLC_OK; ++i)
+        {
+            const glc_encoded *e = enc[i];
+            const uint64_t untrimmed = (e->n_frames + 1) * kHop * e->channels;
+            uint64_t off = 0, len = untrimmed;
+            if (trim)
+                trim_window(untrimmed, e->encoder_delay, e->original_length, &off, &len);
+            float *h = (float *)c->pool.alloc(len * 4);
+            if (!h)
+            {
+                st = fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+                break;
+            }
+            if (len)
+            {
+                cudaError_t ce = cudaMemcpyAsync(h, d_out + files[i].out_off + off, len * 4, cudaMemcpyDeviceToHost, cs);
+                if (ce != cudaSuccess)
+                    st = fail(GLC_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(ce));
+            }
+            c->stats.d2h_bytes += len * 4;
+            pcm[i] = h;
+            n_out[i] = len;
+        }
+    }
+    cudaError_t se = cudaStreamSynchronize(cs);
+    if (st == GLC_OK && se != cudaSuccess)
+        st = fail(GLC_ERR_CUDA, "decode failed: %s", cudaGetErrorString(se));
+    c->pool.release(h_is_raw);
+    c->pool.release(h_pair_off);
+    c->pool.release(h_scales);
+    c->pool.release(h_raw_off);
+    dfree(d_out, cs);
+    dfree(d_is_raw, cs);
+    dfree(d_pair_off, cs);
+    dfree(d_scales, cs);
+    dfree(d_raw_off, cs);
+    dfree(d_pairs, cs);
+    dfree(d_raw, cs);
+    return st;
+}
+
+extern "C" glc_status glc_decode_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
+                                       float **pcm, uint64_t *n_samples)
+{
+    return decode_batch_impl(dec, n_files, enc, true, pcm, n_samples);
+}
+
+extern "C" glc_status glc_decode(glc_decoder *dec, const glc_encoded *enc, float **pcm, uint64_t *n_samples)
+{
+    return decode_batch_impl(dec, 1, &enc, true, pcm, n_samples);
+}
+
+extern "C" glc_status glc_decode_untrimmed(glc_decoder *dec, const glc_encoded *enc, float **pcm,
+                                           uint64_t *n_samples)
+{
+    return decode_batch_impl(dec, 1, &enc, false, pcm, n_samples);
+}
+
+extern "C" glc_status glc_dev_decode(glc_decoder *dec, const glc_dev_encoded *de, glc_dev_pcm **out)
+{
+    if (!dec || !de || !out)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    if (de->files.size() != 1)
+        return fail(GLC_ERR_UNSUPPORTED, "glc_dev_decode handles single-stream objects");
+    glc_ctx *c = dec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const FileDesc &fd = de->files[0];
+    std::vector<DecFileDesc> files(1);
+    files[0].first_row = 0;
+    files[0].first_frame = 0;
+    files[0].out_off = 0;
+    files[0].n_frames = fd.n_frames;
+    files[0].channels = fd.channels;
+    files[0].pad = 0;
+    const uint64_t untrimmed = ((uint64_t)fd.n_frames + 1) * kHop * fd.channels;
+    float *d_out = nullptr;
+    GLC_TRY(decode_core(c, files, de->n_rows, de->n_frames, untrimmed, de->d_is_raw, de->d_pair_off, de->d_pairs,
+                        de->d_scales, de->d_raw_off, de->d_raw, &d_out));
+    glc_dev_pcm *p = new glc_dev_pcm();
+    p->ctx = c;
+    p->d = d_out;
+    p->n_alloc = untrimmed;
+    p->channels = (uint16_t)fd.channels;
+    trim_window(untrimmed, kHop / 2, fd.len * fd.channels, &p->trim_off, &p->n);
+    *out = p;
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_dev_pcm_download(const glc_dev_pcm *p, float **pcm, uint64_t *n_samples)
+{
+    if (!p || !pcm || !n_samples)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    glc_ctx *c = p->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    float *h = (float *)c->pool.alloc(p->n * 4);
+    if (!h)
+        return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+    CUDA_TRY(cudaMemcpyAsync(h, p->d + p->trim_off, p->n * 4, cudaMemcpyDeviceToHost, c->compute));
+    CUDA_TRY(cudaStreamSynchronize(c->compute));
+    c->stats.d2h_bytes += p->n * 4;
+    *pcm = h;
+    *n_samples = p->n;
+    return GLC_OK;
+}
+
+// ------------------------------------------------------- streaming decode
+
+struct glc_stream
+{
+    glc_ctx *ctx;
+    float *all;       // untrimmed decode, pinned
+    uint64_t n_all;
+    uint64_t n_frames;
+    uint32_t channels;
+    uint64_t next_frame; // frames already handed out
+    bool finished;
+};
+
+extern "C" glc_status glc_decode_stream_open(glc_decoder *dec, const glc_encoded *enc, glc_stream **out)
+{
+    if (!dec || !enc || !out)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    float *all = nullptr;
+    uint64_t n = 0;
+    GLC_TRY(glc_decode_untrimmed(dec, enc, &all, &n));
+    glc_stream *s = new glc_stream();
+    s->ctx = dec->ctx;
+    s->all = all;
+    s->n_all = n;
+    s->n_frames = enc->n_frames;
+    s->channels = enc->channels;
+    s->next_frame = 0;
+    s->finished = false;
+    *out = s;
+    return GLC_OK;
+}
+
+extern "C" glc_status glc_decode_stream_next(glc_stream *s, const float **samples, uint64_t *n_samples,
+                                             int *is_last, float *progress_percent)
+{
+    if (!s || !samples || !n_samples || !is_last)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    if (s->finished)
+        return fail(GLC_ERR_INVALID_ARG, "stream already delivered its last chunk");
+    const uint64_t per_frame = (uint64_t)kHop * s->channels;
+    const uint64_t remaining = s->n_frames - s->next_frame;
+    *samples = s->all + s->next_frame * per_frame;
+    if (remaining >= GLC_FRAMES_PER_CHUNK)
+    {
+        // a full chunk is flushed as soon as 500 frames are buffered (src/codec.rs:708-717);
+        // `idx` there is the index of the frame that completed the chunk
+        *n_samples = GLC_FRAMES_PER_CHUNK * per_frame;
+        *is_last = 0;
+        const uint64_t idx = s->next_frame + GLC_FRAMES_PER_CHUNK - 1;
+        if (progress_percent)
+            *progress_percent = (float)idx / (float)s->n_frames * 100.0f;
+        s->next_frame += GLC_FRAMES_PER_CHUNK;
+    }
+    else
+    {
+        *n_samples = (remaining + 1) * per_frame; // leftover frames + final overlap (:723-732)
+        *is_last = 1;
+        if (progress_percent)
+            *progress_percent = -1.0f;
+        s->next_frame = s->n_frames;
+        s->finished = true;
+    }
+    return GLC_OK;
+}
+
+extern "C" void glc_decode_stream_close(glc_stream *s)
+{
+    if (!s)
+        return;
+    glc_free(s->ctx, s->all);
+    delete s;
+}

@@ -1,0 +1,234 @@
+// glc_internal.cuh -- internal declarations shared by the translation units of libglc_b200.so.
+// Nothing here is part of the ABI (include/glc.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "glc.h"
+
+namespace glc
+{
+
+constexpr int kFrame = 2048; // FRAME_SIZE, reference src/codec.rs:15
+constexpr int kHop = 1024;   // HOP_SIZE,   reference src/codec.rs:16
+constexpr int kMaxBands = 64;
+
+// ---- tiling of the EXACT transform kernels ----
+constexpr int kBM = 128;     // frame-channels (rows) per CTA tile
+constexpr int kBN = 128;     // outputs per CTA tile (coefficients for MDCT, samples for IMDCT)
+constexpr int kKC = 32;      // reduction steps per pipeline stage
+constexpr int kGemmThreads = 256;
+
+// One input file inside a batched encode (device copy lives in FileTable::d_files).
+struct FileDesc
+{
+    uint64_t pcm_off;   // offset (floats) of the file's first interleaved sample in the PCM arena
+    uint64_t len;       // samples per channel (L)
+    uint64_t first_row; // first frame-channel row of this file in the batch
+    uint64_t first_frame; // first frame index of this file in the batch-wide frame numbering
+    uint32_t channels;
+    uint32_t n_frames;
+};
+
+// Host-built constant tables (reference: MdctTables::new src/codec.rs:326-356 and
+// PerceptualWeights::new :102-183).  Built with the host libm, never on the device.
+struct HostTables
+{
+    float *cos_tab; // [1024][2048] reference layout tab[k*2048 + i]
+    float window[kFrame];
+    float norm;
+    float noise_floor_factor; // powf(10, -48/20)
+};
+
+struct HostPerceptual
+{
+    float inv_w[kHop];        // 1 / max(w[k], 0.1)            src/codec.rs:228
+    int32_t band_edges[kMaxBands];
+    int32_t n_edges;
+    float band_pf[kMaxBands]; // 1 / max(avg_weight, 0.1)      src/codec.rs:218-222
+    float band_cnt[kMaxBands];
+    float cf;                 // max(1 - 0.7, 0.01)            src/codec.rs:221
+};
+
+void build_host_tables(HostTables *t);
+void free_host_tables(HostTables *t);
+void build_host_perceptual(uint32_t sample_rate, HostPerceptual *p);
+// Re-tile the cosine table for the two transform kernels: [n_block][stage][kKC][kBN]
+void tile_table_for_mdct(const float *cos_tab, float *out);  // rows = i (2048), cols = k (1024)
+void tile_table_for_imdct(const float *cos_tab, float *out); // rows = k (1024), cols = i (2048)
+
+// Device-side perceptual model, passed by value-pointer to the quantize/pack kernel.
+struct DevPerceptual
+{
+    float inv_w[kHop];
+    int32_t band_edges[kMaxBands];
+    float band_pf[kMaxBands];
+    float band_cnt[kMaxBands];
+    uint8_t band_of[kHop];    // band index of every bin
+    int32_t n_edges;
+    float cf;
+    float noise_floor_factor;
+    float pad;
+};
+
+// ---- kernel launchers (each returns the launch error) ----
+struct MdctLaunch
+{
+    const float *pcm_arena;
+    const FileDesc *files;
+    uint32_t n_files;
+    uint64_t row_begin, row_end; // rows (frame-channels) of the batch handled by this launch
+    const float *tab_tiled;
+    const float *window;
+    float norm;
+    float *coefs; // [n_rows][1024], indexed by absolute row
+    int variant;  // 0 scalar FMUL/FADD, 1/2 packed f32x2
+};
+cudaError_t launch_mdct_exact(const MdctLaunch &p, cudaStream_t s);
+
+struct ImdctLaunch
+{
+    const float *coefs;        // dense [n_rows][1024]
+    const uint32_t *stage_mask;// [ceil(n_rows/kBM)] bit s set = some row has a non-zero in k-chunk s
+    uint64_t row_begin, row_end; // row_begin must be a multiple of kBM
+    const float *tab_tiled;
+    const float *window;
+    float norm;
+    float *blocks; // [n_rows][2048] windowed IMDCT output
+    int variant;
+};
+cudaError_t launch_imdct_exact(const ImdctLaunch &p, cudaStream_t s);
+
+struct QuantPackLaunch
+{
+    const float *coefs; // [n_rows][1024]
+    const FileDesc *files;
+    uint32_t n_files;
+    uint64_t frame_begin, frame_end; // batch-wide frame range handled by this launch
+    const DevPerceptual *perc;
+    glc_pair *slots;    // [n_rows][1024]
+    uint32_t *nnz;      // [n_rows]
+    float *scales;      // [n_rows]
+    uint8_t *is_raw;    // [n_frames_total]
+    uint32_t *raw_len;  // [n_frames_total] 0 or 2048*ch
+};
+cudaError_t launch_quant_pack(const QuantPackLaunch &p, cudaStream_t s);
+
+// exclusive scans: u32 -> u64, n+1 outputs
+cudaError_t launch_scan_u32_u64(const uint32_t *in, uint64_t *out, uint64_t n, cudaStream_t s);
+
+struct GatherLaunch
+{
+    const glc_pair *slots;
+    const uint32_t *nnz;
+    const uint64_t *pair_off;
+    glc_pair *pairs;
+    const uint8_t *is_raw;
+    const uint64_t *raw_off;
+    int16_t *raw;
+    const float *pcm_arena;
+    const FileDesc *files;
+    uint32_t n_files;
+    const float *window;
+    uint64_t n_rows;
+    uint64_t n_frames_total;
+};
+cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s);
+
+struct DequantLaunch
+{
+    const glc_pair *pairs;
+    const uint64_t *pair_off; // [n_rows+1]
+    const float *scales;
+    uint64_t n_rows;
+    float *coefs;         // [n_rows][1024], zero-filled here
+    uint32_t *stage_mask; // [ceil(n_rows/kBM)], zero-filled by caller
+};
+cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s);
+
+// One encoded stream inside a batched decode.
+struct DecFileDesc
+{
+    uint64_t first_row;   // first frame-channel row in the batch
+    uint64_t first_frame; // first frame in the batch-wide numbering
+    uint64_t out_off;     // offset (floats) of this file's untrimmed PCM in the output arena
+    uint64_t n_frames;
+    uint32_t channels;
+    uint32_t pad;
+};
+
+struct OlaLaunch
+{
+    const float *blocks;      // [n_rows][2048] windowed IMDCT output
+    const uint8_t *is_raw;    // [n_frames_total]
+    const uint64_t *raw_off;  // [n_frames_total+1]
+    const int16_t *raw;
+    const DecFileDesc *files;
+    uint32_t n_files;
+    uint64_t total_out;       // sum over files of (n_frames+1)*1024*ch
+    float *out;               // per file interleaved, (n_frames+1)*1024*ch values at out_off
+};
+cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s);
+
+cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s);
+cudaError_t launch_fp32_issue_bench(int packed, int iters, float *sink, int blocks, cudaStream_t s);
+
+// ---- FLAC ----
+struct FlacFileDesc
+{
+    uint64_t pcm_off;     // floats
+    uint64_t n_samples;   // interleaved count
+    uint64_t first_block; // index of this file's first block in the batch
+    uint64_t i16_off;     // offset into the i16 arena
+    uint32_t n_blocks;
+    uint32_t block_size;
+    uint32_t channels;
+    uint32_t sample_rate;
+};
+struct FlacLaunch
+{
+    const float *pcm_arena;
+    const FlacFileDesc *files;
+    uint32_t n_files;
+    uint64_t n_blocks_total;
+    int level;
+    uint32_t slot_bytes;   // capacity of one frame slot
+    uint8_t *slots;        // [n_blocks_total][slot_bytes]
+    uint32_t *frame_bytes; // [n_blocks_total]
+    int16_t *i16_arena;    // f32 -> i16 converted samples (for the host MD5)
+};
+cudaError_t launch_flac_blocks(const FlacLaunch &p, cudaStream_t s);
+cudaError_t launch_flac_gather(const uint8_t *slots, uint32_t slot_bytes, const uint32_t *frame_bytes,
+                               const uint64_t *frame_off, uint64_t n_blocks, uint8_t *out,
+                               cudaStream_t s);
+uint32_t flac_slot_bytes(uint32_t block_size, uint32_t channels);
+
+// ---- host-side plumbing shared by the API translation units ----
+glc_status set_error(glc_status st, const char *fmt, ...);
+void *pinned_alloc(glc_ctx *ctx, size_t bytes);
+void pinned_release(glc_ctx *ctx, void *p);
+int ctx_device(glc_ctx *ctx);
+cudaStream_t ctx_compute_stream(glc_ctx *ctx);
+void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n);
+void ctx_count_bytes(glc_ctx *ctx, uint64_t h2d, uint64_t d2h);
+void ctx_time_begin(glc_ctx *ctx, int kernel_id, void **token);
+void ctx_time_end(glc_ctx *ctx, void *token);
+
+// Host image of one or more encoded streams sharing allocations (ref-counted by their boxes).
+struct EncodedBlock
+{
+    glc_ctx *ctx;
+    int refs;
+    std::vector<void *> pinned;
+    std::vector<void *> heap;
+};
+struct EncodedBox
+{
+    glc_encoded pub; // must stay first: the ABI hands out &pub
+    EncodedBlock *blk;
+};
+
+} // namespace glc
