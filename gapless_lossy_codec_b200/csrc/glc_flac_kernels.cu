@@ -1,2 +1,685 @@
-// placeholder, replaced below
+// glc_flac_kernels.cu -- FLAC encoder of the reference (src/flac.rs), one CTA per FLAC block (sm_100a).
+//
+// The reference encoder is a fixed function of its input: fixed predictor
+// whose order depends only on the level (src/flac.rs:692-700), partition order from level and block
+// size (:590-608), Rice parameter floor(log2(mean|r|)) capped at 14 (:515-552), independent
+// channels, 16-bit samples.  Blocks are independent, so the path is two streaming passes:
+//
+//   pass A  "measure": f32 -> i16 (:955-958), residuals, per-partition Rice parameters, exact frame
+//           size in bytes.  Output: i16 arena, parameters, frame_bytes[].
+//   (scan of frame_bytes on the device gives every frame its final byte offset)
+//   pass B  "emit":    per-sample code lengths -> block-wide exclusive scan -> every thread writes its
+//           own contiguous run of codes into a zeroed shared-memory bit buffer (atomicOr on the
+//           words it shares with neighbours), CRC-8 of the header, parallel CRC-16 of the frame
+//           (per-thread partial CRCs combined with x^(8n) mod P multiplications), coalesced copy
+//           to the frame's final position.
+//
+// Integer work only: bit-exact against the oracle is the bar.  HBM-bound: 4 B/sample read in pass
+// A, 2 B/sample written, 2 B/sample + bitstream in pass B.
+#include <algorithm>
+
 #include "glc_internal.cuh"
+
+namespace glc
+{
+
+namespace
+{
+
+constexpr int kFlacThreads = 256;
+constexpr int kMaxParts = 64; // partition order <= 6
+
+struct BlockGeom
+{
+    uint32_t file;       // index into the file table
+    uint32_t frame_no;   // frame number inside the file
+    uint32_t bs;         // samples per channel in this block
+    uint32_t ch;
+    uint32_t rate;
+    uint64_t smp_off;    // interleaved sample offset of the block inside the file
+};
+
+__device__ __forceinline__ BlockGeom locate_block(const FlacFileDesc *files, uint32_t n_files, uint64_t b)
+{
+    uint32_t lo = 0, hi = n_files - 1;
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (files[mid].first_block <= b)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const FlacFileDesc &fd = files[lo];
+    BlockGeom g;
+    g.file = lo;
+    g.frame_no = (uint32_t)(b - fd.first_block);
+    g.ch = fd.channels;
+    g.rate = fd.sample_rate;
+    g.smp_off = (uint64_t)g.frame_no * fd.block_size * fd.channels;
+    const uint64_t remaining = fd.n_samples - g.smp_off;
+    const uint64_t per_ch = remaining / fd.channels; // src/flac.rs:1026-1027
+    g.bs = (uint32_t)(per_ch < fd.block_size ? per_ch : fd.block_size);
+    return g;
+}
+
+// src/flac.rs:692-700
+__device__ __forceinline__ int predictor_order(int level, uint32_t bs)
+{
+    if (level == 0)
+        return 0;
+    if (level == 1)
+        return bs >= 1 ? 1 : 0;
+    if (level == 2)
+        return bs >= 2 ? 2 : 0;
+    if (level <= 4)
+        return bs >= 3 ? 3 : 0;
+    return bs >= 4 ? 4 : 0;
+}
+
+// src/flac.rs:590-608
+__device__ __forceinline__ int partition_order(int level, uint32_t bs, int order)
+{
+    int tz = bs ? (__ffs(bs) - 1) : 32;
+    if (tz > 8)
+        tz = 8;
+    const int cap = level == 0 ? 0 : (level <= 2 ? 2 : (level <= 5 ? 4 : 6));
+    int po = cap < tz ? cap : tz;
+    while (po > 0)
+    {
+        const uint32_t ps = bs >> po;
+        if (ps > (uint32_t)order && ps >= 4)
+            break;
+        --po;
+    }
+    return po;
+}
+
+// (s * 32767.0).clamp(-32768.0, 32767.0) as i16          src/flac.rs:955-958
+__device__ __forceinline__ int f32_to_i16(float s)
+{
+    const float v = __fmul_rn(s, 32767.0f);
+    if (v != v)
+        return 0;
+    return __float2int_rz(fminf(fmaxf(v, -32768.0f), 32767.0f));
+}
+
+// residual of the fixed predictors, src/flac.rs:498-507 (no overflow for 16-bit input)
+__device__ __forceinline__ int residual_at(const int16_t *s, uint32_t i, int order)
+{
+    switch (order)
+    {
+    case 1:
+        return (int)s[i] - (int)s[i - 1];
+    case 2:
+        return (int)s[i] - (2 * (int)s[i - 1] - (int)s[i - 2]);
+    case 3:
+        return (int)s[i] - (3 * (int)s[i - 1] - 3 * (int)s[i - 2] + (int)s[i - 3]);
+    case 4:
+        return (int)s[i] - (4 * (int)s[i - 1] - 6 * (int)s[i - 2] + 4 * (int)s[i - 3] - (int)s[i - 4]);
+    default:
+        return (int)s[i];
+    }
+}
+
+__device__ __forceinline__ uint32_t zigzag(int r) // src/flac.rs:560-567
+{
+    return r >= 0 ? ((uint32_t)r << 1) : ((((uint32_t)(-(r + 1))) << 1) | 1u);
+}
+
+// src/flac.rs:515-552: floor(log2(mean)) capped at 14 (the "adjust" branch can never fire)
+__device__ __forceinline__ uint32_t rice_param(unsigned long long sum_abs, uint32_t n)
+{
+    if (n == 0)
+        return 0;
+    const unsigned long long mean = sum_abs / n;
+    if (mean == 0)
+        return 0;
+    const int lg = 63 - __clzll((long long)mean);
+    return lg < 14 ? (uint32_t)lg : 14u;
+}
+
+__device__ __forceinline__ uint32_t header_bytes(uint32_t bs, uint32_t frame_no)
+{
+    uint32_t n = 4;
+    n += frame_no < 0x80 ? 1 : (frame_no < 0x800 ? 2 : (frame_no < 0x10000 ? 3 : (frame_no < 0x200000 ? 4 : (frame_no < 0x4000000 ? 5 : (frame_no < 0x80000000u ? 6 : 7)))));
+    uint32_t code;
+    switch (bs)
+    {
+    case 192: case 576: case 1152: case 2304: case 4608:
+    case 256: case 512: case 1024: case 2048: case 4096: case 8192: case 16384: case 32768:
+        code = 1;
+        break;
+    default:
+        code = bs < 256 ? 6 : 7;
+        break;
+    }
+    if (code == 6)
+        n += 1;
+    else if (code == 7)
+        n += 2;
+    return n + 1; // + CRC-8
+}
+
+// loads the block's samples as planar i16 into shared memory: s[c*bs + i]
+template <bool FROM_F32>
+__device__ __forceinline__ void load_block(const FlacLaunch &p, const FlacFileDesc &fd, const BlockGeom &g,
+                                           int16_t *s_smp)
+{
+    const uint32_t n = g.bs * g.ch;
+    if (FROM_F32)
+    {
+        const float *src = p.pcm_arena + fd.pcm_off + g.smp_off;
+        int16_t *arena = p.i16_arena + fd.i16_off + g.smp_off;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x)
+        {
+            const int q = f32_to_i16(__ldg(src + e));
+            arena[e] = (int16_t)q;
+            const uint32_t i = e / g.ch, c = e - i * g.ch;
+            s_smp[c * g.bs + i] = (int16_t)q;
+        }
+    }
+    else
+    {
+        const int16_t *src = p.i16_arena + fd.i16_off + g.smp_off;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x)
+        {
+            const uint32_t i = e / g.ch, c = e - i * g.ch;
+            s_smp[c * g.bs + i] = src[e];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ pass A
+
+__global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLaunch p, uint8_t *rice_k /* [blocks][ch][64] */,
+                                                                    uint32_t max_ch)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int16_t *s_smp = reinterpret_cast<int16_t *>(smem_raw);
+    __shared__ unsigned long long s_part_bits[kMaxParts];
+    __shared__ unsigned long long s_total_bits;
+
+    const uint64_t b = blockIdx.x;
+    if (b >= p.n_blocks_total)
+        return;
+    const BlockGeom g = locate_block(p.files, p.n_files, b);
+    const FlacFileDesc &fd = p.files[g.file];
+    load_block<true>(p, fd, g, s_smp);
+    if (threadIdx.x == 0)
+        s_total_bits = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int order = predictor_order(p.level, g.bs);
+    const int po = order ? partition_order(p.level, g.bs, order) : 0;
+    const uint32_t nparts = 1u << po, dps = g.bs >> po;
+
+    for (uint32_t c = 0; c < g.ch; ++c)
+    {
+        const int16_t *s = s_smp + c * g.bs;
+        uint8_t *kout = rice_k + (b * max_ch + c) * kMaxParts;
+        if (order == 0)
+        {
+            if (threadIdx.x == 0)
+                s_total_bits += 8ull + 16ull * g.bs; // verbatim subframe, src/flac.rs:722-729
+            continue;
+        }
+        for (uint32_t part = warp; part < nparts; part += kFlacThreads / 32)
+        {
+            const uint32_t lo = part == 0 ? (uint32_t)order : part * dps;
+            const uint32_t hi = (part + 1) * dps;
+            unsigned long long sum = 0;
+            for (uint32_t i = lo + lane; i < hi; i += 32)
+            {
+                const int r = residual_at(s, i, order);
+                sum += (unsigned long long)(r < 0 ? -r : r);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const uint32_t cnt = hi - lo;
+            const uint32_t k = rice_param(sum, cnt);
+            unsigned long long bits = 0;
+            for (uint32_t i = lo + lane; i < hi; i += 32)
+                bits += (zigzag(residual_at(s, i, order)) >> k) + 1u + k;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                bits += __shfl_xor_sync(0xffffffffu, bits, o);
+            if (lane == 0)
+            {
+                s_part_bits[part] = cnt ? bits + 4ull : 0ull; // empty first partition writes nothing (:632-635)
+                kout[part] = (uint8_t)k;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned long long t = 8ull + 16ull * order + 6ull;
+            for (uint32_t part = 0; part < nparts; ++part)
+                t += s_part_bits[part];
+            s_total_bits += t;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned long long body = (s_total_bits + 7ull) >> 3;
+        p.frame_bytes[b] = (uint32_t)(header_bytes(g.bs, g.frame_no) + body + 2ull);
+    }
+}
+
+// ------------------------------------------------------------------ pass B
+
+struct BitWriter
+{
+    uint32_t *buf;
+    uint32_t wi;
+    unsigned long long acc;
+    int nacc;
+    __device__ __forceinline__ void init(uint32_t *b, unsigned long long bitpos)
+    {
+        buf = b;
+        wi = (uint32_t)(bitpos >> 5);
+        nacc = (int)(bitpos & 31);
+        acc = 0;
+    }
+    // append the low n bits of v (n <= 31), MSB first
+    __device__ __forceinline__ void put(uint32_t v, int n)
+    {
+        acc = (acc << n) | v;
+        nacc += n;
+        if (nacc >= 32)
+        {
+            atomicOr(buf + wi, (uint32_t)(acc >> (nacc - 32)));
+            ++wi;
+            nacc -= 32;
+            acc &= (1ull << nacc) - 1ull;
+        }
+    }
+    // append z zero bits (the buffer is pre-zeroed)
+    __device__ __forceinline__ void skip(uint32_t z)
+    {
+        const uint32_t total = (uint32_t)nacc + z;
+        if (total >= 32)
+        {
+            if (acc)
+                atomicOr(buf + wi, (uint32_t)(acc << (32 - nacc)));
+            wi += total >> 5;
+            nacc = (int)(total & 31);
+            acc = 0;
+        }
+        else
+        {
+            acc <<= z;
+            nacc = (int)total;
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (nacc && acc)
+            atomicOr(buf + wi, (uint32_t)(acc << (32 - nacc)));
+    }
+};
+
+__device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b) // mod x^16+x^15+x^2+1
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 15; i >= 0; --i)
+    {
+        r <<= 1;
+        if (r & 0x10000u)
+            r ^= 0x18005u;
+        if ((b >> i) & 1u)
+            r ^= a;
+    }
+    return r & 0xffffu;
+}
+
+__device__ __forceinline__ uint32_t buf_byte(const volatile uint32_t *buf, uint32_t j)
+{
+    return (buf[j >> 2] >> (24 - 8 * (j & 3))) & 0xffu;
+}
+
+__global__ void __launch_bounds__(kFlacThreads) flac_emit_kernel(const FlacLaunch p, const uint8_t *rice_k, uint32_t max_ch,
+                                                                 const uint64_t *frame_off, uint8_t *out_arena,
+                                                                 uint32_t smp_bytes, uint32_t buf_words,
+                                                                 uint32_t *g_scratch /* null = bit buffer in smem */)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int16_t *s_smp = reinterpret_cast<int16_t *>(smem_raw);
+    uint32_t *bitbuf = g_scratch ? g_scratch + (size_t)blockIdx.x * buf_words
+                                 : reinterpret_cast<uint32_t *>(smem_raw + smp_bytes);
+    __shared__ uint32_t s_scan[kFlacThreads / 32];
+    __shared__ uint16_t s_crc_tab[256];
+    __shared__ uint16_t s_xpow[32];
+    __shared__ uint32_t s_crc_part[kFlacThreads / 32];
+    __shared__ unsigned long long s_bitpos;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        // CRC-16 table (poly 0x8005, MSB first, init 0; src/flac.rs:54-80) and x^(8*2^j) mod P
+        uint32_t crc = (uint32_t)tid << 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x8005u) : (crc << 1);
+        s_crc_tab[tid] = (uint16_t)crc;
+        if (tid == 0)
+        {
+            uint32_t x = 0x0100u; // x^8
+            for (int j = 0; j < 32; ++j)
+            {
+                s_xpow[j] = (uint16_t)x;
+                x = gf16_mul(x, x);
+            }
+        }
+    }
+    __syncthreads();
+
+    for (uint64_t b = blockIdx.x; b < p.n_blocks_total; b += gridDim.x)
+    {
+        const BlockGeom g = locate_block(p.files, p.n_files, b);
+        const FlacFileDesc &fd = p.files[g.file];
+        const uint32_t fbytes = p.frame_bytes[b];
+        const uint32_t fwords = (fbytes + 3) >> 2;
+        for (uint32_t w = tid; w < fwords + 1 && w < buf_words; w += kFlacThreads)
+            bitbuf[w] = 0;
+        load_block<false>(p, fd, g, s_smp);
+        __syncthreads();
+
+        const uint32_t hbytes = header_bytes(g.bs, g.frame_no);
+        if (tid == 0)
+        {
+            // frame header, src/flac.rs:759-871
+            uint8_t h[16];
+            uint32_t n = 0;
+            h[n++] = 0xFF;
+            h[n++] = 0xF8;
+            uint32_t bsb;
+            switch (g.bs)
+            {
+            case 192: bsb = 1; break;
+            case 576: bsb = 2; break;
+            case 1152: bsb = 3; break;
+            case 2304: bsb = 4; break;
+            case 4608: bsb = 5; break;
+            case 256: bsb = 8; break;
+            case 512: bsb = 9; break;
+            case 1024: bsb = 10; break;
+            case 2048: bsb = 11; break;
+            case 4096: bsb = 12; break;
+            case 8192: bsb = 13; break;
+            case 16384: bsb = 14; break;
+            case 32768: bsb = 15; break;
+            default: bsb = g.bs < 256 ? 6 : 7; break;
+            }
+            uint32_t srb;
+            switch (g.rate)
+            {
+            case 88200: srb = 1; break;
+            case 176400: srb = 2; break;
+            case 192000: srb = 3; break;
+            case 8000: srb = 4; break;
+            case 16000: srb = 5; break;
+            case 22050: srb = 6; break;
+            case 24000: srb = 7; break;
+            case 32000: srb = 8; break;
+            case 44100: srb = 9; break;
+            case 48000: srb = 10; break;
+            case 96000: srb = 11; break;
+            default: srb = 0; break;
+            }
+            h[n++] = (uint8_t)((bsb << 4) | srb);
+            const uint32_t chb = g.ch == 1 ? 0 : (g.ch == 2 ? 1 : ((g.ch - 1) & 0xF));
+            h[n++] = (uint8_t)((chb << 4) | (4u << 1)); // 16 bits per sample -> 0b100, reserved 0
+            const uint32_t v = g.frame_no; // UTF-8 style number, src/flac.rs:427-478
+            if (v < 0x80)
+                h[n++] = (uint8_t)v;
+            else if (v < 0x800)
+            {
+                h[n++] = (uint8_t)(0xC0 | ((v >> 6) & 0x1F));
+                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+            }
+            else if (v < 0x10000)
+            {
+                h[n++] = (uint8_t)(0xE0 | ((v >> 12) & 0x0F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+            }
+            else if (v < 0x200000)
+            {
+                h[n++] = (uint8_t)(0xF0 | ((v >> 18) & 0x07));
+                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+            }
+            else if (v < 0x4000000)
+            {
+                h[n++] = (uint8_t)(0xF8 | ((v >> 24) & 0x03));
+                h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+            }
+            else if (v < 0x80000000u)
+            {
+                h[n++] = (uint8_t)(0xFC | ((v >> 30) & 0x01));
+                h[n++] = (uint8_t)(0x80 | ((v >> 24) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+            }
+            else
+            {
+                h[n++] = 0xFE;
+                h[n++] = (uint8_t)(0x80 | ((v >> 30) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 24) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+            }
+            if (bsb == 6)
+                h[n++] = (uint8_t)((g.bs - 1) & 0xFF);
+            else if (bsb == 7)
+            {
+                h[n++] = (uint8_t)(((g.bs - 1) >> 8) & 0xFF);
+                h[n++] = (uint8_t)((g.bs - 1) & 0xFF);
+            }
+            uint32_t c8 = 0; // CRC-8 poly 0x07, src/flac.rs:19-51
+            for (uint32_t j = 0; j < n; ++j)
+            {
+                c8 ^= h[j];
+                for (int i = 0; i < 8; ++i)
+                    c8 = (c8 & 0x80u) ? (((c8 << 1) ^ 0x07u) & 0xFFu) : ((c8 << 1) & 0xFFu);
+            }
+            h[n++] = (uint8_t)c8;
+            BitWriter w;
+            w.init(bitbuf, 0);
+            for (uint32_t j = 0; j < n; ++j)
+                w.put(h[j], 8);
+            w.finish();
+            s_bitpos = (unsigned long long)hbytes * 8ull;
+        }
+        __syncthreads();
+
+        const int order = predictor_order(p.level, g.bs);
+        const int po = order ? partition_order(p.level, g.bs, order) : 0;
+        const uint32_t dps = g.bs >> po;
+        const uint32_t per_thread = (g.bs + kFlacThreads - 1) / kFlacThreads;
+
+        for (uint32_t c = 0; c < g.ch; ++c)
+        {
+            const int16_t *s = s_smp + c * g.bs;
+            const uint8_t *kin = rice_k + (b * max_ch + c) * kMaxParts;
+            const unsigned long long sub0 = s_bitpos; // first bit of this subframe
+            const uint32_t lo = min(g.bs, (uint32_t)tid * per_thread);
+            const uint32_t hi = min(g.bs, lo + per_thread);
+            const uint32_t first = max(lo, (uint32_t)order);
+
+            // bits this thread will emit for the residual section (or the verbatim samples)
+            uint32_t mine = 0;
+            if (order == 0)
+                mine = (hi - lo) * 16u;
+            else
+                for (uint32_t i = first; i < hi; ++i)
+                {
+                    const uint32_t part = i / dps;
+                    const uint32_t k = kin[part];
+                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * dps;
+                    mine += (zigzag(residual_at(s, i, order)) >> k) + 1u + k + (i == pstart ? 4u : 0u);
+                }
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            if (lane == 31)
+                s_scan[warp] = incl;
+            __syncthreads();
+            uint32_t woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kFlacThreads / 32; ++w)
+            {
+                if (w < warp)
+                    woff += s_scan[w];
+                total += s_scan[w];
+            }
+            const unsigned long long fixed = 8ull + (order ? 16ull * order + 6ull : 0ull);
+            BitWriter w;
+            if (tid == 0)
+            {
+                // subframe header + warm-up + residual header, src/flac.rs:704-720, 733-736, 611-614
+                w.init(bitbuf, sub0);
+                w.put(order == 0 ? 0x02u : ((0x08u | (uint32_t)order) << 1), 8); // 0 | type(6) | 0
+                for (int i = 0; i < order; ++i)
+                    w.put((uint32_t)(uint16_t)s[i], 16);
+                if (order)
+                    w.put((uint32_t)po, 6); // method 00 + partition order
+                w.finish();
+            }
+            w.init(bitbuf, sub0 + fixed + woff + (incl - mine));
+            if (order == 0)
+                for (uint32_t i = lo; i < hi; ++i)
+                    w.put((uint32_t)(uint16_t)s[i], 16);
+            else
+                for (uint32_t i = first; i < hi; ++i)
+                {
+                    const uint32_t part = i / dps;
+                    const uint32_t k = kin[part];
+                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * dps;
+                    if (i == pstart)
+                        w.put(k, 4);
+                    const uint32_t u = zigzag(residual_at(s, i, order));
+                    w.skip(u >> k);                                // unary zeros
+                    w.put((1u << k) | (u & ((1u << k) - 1u)), (int)k + 1); // stop bit + k low bits
+                }
+            w.finish();
+            __syncthreads();
+            if (tid == 0)
+                s_bitpos = sub0 + fixed + total;
+            __syncthreads();
+        }
+
+        // ---- CRC-16 over bytes [0, nb) ----
+        const uint32_t nb = fbytes - 2;
+        {
+            const uint32_t cb = (nb + kFlacThreads - 1) / kFlacThreads;
+            const uint32_t b0 = min(nb, (uint32_t)tid * cb), b1 = min(nb, b0 + cb);
+            uint32_t crc = 0;
+            for (uint32_t j = b0; j < b1; ++j)
+                crc = ((crc << 8) & 0xffffu) ^ s_crc_tab[((crc >> 8) ^ buf_byte(bitbuf, j)) & 0xffu];
+            // append (nb - b1) zero bytes: multiply by x^(8*(nb-b1)) mod P
+            uint32_t e = nb - b1;
+            for (int j = 0; e; ++j, e >>= 1)
+                if (e & 1u)
+                    crc = gf16_mul(crc, s_xpow[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+            if (lane == 0)
+                s_crc_part[warp] = crc;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            uint32_t crc = 0;
+            for (int w = 0; w < kFlacThreads / 32; ++w)
+                crc ^= s_crc_part[w];
+            BitWriter w;
+            w.init(bitbuf, (unsigned long long)nb * 8ull);
+            w.put(crc & 0xffffu, 16);
+            w.finish();
+        }
+        __syncthreads();
+        uint8_t *dst = out_arena + frame_off[b];
+        for (uint32_t j = tid; j < fbytes; j += kFlacThreads)
+            dst[j] = (uint8_t)buf_byte(bitbuf, j);
+        __syncthreads();
+    }
+}
+
+} // namespace
+
+uint32_t flac_slot_bytes(uint32_t block_size, uint32_t channels)
+{
+    // worst case per sample with 16-bit input: k capped at 14, |r| < 2^19 -> about 79 bits
+    return 32u + channels * (block_size * 10u + 64u);
+}
+
+cudaError_t launch_flac_measure(const FlacLaunch &p, uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs, cudaStream_t s)
+{
+    if (p.n_blocks_total == 0)
+        return cudaSuccess;
+    const size_t smem = (size_t)max_bs * max_ch * sizeof(int16_t);
+    cudaError_t e = cudaFuncSetAttribute(flac_measure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    flac_measure_kernel<<<(unsigned)p.n_blocks_total, kFlacThreads, smem, s>>>(p, rice_k, max_ch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flac_emit(const FlacLaunch &p, const uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs,
+                             uint32_t max_frame_bytes, const uint64_t *frame_off, uint8_t *out_arena,
+                             uint32_t **scratch_io, int sm_count, cudaStream_t s)
+{
+    if (p.n_blocks_total == 0)
+        return cudaSuccess;
+    const uint32_t smp_bytes = (uint32_t)(((size_t)max_bs * max_ch * sizeof(int16_t) + 15) & ~(size_t)15);
+    const uint32_t buf_words = ((max_frame_bytes + 3) >> 2) + 2;
+    size_t smem = (size_t)smp_bytes + (size_t)buf_words * 4;
+    uint32_t *scratch = nullptr;
+    unsigned grid;
+    const size_t smem_limit = 200 * 1024;
+    if (smem > smem_limit)
+    {
+        // frames too large for shared memory (pathological residuals / many channels): the bit
+        // buffer moves to a per-CTA global scratch area, same code path through generic pointers
+        smem = smp_bytes;
+        grid = (unsigned)std::min<uint64_t>(p.n_blocks_total, (uint64_t)sm_count * 2);
+        cudaError_t e = cudaMallocAsync((void **)&scratch, (size_t)grid * buf_words * 4, s);
+        if (e != cudaSuccess)
+            return e;
+        *scratch_io = scratch;
+    }
+    else
+    {
+        // as many CTAs as fit; each loops over blocks with a grid stride
+        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+        grid = (unsigned)std::min<uint64_t>(p.n_blocks_total, (uint64_t)sm_count * per_sm);
+    }
+    cudaError_t e = cudaFuncSetAttribute(flac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    flac_emit_kernel<<<grid, kFlacThreads, smem, s>>>(p, rice_k, max_ch, frame_off, out_arena, smp_bytes, buf_words,
+                                                      scratch);
+    return cudaGetLastError();
+}
+
+} // namespace glc

@@ -195,15 +195,14 @@ struct FlacLaunch
     uint32_t n_files;
     uint64_t n_blocks_total;
     int level;
-    uint32_t slot_bytes;   // capacity of one frame slot
-    uint8_t *slots;        // [n_blocks_total][slot_bytes]
-    uint32_t *frame_bytes; // [n_blocks_total]
+    uint32_t *frame_bytes; // [n_blocks_total] exact size of every frame
     int16_t *i16_arena;    // f32 -> i16 converted samples (for the host MD5)
 };
-cudaError_t launch_flac_blocks(const FlacLaunch &p, cudaStream_t s);
-cudaError_t launch_flac_gather(const uint8_t *slots, uint32_t slot_bytes, const uint32_t *frame_bytes,
-                               const uint64_t *frame_off, uint64_t n_blocks, uint8_t *out,
-                               cudaStream_t s);
+cudaError_t launch_flac_measure(const FlacLaunch &p, uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs,
+                                cudaStream_t s);
+cudaError_t launch_flac_emit(const FlacLaunch &p, const uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs,
+                             uint32_t max_frame_bytes, const uint64_t *frame_off, uint8_t *out_arena,
+                             uint32_t **scratch_io, int sm_count, cudaStream_t s);
 uint32_t flac_slot_bytes(uint32_t block_size, uint32_t channels);
 
 // ---- host-side plumbing shared by the API translation units ----

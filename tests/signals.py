@@ -98,7 +98,7 @@ def multi_sine(sample_rate, channels, duration, partials=20, base=100.0, step=17
 def music_like(sample_rate, channels, duration, seed=12345):
     """Deterministic mix exercising sparse AND raw frames: multi-sine + low-passed LCG noise for
     ~70 % of each second, white LCG noise (+-0.3) for the rest."""
-    total = int(sample_rate * duration)
+    total = int(F32(sample_rate) * F32(duration))
     tones = multi_sine(sample_rate, channels, duration).reshape(total, channels)
     out = np.empty((total, channels), F32)
     for c in range(channels):

@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary (no compute calls without a GPU): the C-ABI library
+loads, exports every symbol include/glc.h declares, and fails loudly -- never falls back -- when
+there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "glc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(glc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gapless_lossy_codec_b200 import _ffi
+
+    lib = _ffi.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 40
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared in include/glc.h but not exported: {missing}"
+    assert sorted(_ffi.EXPORTS) == declared, "the ctypes binding must cover exactly the declared ABI"
+    assert lib.glc_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    from gapless_lossy_codec_b200 import _ffi
+
+    assert C.sizeof(_ffi.Pair) == 4
+    assert C.sizeof(_ffi.Encoded) == 96
+    assert _ffi.Encoded.frame_is_raw.offset == 40 and _ffi.Encoded.raw.offset == 88
+    import oracle
+
+    assert C.sizeof(oracle.Encoded) == C.sizeof(_ffi.Encoded)
+    for (n1, _), (n2, _) in zip(oracle.Encoded._fields_, _ffi.Encoded._fields_):
+        assert n1 == n2 and getattr(oracle.Encoded, n1).offset == getattr(_ffi.Encoded, n2).offset
+
+
+def _gpu_present():
+    from gapless_lossy_codec_b200 import _ffi
+
+    n = C.c_int()
+    return _ffi.load().glc_device_count(C.byref(n)) == 0
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU every product entry point must raise; nothing may route to the oracle."""
+    if _gpu_present():
+        pytest.skip("a CUDA device is present")
+    import numpy as np
+    from gapless_lossy_codec_b200 import Context, Encoder, GlcError, flac
+
+    with pytest.raises(GlcError) as e:
+        Context(0)
+    assert e.value.status == 6 and "no CPU fallback" in e.value.message
+    with pytest.raises(GlcError):
+        Encoder(44100)
+    with pytest.raises(GlcError):
+        flac.encode_flac(np.zeros(100, np.float32), 44100, 1)
+
+
+def test_product_package_never_uses_the_oracle():
+    pkg = os.path.join(ROOT, "gapless_lossy_codec_b200")
+    for dirpath, dirs, files in os.walk(pkg):
+        dirs[:] = [d for d in dirs if d not in ("build", "__pycache__")]
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for needle in ("import oracle", "from oracle", "libglc_oracle", "oracle/", "orc_"):
+                    assert needle not in text, f"{f} references the oracle ({needle})"

@@ -1,0 +1,181 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of libglc_b200.so) against the CPU
+oracle on identical inputs.  Bar: bit-exact for every integer field, for the f32 bit patterns of
+the scale factors and for the decoded PCM (EXACT transform mode reproduces the reference's
+operation order, so no tolerance is needed or allowed)."""
+import numpy as np
+import pytest
+
+import oracle
+import signals
+from parity import assert_encoded_equal, assert_pcm_bits_equal, to_oracle, to_product
+
+pytestmark = pytest.mark.gpu
+
+
+def _roundtrip_case(gpu_ctx, x, ch, sr, what):
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    ref = oracle.encode(x, ch, sr)
+    enc = Encoder(sr, gpu_ctx).encode(x, ch)
+    assert_encoded_equal(enc, ref, what)
+    dec = Decoder(ch, sr, gpu_ctx)
+    pcm_ref = oracle.decode(ref)
+    pcm = dec.decode(enc)
+    assert_pcm_bits_equal(pcm, pcm_ref, what + " decode")
+    assert len(pcm) == len(x), f"{what}: gapless length {len(pcm)} != {len(x)}"
+    un_ref = oracle.decode(ref, trimmed=False)
+    un = dec.decode_untrimmed(enc)
+    assert_pcm_bits_equal(un, un_ref, what + " untrimmed")
+    return enc, pcm
+
+
+CASES = [
+    # the reference's own cases: tests/test_simple.rs, test_codec.rs, test_comprehensive.rs
+    ("sine440_mono_2s", lambda: signals.sine(440, 44100, 1, 2.0), 1, 44100),
+    ("sine440_stereo_2s", lambda: signals.sine(440, 44100, 2, 2.0), 2, 44100),
+    ("square_mono_1s", lambda: signals.square(440, 44100, 1, 1.0), 1, 44100),
+    ("saw_mono_1s", lambda: signals.sawtooth(440, 44100, 1, 1.0), 1, 44100),
+    ("sweep_48k_stereo", lambda: signals.sweep(100, 8000, 48000, 2, 1.0), 2, 48000),
+    ("noise_stereo_raw_frames", lambda: signals.white_noise(44100, 2, 1.0, 12345), 2, 44100),
+    ("music_like_stereo", lambda: signals.music_like(44100, 2, 3.0), 2, 44100),
+    ("six_channel_48k", lambda: signals.music_like(48000, 6, 1.0, seed=1000), 6, 48000),
+    ("rate_96k_mono", lambda: signals.sine(1000, 96000, 1, 0.5), 1, 96000),
+    ("rate_8k_mono", lambda: signals.sine(300, 8000, 1, 1.0), 1, 8000),
+    ("silence", lambda: np.zeros(30000, np.float32), 1, 44100),
+    ("full_scale_clip", lambda: np.clip(signals.sine(997, 44100, 1, 0.5, amp=1.5), -1, 1), 1, 44100),
+]
+
+
+@pytest.mark.parametrize("name,gen,ch,sr", CASES, ids=[c[0] for c in CASES])
+def test_encode_decode_bit_exact(gpu_ctx, name, gen, ch, sr):
+    _roundtrip_case(gpu_ctx, gen(), ch, sr, name)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_gemm_variants_identical(gpu_ctx, variant):
+    """scalar FMUL/FADD and the two packed f32x2 forms must give the same bits."""
+    try:
+        gpu_ctx.set_tuning(variant, 0)
+        _roundtrip_case(gpu_ctx, signals.music_like(44100, 2, 1.5), 2, 44100, f"variant{variant}")
+    finally:
+        gpu_ctx.set_tuning(-1, 0)
+
+
+@pytest.mark.parametrize("n", [513, 514, 1023, 1024, 1025, 1535, 1536, 1537, 2048, 4097])
+def test_ragged_lengths(gpu_ctx, n):
+    """padding / frame-count rules, src/codec.rs:433-455"""
+    x = signals.sine(440, 44100, 1, 0.2)[:n].copy()
+    _roundtrip_case(gpu_ctx, x, 1, 44100, f"len{n}")
+
+
+def test_too_short_is_an_error(gpu_ctx):
+    from gapless_lossy_codec_b200 import Encoder, GlcError
+
+    for n in (0, 1, 512):
+        with pytest.raises(GlcError) as ei:
+            Encoder(44100, gpu_ctx).encode(np.zeros(n, np.float32), 1)
+        assert ei.value.status == 2
+    with pytest.raises(GlcError):
+        Encoder(44100, gpu_ctx).encode(np.zeros(2001, np.float32), 2)  # not a multiple of channels
+
+
+def test_stereo_header_wins_over_decoder_arg(gpu_ctx):
+    """tests/test_codec.rs:98 constructs Decoder::new(1, ..) for stereo data."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    x = signals.sine(440, 44100, 2, 1.0)
+    enc = Encoder(44100, gpu_ctx).encode(x, 2)
+    pcm = Decoder(1, 44100, gpu_ctx).decode(enc)
+    assert len(pcm) == len(x)
+    assert signals.snr_db(x, pcm) > -10.0
+
+
+def test_batch_equals_singles_and_gapless_sum(gpu_ctx):
+    """tests/test_codec.rs:140-170 (sum of decoded lengths == sum of original lengths) through the
+    batched entry points; every file of the batch must equal its single-file encode."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    files = [signals.sine(440, 44100, 1, 2.0), signals.sine(880, 44100, 1, 1.3),
+             signals.square(440, 44100, 1, 0.7), signals.music_like(44100, 2, 1.1),
+             signals.white_noise(44100, 2, 0.4, 7)]
+    chs = [1, 1, 1, 2, 2]
+    enc = Encoder(44100, gpu_ctx)
+    batch = enc.encode_batch(files, chs)
+    for i, (x, ch) in enumerate(zip(files, chs)):
+        assert_encoded_equal(batch[i], oracle.encode(x, ch, 44100), f"batch file {i}")
+    outs = Decoder(1, 44100, gpu_ctx).decode_batch(batch)
+    assert sum(len(o) for o in outs) == sum(len(f) for f in files)
+    for i, o in enumerate(outs):
+        assert_pcm_bits_equal(o, oracle.decode(to_oracle(batch[i])), f"batch decode {i}")
+
+
+def test_streaming_chunks_match_reference_shape(gpu_ctx):
+    """decode_streaming: chunks of exactly 500 frames, tail with is_last (src/codec.rs:708-732)."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    x = signals.sine(440, 44100, 1, 25.0)  # 1078 frames -> 500 + 500 + (78 + overlap)
+    enc = Encoder(44100, gpu_ctx).encode(x, 1)
+    events = []
+    chunks = list(Decoder(1, 44100, gpu_ctx).decode_streaming(enc, progress=events.append))
+    assert [c.is_last for c in chunks] == [False] * (len(chunks) - 1) + [True]
+    assert all(len(c.samples) == 500 * 1024 for c in chunks[:-1])
+    assert len(chunks[-1].samples) == (enc.n_frames % 500 + 1) * 1024
+    cat = np.concatenate([c.samples for c in chunks])
+    assert_pcm_bits_equal(cat, oracle.decode(to_oracle(enc), trimmed=False), "streaming concat")
+    kinds = [e.kind for e in events]
+    assert kinds[0] == "Status" and kinds[-1] == "Complete" and kinds.count("Decoding") == len(chunks) - 1
+    pct = [e.value for e in events if e.kind == "Decoding"]
+    assert pct[0] == pytest.approx(499 / enc.n_frames * 100, rel=1e-6)
+
+
+def test_decoder_accepts_unsorted_and_duplicate_pairs(gpu_ctx):
+    """'later duplicates overwrite' + idx >= 1024 ignored (src/codec.rs:659-665)."""
+    from gapless_lossy_codec_b200 import Decoder
+
+    ref = oracle.encode(signals.sine(440, 44100, 1, 0.3), 1, 44100)
+    rng = np.random.default_rng(5)
+    idx, q, nnz = [], [], []
+    for r in range(ref.n_frames):
+        n = int(rng.integers(0, 40))
+        ii = rng.integers(0, 1100, n).astype(np.uint16)  # duplicates and out-of-range on purpose
+        idx.append(ii)
+        q.append(rng.integers(-3000, 3000, n).astype(np.int16))
+        nnz.append(n)
+    ref.nnz = np.array(nnz, np.uint32)
+    ref.pair_offset = np.concatenate([[0], np.cumsum(nnz)]).astype(np.uint64)
+    ref.pair_idx = np.concatenate(idx) if idx else np.zeros(0, np.uint16)
+    ref.pair_q = np.concatenate(q) if q else np.zeros(0, np.int16)
+    ref.scales = rng.random(ref.n_frames).astype(np.float32)
+    pcm = Decoder(1, 44100, gpu_ctx).decode(to_product(ref))
+    assert_pcm_bits_equal(pcm, oracle.decode(ref), "hostile pairs")
+
+
+def test_bincode_container_matches_oracle_image(gpu_ctx):
+    from gapless_lossy_codec_b200 import Encoder, encoded_from_bytes, encoded_to_bytes
+
+    x = signals.music_like(44100, 2, 1.0)
+    enc = Encoder(44100, gpu_ctx).encode(x, 2)
+    blob = encoded_to_bytes(enc, gpu_ctx)
+    assert blob == oracle.bincode_serialize(to_oracle(enc))
+    back = encoded_from_bytes(blob, gpu_ctx)
+    assert_encoded_equal(back, to_oracle(enc), "bincode round trip")
+
+
+def test_large_property_roundtrip(gpu_ctx):
+    """A size the oracle would take minutes on: size-independent properties only
+    (exact gapless length, sane SNR, sparse < 50 % on tonal content, determinism)."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    x = np.tile(signals.music_like(44100, 2, 10.0), 30)  # 5 minutes stereo
+    enc = Encoder(44100, gpu_ctx)
+    e1 = enc.encode(x, 2)
+    e2 = enc.encode(x, 2)
+    assert_encoded_equal(e1, to_oracle(e2), "determinism")
+    pcm = Decoder(2, 44100, gpu_ctx).decode(e1)
+    assert len(pcm) == len(x)
+    assert e1.padding == (e1.n_frames + 1) * 1024 - len(x) // 2
+    # the stereo trim offset is 256 sample frames (src/codec.rs:756-761): compare after aligning.
+    # The codec is very lossy on this content (raw frames are overlap-added with the analysis window
+    # only), so the bar is the reference's own -10 dB (tests/test_codec.rs:104-106).
+    snr = signals.snr_db(x[:-512], pcm[512:])
+    assert snr > -10.0, snr
