@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native gapless-lossy-codec hot path.
+
+Metric (BASELINE.json): encode/decode audio-seconds per second.  One "step" is one pass of the hot
+path over one batch: Encoder::encode followed by Decoder::decode of `--seconds` (default 3600 = the
+"1 h synthetic 44.1 kHz stereo PCM on 1 B200" configuration, configs[1]) of audio PER GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm (C restatement of the reference)
+
+What the single JSON line holds
+  value         whole-job audio-s/s of the encode+decode round trip with the PCM ALREADY RESIDENT in
+                HBM (glc_dev_encode / glc_dev_decode), timed with CUDA events on the library's compute
+                stream, max over ranks.  encode_value / decode_value split it.
+  e2e           the same metric through the reference-facing C ABI with HOST buffers (glc_encode /
+                glc_decode: pinned host PCM in, host stream out, host PCM back), H2D and D2H inside the
+                timed region.
+  roofline      the dominant kernel (fused window + direct MDCT, EXACT mode).  It is FP32-issue bound by
+                construction (SURVEY.md section 0, F2 / DESIGN.md section 5): `bound` says so, `peak` is the
+                non-FMA FMUL+FADD issue rate measured on this GPU in the same run, and `hbm` carries
+                the HBM view of the same kernel against MEASURED_PEAKS.json.
+  cpu_baseline  the oracle (C restatement of the reference; the Rust crate cannot be built in this
+                image) timed on this box's host cores on a bounded prefix of the same workload.
+Multi-GPU: the path shards by file / frame range with no collective: every rank
+processes its own `--seconds` of audio ("weak" scaling); torch.distributed is only the barrier and
+the max-over-ranks reduction of the timings.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+SR = 44100
+CH = 2
+METRIC = "encode+decode audio-seconds per second (Encoder::encode then Decoder::decode, 44.1 kHz stereo)"
+UNIT = "audio-s/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seconds", type=float, default=3600.0, help="audio seconds per GPU per step")
+    ap.add_argument("--ref-seconds", type=float, default=30.0,
+                    help="audio seconds per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flac", action="store_true")
+    ap.add_argument("--flac-seconds", type=float, default=600.0)
+    return ap.parse_args()
+
+
+def synth(seconds: float, seed: int = 12345) -> np.ndarray:
+    """~70 % multi-sine + low-passed LCG noise (sparse frames), ~30 % white LCG
+    noise (raw-PCM frames); a 20 s deterministic period tiled to the requested length."""
+    import signals
+
+    period = signals.music_like(SR, CH, 20.0, seed=seed)
+    n = int(round(seconds * SR)) * CH
+    reps = (n + period.size - 1) // period.size
+    return np.tile(period, reps)[:n]
+
+
+# ------------------------------------------------------------------ clocks
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.25:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smmax.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm
+
+
+def cpu_codec_pass(x: np.ndarray, threads: int):
+    """One encode + decode of the oracle, threaded like the reference (rayon over frames in encode,
+    over 32-frame batches in decode) with the reference's own dense IMDCT loop (literal_imdct)."""
+    import oracle
+
+    t0 = time.perf_counter()
+    enc = oracle.encode(x, CH, SR, threads=threads)
+    t1 = time.perf_counter()
+    pcm = oracle.decode(enc, threads=threads, literal_imdct=True)
+    t2 = time.perf_counter()
+    assert len(pcm) == len(x)
+    return t1 - t0, t2 - t1
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is a Rust
+    crate and this image has no cargo/rustc (oracle/_ref is empty), so the arm
+    is the oracle port on all host threads; each step is a bounded sample of the workload."""
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    x = synth(args.ref_seconds)
+    for _ in range(max(args.warmup, 0)):
+        cpu_codec_pass(x[: min(x.size, 10 * SR * CH)], cores)
+    te = td = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = cpu_codec_pass(x, cores)
+        te += a
+        td += b
+    wall = time.perf_counter() - t0
+    secs = x.size / CH / SR
+    value = secs * args.steps / wall
+    sample = (f"first {secs:.0f} s of the 44.1 kHz stereo synthetic workload per step, {args.steps} steps; "
+              "C restatement of the reference (dense reference-order IMDCT), pthreads over frames")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"encode+decode of 44.1 kHz stereo synthetic PCM, {secs:.0f} s sample per step "
+                               "(bounded sample of the 1 h configuration)", "mode": "EXACT (reference arithmetic)"},
+        "encode_value": secs * args.steps / te, "decode_value": secs * args.steps / td,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_b200(args, rank: int, local_rank: int, world: int):
+    from gapless_lossy_codec_b200 import _ffi
+    from gapless_lossy_codec_b200.codec import Context
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if not dist:
+            return v
+        import torch
+
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v: float) -> float:
+        if not dist:
+            return v
+        import torch
+
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = Context(local_rank)  # raises GlcError when the CUDA library / device is missing: no fallback
+    L = ctx._lib
+    chk = _ffi.check
+
+    # ---- workload: this rank's shard (its own files; no data-path collective) ----
+    x = synth(args.seconds, seed=12345 + 977 * rank)
+    secs = x.size / CH / SR
+    xp = ctx.pinned_array(x.size)
+    xp[:] = x
+    del x
+    enc_h, dec_h = C.c_void_p(), C.c_void_p()
+    chk(L.glc_encoder_new(ctx.handle, SR, C.byref(enc_h)))
+    chk(L.glc_decoder_new(ctx.handle, CH, SR, C.byref(dec_h)))
+    dpcm = C.c_void_p()
+    chk(L.glc_dev_upload(ctx.handle, xp.ctypes.data, xp.size, CH, C.byref(dpcm)))
+
+    # the measured non-FMA FP32 issue roof of this GPU (same run, same clocks)
+    tera = C.c_double()
+    chk(L.glc_measure_fp32_issue(ctx.handle, 0, C.byref(tera)))
+    fp32_roof = tera.value  # 1e12 lane-ops / s
+
+    def dev_step():
+        de, dq = C.c_void_p(), C.c_void_p()
+        ms_e, ms_d = C.c_float(), C.c_float()
+        chk(L.glc_timer_begin(ctx.handle))
+        chk(L.glc_dev_encode(enc_h, dpcm, C.byref(de)))
+        chk(L.glc_timer_end(ctx.handle, C.byref(ms_e)))
+        chk(L.glc_timer_begin(ctx.handle))
+        chk(L.glc_dev_decode(dec_h, de, C.byref(dq)))
+        chk(L.glc_timer_end(ctx.handle, C.byref(ms_d)))
+        L.glc_dev_pcm_free(dq)
+        L.glc_dev_encoded_free(de)
+        return ms_e.value, ms_d.value
+
+    def host_step():
+        out = C.POINTER(_ffi.Encoded)()
+        chk(L.glc_encode(enc_h, xp.ctypes.data, xp.size, CH, C.byref(out)))
+        p, n = C.POINTER(C.c_float)(), C.c_uint64()
+        chk(L.glc_decode(dec_h, out, C.byref(p), C.byref(n)))
+        got = n.value
+        first = float(p[0]) if got else 0.0  # the step's result is read on the host
+        L.glc_free(ctx.handle, p)
+        L.glc_encoded_free(ctx.handle, out)
+        return got, first
+
+    warm = max(args.warmup, 3)  # timing rule: W >= 3
+    for _ in range(warm):
+        dev_step()
+    ctx.sync()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if sampler else 0.0)
+
+    # ---- timed region 1: device-resident (value) ----
+    ctx.enable_kernel_timing(True)
+    ctx.stats_reset()
+    barrier()
+    ctx.sync()
+    t_region0 = time.perf_counter()
+    enc_ms = dec_ms = 0.0
+    for _ in range(args.steps):
+        a, b = dev_step()
+        enc_ms += a
+        dec_ms += b
+    ctx.sync()
+    barrier()
+    wall_dev = time.perf_counter() - t_region0
+    st = ctx.stats()
+    ctx.enable_kernel_timing(False)
+    step_ms = max_over_ranks((enc_ms + dec_ms) / args.steps)
+    enc_ms_max = max_over_ranks(enc_ms / args.steps)
+    dec_ms_max = max_over_ranks(dec_ms / args.steps)
+    total_secs = sum_over_ranks(secs)
+    launches = sum(st["launches"].values())
+
+    # ---- timed region 2: end to end through the C ABI with host buffers (e2e) ----
+    for _ in range(max(1, min(args.warmup, 3))):
+        host_step()
+    ctx.stats_reset()
+    barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        got, _first = host_step()
+        assert got == xp.size, f"gapless length {got} != {xp.size}"
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t_region1 = time.perf_counter()
+    st2 = ctx.stats()
+    e2e_ms = max_over_ranks(e2e_s / args.steps * 1e3)
+    launches += sum(st2["launches"].values())
+
+    clocks = sampler.stop(t_region0, t_region1) if sampler else None
+
+    # ---- roofline of the dominant kernel (rank 0's own launches) ----
+    L_per_ch = xp.size // CH
+    padded = 512 + L_per_ch
+    padded += (-padded) % 1024
+    padded += 512
+    n_frames = (padded - 2048) // 1024 + 1
+    rows = n_frames * CH
+    k_ms = st["kernel_ms"]
+    k_n = st["launches"]
+    mdct_ms_per_step = k_ms["mdct_exact"] / args.steps
+    flops = rows * 2.0 * 1024 * 2048  # non-FMA FP32 lane operations (FMUL + FADD), SURVEY.md 8(d)
+    achieved_tops = flops / (mdct_ms_per_step * 1e-3) / 1e12
+    hbm_peak, peak_src = load_peaks()
+    # algorithmic bytes of the MDCT kernel: every new PCM sample once (4096 B per row) + the dense
+    # coefficient row it hands to quantize/pack (4096 B per row)
+    mdct_bytes = rows * (4096.0 + 4096.0)
+    hbm_gbs = mdct_bytes / (mdct_ms_per_step * 1e-3) / 1e9
+    roofline = {
+        "kernel": "exact_gemm_kernel<MDCT> (fused window + direct-form MDCT, EXACT mode)",
+        "bound": "fp32_issue", "achieved": achieved_tops, "peak": fp32_roof, "unit": "TFLOP/s",
+        "frac": achieved_tops / fp32_roof if fp32_roof else None,
+        "peak_source": "FMUL+FADD issue micro-benchmark on this GPU in this run (glc_measure_fp32_issue); "
+                       "non-FMA FP32 lane-ops: tensor cores / FMA / reordering break bit-exact parity",
+        "traffic": None,
+        "launches_per_step": k_n["mdct_exact"] / args.steps,
+        "ms_per_launch": k_ms["mdct_exact"] / max(k_n["mdct_exact"], 1),
+        "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_frame_channel": 8192},
+        "kernel_ms_per_step": {k: v / args.steps for k, v in k_ms.items() if v},
+    }
+
+    line = {
+        "metric": METRIC, "value": total_secs / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"batched encode+decode of {secs:.0f} s synthetic 44.1 kHz stereo PCM per GPU "
+                               f"({n_frames} frames, {rows} frame-channels; ~30 % raw-PCM frames)",
+                   "mode": "EXACT (bit-exact with the reference arithmetic)", "sharding": f"by file, {world} rank(s), no collective",
+                   "l2": f"inputs larger than L2 ({xp.size * 4 / 1e6:.0f} MB PCM per step vs 126 MB)"},
+        "encode_value": total_secs / (enc_ms_max * 1e-3), "decode_value": total_secs / (dec_ms_max * 1e-3),
+        "e2e": {"value": total_secs / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps,
+                "ms_per_step": e2e_ms, "api": "glc_encode + glc_decode (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": clocks,
+        "wall_s_device_region": wall_dev,
+    }
+
+    if rank == 0 and not args.no_flac:
+        line["flac"] = bench_flac(ctx, args)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    L.glc_dev_pcm_free(dpcm)
+    L.glc_encoder_free(enc_h)
+    L.glc_decoder_free(dec_h)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_flac(ctx, args) -> dict:
+    """Secondary figure: flac::encode_flac_with_level(level 8) of 96 kHz stereo PCM through the C ABI
+    (host buffers; BASELINE config 5 at `--flac-seconds`)."""
+    import signals
+
+    L = ctx._lib
+    from gapless_lossy_codec_b200 import _ffi
+
+    sr = 96000
+    period = signals.music_like(sr, 2, 10.0, seed=7)
+    # "24-bit" source as src/audio.rs:51-59 would load it: integer / 2^23
+    period = (np.round(period.astype(np.float64) * 8388608.0) / 8388608.0).astype(np.float32)
+    n = int(args.flac_seconds * sr) * 2
+    x = np.tile(period, (n + period.size - 1) // period.size)[:n]
+    xp = ctx.pinned_array(x.size)
+    xp[:] = x
+    del x
+
+    def one():
+        b, ln = C.POINTER(C.c_uint8)(), C.c_uint64()
+        _ffi.check(L.glc_flac_encode(ctx.handle, xp.ctypes.data, xp.size, sr, 2, 8, C.byref(b), C.byref(ln)))
+        L.glc_free(ctx.handle, b)
+        return ln.value
+
+    one()
+    one()
+    ctx.enable_kernel_timing(True)
+    ctx.stats_reset()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        nbytes = one()
+    dt = (time.perf_counter() - t0) / reps
+    st = ctx.stats()
+    ctx.enable_kernel_timing(False)
+    hbm_peak, peak_src = load_peaks()
+    k_ms = (st["kernel_ms"]["flac_block"] + st["kernel_ms"]["flac_gather"]) / reps
+    # algorithmic bytes per sample: 4 B f32 in + the emitted bitstream
+    alg = xp.size * 4.0 + nbytes
+    return {"workload": f"FLAC level 8, {args.flac_seconds:.0f} s 96 kHz stereo, 16-bit (reference truncates 24-bit)",
+            "e2e_audio_s_per_s": args.flac_seconds / dt, "e2e_ms": dt * 1e3, "bytes_out": int(nbytes),
+            "kernel_ms": k_ms, "kernel_audio_s_per_s": args.flac_seconds / (k_ms * 1e-3) if k_ms else None,
+            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": (alg / (k_ms * 1e-3) / 1e9) / hbm_peak if k_ms else None,
+                         "peak_source": peak_src}}
+
+
+def cpu_baseline(args) -> dict:
+    import oracle
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    secs = min(args.ref_seconds * 2, args.seconds)
+    x = synth(secs)
+    cpu_codec_pass(x[: 5 * SR * CH], cores)
+    te, td = cpu_codec_pass(x, cores)
+    return {"value": secs / (te + td), "unit": UNIT, "cores": cores, "kind": "port",
+            "encode_value": secs / te, "decode_value": secs / td,
+            "sample": f"first {secs:.0f} s of the same workload, one pass; C restatement of the reference "
+                      f"(the Rust crate cannot be built here), {cores} pthreads over frames, dense reference-order IMDCT"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

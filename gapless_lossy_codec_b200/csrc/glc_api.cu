@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <new>
 #include <string>
@@ -499,6 +500,43 @@ void ctx_time_end(glc_ctx *ctx, void *token)
 
 // ------------------------------------------------------------ small helpers
 
+// GLC_TRACE=1: print host-side phase timings (each phase boundary synchronises the stream, so the
+// numbers are only for finding overheads, never for benchmarks).
+struct PhaseTrace
+{
+    bool on;
+    cudaStream_t s;
+    const char *what;
+    double t_last;
+    static double now()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    PhaseTrace(const char *w, cudaStream_t st) : s(st), what(w)
+    {
+        static const bool enabled = getenv("GLC_TRACE") != nullptr;
+        on = enabled;
+        if (on)
+        {
+            cudaStreamSynchronize(s);
+            t_last = now();
+        }
+    }
+    void mark(const char *phase)
+    {
+        if (!on)
+            return;
+        const double t_host = now();
+        cudaStreamSynchronize(s);
+        const double t = now();
+        fprintf(stderr, "[glc trace] %s: %-14s host %.3f ms, +gpu drain %.3f ms\n", what, phase, t_host - t_last,
+                t - t_host);
+        t_last = t;
+    }
+};
+
 template <typename T>
 static cudaError_t dmalloc(T **p, size_t count, cudaStream_t s)
 {
@@ -687,6 +725,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     glc_ctx *c = enc->ctx;
     cudaStream_t cs = c->compute;
     const uint32_t n_files = (uint32_t)files.size();
+    PhaseTrace tr("encode", cs);
 
     FileDesc *d_files = nullptr;
     CUDA_TRY(dmalloc(&d_files, n_files, cs));
@@ -743,6 +782,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         }
     }
     CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
+    tr.mark("alloc");
 
     // H2D plan: file i is needed by the first wave that touches it; copy whole files in order,
     // splitting big files at wave boundaries so that copy and compute overlap.
@@ -824,6 +864,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     }
     if (ev_copy)
         c->ev_free.push_back(ev_copy);
+    tr.mark("waves");
 
     {
         LaunchScope ls(c, GLC_K_SCAN, cs, 2);
@@ -837,8 +878,10 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     c->stats.d2h_bytes += 16;
     de->n_pairs = totals[0];
     de->n_raw = totals[1];
+    tr.mark("scan+totals");
     CUDA_TRY(dmalloc(&de->d_pairs, de->n_pairs, cs));
     CUDA_TRY(dmalloc(&de->d_raw, de->n_raw, cs));
+    tr.mark("alloc out");
     {
         LaunchScope ls(c, GLC_K_GATHER, cs, 2);
         GatherLaunch g{};
@@ -857,10 +900,12 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         g.n_frames_total = tot_frames;
         CUDA_TRY(launch_gather(g, cs));
     }
+    tr.mark("gather");
     dfree(d_slots, cs);
     dfree(d_raw_len, cs);
     dfree(d_coefs, cs);
     dfree(d_files, cs);
+    tr.mark("free");
     *out = de;
     return GLC_OK;
 }
@@ -1097,6 +1142,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     float *d_coefs = nullptr, *d_blocks = nullptr, *d_out = nullptr;
     uint32_t *d_mask = nullptr;
     const uint64_t n_tiles = (tot_rows + kBM - 1) / kBM;
+    PhaseTrace tr("decode", cs);
     CUDA_TRY(dmalloc(&d_files, n_files, cs));
     CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(DecFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
     c->stats.h2d_bytes += sizeof(DecFileDesc) * n_files;
@@ -1105,6 +1151,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     CUDA_TRY(dmalloc(&d_mask, n_tiles, cs));
     CUDA_TRY(dmalloc(&d_out, total_out, cs));
     CUDA_TRY(cudaMemsetAsync(d_mask, 0, std::max<uint64_t>(n_tiles, 1) * 4, cs));
+    tr.mark("alloc");
     {
         LaunchScope ls(c, GLC_K_DEQUANT, cs);
         DequantLaunch q{};
@@ -1116,6 +1163,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         q.stage_mask = d_mask;
         CUDA_TRY(launch_dequant(q, cs));
     }
+    tr.mark("dequant");
     {
         LaunchScope ls(c, GLC_K_IMDCT_EXACT, cs);
         ImdctLaunch m{};
@@ -1130,6 +1178,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         m.variant = c->gemm_variant;
         CUDA_TRY(launch_imdct_exact(m, cs));
     }
+    tr.mark("imdct");
     {
         LaunchScope ls(c, GLC_K_OLA, cs);
         OlaLaunch o{};
@@ -1143,10 +1192,12 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         o.out = d_out;
         CUDA_TRY(launch_ola(o, cs));
     }
+    tr.mark("ola");
     dfree(d_coefs, cs);
     dfree(d_blocks, cs);
     dfree(d_mask, cs);
     dfree(d_files, cs);
+    tr.mark("free");
     (void)tot_frames;
     *d_out_ret = d_out;
     return GLC_OK;
