@@ -135,6 +135,106 @@ struct PinnedPool
     }
 };
 
+// ----------------------------------------------------------- device pool
+//
+// Grow-only cache of cudaMalloc blocks owned by the context.  The hot path allocates and frees
+// multi-GB scratch and output buffers on every call; the driver's stream-ordered allocator
+// (cudaMallocAsync / cudaFreeAsync) put tens of milliseconds of idle time on the GPU timeline of an
+// hour-long batch (measured), so steady-state calls never enter the driver:
+// a freed block goes back to this list and the next request of a similar size takes it.
+// Reuse is safe without events because every consumer is stream-ordered: a block last used on
+// stream A is handed to stream A again without a wait, and to another stream only after A drained.
+struct DevBlock
+{
+    void *p;
+    size_t cap;
+    bool used;
+    cudaStream_t last;
+};
+
+struct DevicePool
+{
+    std::vector<DevBlock> blocks;
+    std::mutex mu;
+    size_t total = 0;
+
+    cudaError_t alloc(void **out, size_t bytes, cudaStream_t s)
+    {
+        *out = nullptr;
+        if (bytes == 0)
+            bytes = 256;
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (int pass = 0; pass < 2 && best < 0; ++pass)
+            for (size_t i = 0; i < blocks.size(); ++i)
+            {
+                const DevBlock &b = blocks[i];
+                if (b.used || b.cap < bytes || b.cap > bytes + bytes / 4 + ((size_t)4 << 20))
+                    continue;
+                if (pass == 0 && b.last != s)
+                    continue; // prefer a block whose previous user ran on the same stream
+                if (best < 0 || b.cap < blocks[best].cap)
+                    best = (int)i;
+            }
+        if (best >= 0)
+        {
+            DevBlock &b = blocks[best];
+            if (b.last != s && b.last != nullptr)
+                cudaStreamSynchronize(b.last);
+            b.used = true;
+            b.last = s;
+            *out = b.p;
+            return cudaSuccess;
+        }
+        const size_t gran = bytes >= ((size_t)1 << 20) ? ((size_t)2 << 20) : 512;
+        const size_t cap = (bytes + gran - 1) / gran * gran;
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, cap);
+        if (e != cudaSuccess)
+        {
+            // out of memory: give every idle block back to the driver and retry once
+            (void)cudaGetLastError();
+            cudaDeviceSynchronize();
+            for (size_t i = 0; i < blocks.size();)
+                if (!blocks[i].used)
+                {
+                    cudaFree(blocks[i].p);
+                    total -= blocks[i].cap;
+                    blocks.erase(blocks.begin() + (long)i);
+                }
+                else
+                    ++i;
+            e = cudaMalloc(&p, cap);
+            if (e != cudaSuccess)
+                return e;
+        }
+        blocks.push_back({p, cap, true, s});
+        total += cap;
+        *out = p;
+        return cudaSuccess;
+    }
+    void release(void *p, cudaStream_t s)
+    {
+        if (!p)
+            return;
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &b : blocks)
+            if (b.p == p)
+            {
+                b.used = false;
+                b.last = s;
+                return;
+            }
+    }
+    void destroy()
+    {
+        for (auto &b : blocks)
+            cudaFree(b.p);
+        blocks.clear();
+        total = 0;
+    }
+};
+
 // ------------------------------------------------------------------ context
 
 struct TimedLaunch
@@ -152,6 +252,7 @@ struct glc_ctx
     HostTables host;
     float *d_tab_mdct, *d_tab_imdct, *d_window;
     PinnedPool pool;
+    DevicePool dpool;
     glc_stats stats;
     bool timing;
     std::vector<TimedLaunch> timed;
@@ -265,13 +366,6 @@ extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->t0));
     CUDA_TRY(cudaEventCreate(&c->t1));
-    // keep freed stream-ordered allocations cached in the pool (no trimming at sync points)
-    cudaMemPool_t mp;
-    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess)
-    {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     // tables: host libm -> tiled copies -> device
     build_host_tables(&c->host);
     const size_t tab_bytes = sizeof(float) * (size_t)kHop * kFrame;
@@ -306,6 +400,7 @@ extern "C" void glc_ctx_destroy(glc_ctx *c)
     if (c->d_flush)
         cudaFree(c->d_flush);
     c->pool.destroy();
+    c->dpool.destroy();
     free_host_tables(&c->host);
     cudaEventDestroy(c->t0);
     cudaEventDestroy(c->t1);
@@ -466,6 +561,8 @@ glc_status set_error(glc_status st, const char *fmt, ...)
 }
 void *pinned_alloc(glc_ctx *ctx, size_t bytes) { return ctx->pool.alloc(bytes); }
 void pinned_release(glc_ctx *ctx, void *p) { ctx->pool.release(p); }
+cudaError_t dev_alloc(glc_ctx *ctx, void **out, size_t bytes, cudaStream_t s) { return ctx->dpool.alloc(out, bytes, s); }
+void dev_free(glc_ctx *ctx, void *p, cudaStream_t s) { ctx->dpool.release(p, s); }
 int ctx_device(glc_ctx *ctx) { return ctx->device; }
 cudaStream_t ctx_compute_stream(glc_ctx *ctx) { return ctx->compute; }
 void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n) { ctx->stats.launches[kernel_id] += n; }
@@ -504,50 +601,79 @@ void ctx_time_end(glc_ctx *ctx, void *token)
 // numbers are only for finding overheads, never for benchmarks).
 struct PhaseTrace
 {
-    bool on;
+    // GLC_TRACE=1: sync at every phase boundary and print host/GPU-drain times
+    // GLC_TRACE=2: host timestamps only
+    // GLC_TRACE=3: CUDA events at phase boundaries (no added sync), printed when the scope ends
+    int level;
     cudaStream_t s;
     const char *what;
     double t_last;
+    std::vector<std::pair<const char *, cudaEvent_t>> evs;
     static double now()
     {
         timespec ts;
         clock_gettime(CLOCK_MONOTONIC, &ts);
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     }
+    void ev(const char *name)
+    {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        evs.push_back({name, e});
+    }
     PhaseTrace(const char *w, cudaStream_t st) : s(st), what(w)
     {
-        static const bool enabled = getenv("GLC_TRACE") != nullptr;
-        on = enabled;
-        if (on)
-        {
+        static const int lv = getenv("GLC_TRACE") ? atoi(getenv("GLC_TRACE")) : 0;
+        level = lv;
+        if (level == 1)
             cudaStreamSynchronize(s);
+        if (level == 3)
+            ev("begin");
+        if (level)
             t_last = now();
-        }
     }
     void mark(const char *phase)
     {
-        if (!on)
+        if (!level)
             return;
+        if (level == 3)
+        {
+            ev(phase);
+            return;
+        }
         const double t_host = now();
-        cudaStreamSynchronize(s);
+        if (level == 1)
+            cudaStreamSynchronize(s);
         const double t = now();
         fprintf(stderr, "[glc trace] %s: %-14s host %.3f ms, +gpu drain %.3f ms\n", what, phase, t_host - t_last,
                 t - t_host);
         t_last = t;
     }
+    ~PhaseTrace()
+    {
+        if (level != 3 || evs.empty())
+            return;
+        cudaEventSynchronize(evs.back().second);
+        for (size_t i = 1; i < evs.size(); ++i)
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i - 1].second, evs[i].second);
+            fprintf(stderr, "[glc trace] %s: %-14s gpu %.3f ms\n", what, evs[i].first, ms);
+        }
+        for (auto &e : evs)
+            cudaEventDestroy(e.second);
+    }
 };
 
+#define dmalloc(pp, count, s) dmalloc_impl(c, pp, count, s)
+#define dfree(p, s) c->dpool.release(p, s)
+
 template <typename T>
-static cudaError_t dmalloc(T **p, size_t count, cudaStream_t s)
+static cudaError_t dmalloc_impl(glc_ctx *c, T **p, size_t count, cudaStream_t s)
 {
     *p = nullptr;
-    return cudaMallocAsync((void **)p, std::max<size_t>(count, 1) * sizeof(T), s);
-}
-
-static void dfree(void *p, cudaStream_t s)
-{
-    if (p)
-        cudaFreeAsync(p, s);
+    return c->dpool.alloc((void **)p, std::max<size_t>(count, 1) * sizeof(T), s);
 }
 
 static uint64_t padded_len(uint64_t L)
@@ -607,8 +733,8 @@ extern "C" void glc_dev_pcm_free(glc_dev_pcm *p)
 {
     if (!p)
         return;
-    cudaSetDevice(p->ctx->device);
-    dfree(p->d, p->ctx->compute);
+    glc_ctx *c = p->ctx;
+    dfree(p->d, c->compute);
     delete p;
 }
 
@@ -616,8 +742,8 @@ extern "C" void glc_dev_encoded_free(glc_dev_encoded *e)
 {
     if (!e)
         return;
-    cudaSetDevice(e->ctx->device);
-    cudaStream_t s = e->ctx->compute;
+    glc_ctx *c = e->ctx;
+    cudaStream_t s = c->compute;
     dfree(e->d_is_raw, s);
     dfree(e->d_nnz, s);
     dfree(e->d_pair_off, s);

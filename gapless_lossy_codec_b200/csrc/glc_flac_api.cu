@@ -264,12 +264,12 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
             break;                                                                                \
         }                                                                                         \
     }
-        FL_STEP(cudaMallocAsync((void **)&d_pcm, std::max<uint64_t>(tot_pcm, 1) * 4, cs));
-        FL_STEP(cudaMallocAsync((void **)&d_i16, std::max<uint64_t>(tot_pcm, 1) * 2, cs));
-        FL_STEP(cudaMallocAsync((void **)&d_files, sizeof(FlacFileDesc) * n_files, cs));
-        FL_STEP(cudaMallocAsync((void **)&d_k, std::max<uint64_t>(tot_blocks, 1) * max_ch * 64, cs));
-        FL_STEP(cudaMallocAsync((void **)&d_fbytes, std::max<uint64_t>(tot_blocks, 1) * 4, cs));
-        FL_STEP(cudaMallocAsync((void **)&d_foff, (tot_blocks + 1) * 8, cs));
+        FL_STEP(dev_alloc(ctx, (void **)&d_pcm, std::max<uint64_t>(tot_pcm, 1) * 4, cs));
+        FL_STEP(dev_alloc(ctx, (void **)&d_i16, std::max<uint64_t>(tot_pcm, 1) * 2, cs));
+        FL_STEP(dev_alloc(ctx, (void **)&d_files, sizeof(FlacFileDesc) * n_files, cs));
+        FL_STEP(dev_alloc(ctx, (void **)&d_k, std::max<uint64_t>(tot_blocks, 1) * max_ch * 64, cs));
+        FL_STEP(dev_alloc(ctx, (void **)&d_fbytes, std::max<uint64_t>(tot_blocks, 1) * 4, cs));
+        FL_STEP(dev_alloc(ctx, (void **)&d_foff, (tot_blocks + 1) * 8, cs));
         FL_STEP(cudaMemcpyAsync(d_files, files.data(), sizeof(FlacFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
         bool bad = false;
         for (uint32_t i = 0; i < n_files && !bad; ++i)
@@ -324,10 +324,12 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
             }
             tot_bytes += file_bytes[i];
         }
-        FL_STEP(cudaMallocAsync((void **)&d_out, std::max<uint64_t>(tot_bytes, 1), cs));
+        FL_STEP(dev_alloc(ctx, (void **)&d_out, std::max<uint64_t>(tot_bytes, 1), cs));
+        if (const size_t sw = flac_emit_scratch_words(tot_blocks, max_ch, max_bs, max_frame, prop.multiProcessorCount))
+            FL_STEP(dev_alloc(ctx, (void **)&d_scratch, sw * 4, cs));
         ctx_count_launch(ctx, GLC_K_FLAC_GATHER, 1);
         ctx_time_begin(ctx, GLC_K_FLAC_GATHER, &tok);
-        FL_STEP(launch_flac_emit(fl, d_k, max_ch, max_bs, max_frame, d_foff, d_out, &d_scratch,
+        FL_STEP(launch_flac_emit(fl, d_k, max_ch, max_bs, max_frame, d_foff, d_out, d_scratch,
                                  prop.multiProcessorCount, cs));
         ctx_time_end(ctx, tok);
 
@@ -388,16 +390,14 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
     }
     if (h_fbytes)
         pinned_release(ctx, h_fbytes);
-    cudaFreeAsync(d_pcm, cs);
-    cudaFreeAsync(d_i16, cs);
-    cudaFreeAsync(d_files, cs);
-    cudaFreeAsync(d_k, cs);
-    cudaFreeAsync(d_fbytes, cs);
-    cudaFreeAsync(d_foff, cs);
-    if (d_out)
-        cudaFreeAsync(d_out, cs);
-    if (d_scratch)
-        cudaFreeAsync(d_scratch, cs);
+    dev_free(ctx, d_pcm, cs);
+    dev_free(ctx, d_i16, cs);
+    dev_free(ctx, d_files, cs);
+    dev_free(ctx, d_k, cs);
+    dev_free(ctx, d_fbytes, cs);
+    dev_free(ctx, d_foff, cs);
+    dev_free(ctx, d_out, cs);
+    dev_free(ctx, d_scratch, cs);
     return st;
 }
 

@@ -645,40 +645,63 @@ cudaError_t launch_flac_measure(const FlacLaunch &p, uint8_t *rice_k, uint32_t m
     return cudaGetLastError();
 }
 
-cudaError_t launch_flac_emit(const FlacLaunch &p, const uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs,
-                             uint32_t max_frame_bytes, const uint64_t *frame_off, uint8_t *out_arena,
-                             uint32_t **scratch_io, int sm_count, cudaStream_t s)
+namespace
 {
-    if (p.n_blocks_total == 0)
-        return cudaSuccess;
-    const uint32_t smp_bytes = (uint32_t)(((size_t)max_bs * max_ch * sizeof(int16_t) + 15) & ~(size_t)15);
-    const uint32_t buf_words = ((max_frame_bytes + 3) >> 2) + 2;
-    size_t smem = (size_t)smp_bytes + (size_t)buf_words * 4;
-    uint32_t *scratch = nullptr;
+constexpr size_t kEmitSmemLimit = 200 * 1024;
+struct EmitPlan
+{
+    uint32_t smp_bytes, buf_words;
+    size_t smem;
     unsigned grid;
-    const size_t smem_limit = 200 * 1024;
-    if (smem > smem_limit)
+    bool global_scratch;
+};
+EmitPlan plan_emit(uint64_t n_blocks, uint32_t max_ch, uint32_t max_bs, uint32_t max_frame_bytes, int sm_count)
+{
+    EmitPlan pl;
+    pl.smp_bytes = (uint32_t)(((size_t)max_bs * max_ch * sizeof(int16_t) + 15) & ~(size_t)15);
+    pl.buf_words = ((max_frame_bytes + 3) >> 2) + 2;
+    pl.smem = (size_t)pl.smp_bytes + (size_t)pl.buf_words * 4;
+    pl.global_scratch = pl.smem > kEmitSmemLimit;
+    if (pl.global_scratch)
     {
         // frames too large for shared memory (pathological residuals / many channels): the bit
         // buffer moves to a per-CTA global scratch area, same code path through generic pointers
-        smem = smp_bytes;
-        grid = (unsigned)std::min<uint64_t>(p.n_blocks_total, (uint64_t)sm_count * 2);
-        cudaError_t e = cudaMallocAsync((void **)&scratch, (size_t)grid * buf_words * 4, s);
-        if (e != cudaSuccess)
-            return e;
-        *scratch_io = scratch;
+        pl.smem = pl.smp_bytes;
+        pl.grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)sm_count * 2);
     }
     else
     {
         // as many CTAs as fit; each loops over blocks with a grid stride
-        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
-        grid = (unsigned)std::min<uint64_t>(p.n_blocks_total, (uint64_t)sm_count * per_sm);
+        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (pl.smem + 1024)));
+        pl.grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)sm_count * per_sm);
     }
-    cudaError_t e = cudaFuncSetAttribute(flac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return pl;
+}
+} // namespace
+
+size_t flac_emit_scratch_words(uint64_t n_blocks, uint32_t max_ch, uint32_t max_bs, uint32_t max_frame_bytes,
+                               int sm_count)
+{
+    if (n_blocks == 0)
+        return 0;
+    const EmitPlan pl = plan_emit(n_blocks, max_ch, max_bs, max_frame_bytes, sm_count);
+    return pl.global_scratch ? (size_t)pl.grid * pl.buf_words : 0;
+}
+
+cudaError_t launch_flac_emit(const FlacLaunch &p, const uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs,
+                             uint32_t max_frame_bytes, const uint64_t *frame_off, uint8_t *out_arena,
+                             uint32_t *scratch, int sm_count, cudaStream_t s)
+{
+    if (p.n_blocks_total == 0)
+        return cudaSuccess;
+    const EmitPlan pl = plan_emit(p.n_blocks_total, max_ch, max_bs, max_frame_bytes, sm_count);
+    if (pl.global_scratch && !scratch)
+        return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(flac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess)
         return e;
-    flac_emit_kernel<<<grid, kFlacThreads, smem, s>>>(p, rice_k, max_ch, frame_off, out_arena, smp_bytes, buf_words,
-                                                      scratch);
+    flac_emit_kernel<<<pl.grid, kFlacThreads, pl.smem, s>>>(p, rice_k, max_ch, frame_off, out_arena, pl.smp_bytes,
+                                                            pl.buf_words, pl.global_scratch ? scratch : nullptr);
     return cudaGetLastError();
 }
 

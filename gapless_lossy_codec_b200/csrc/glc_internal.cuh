@@ -200,15 +200,20 @@ struct FlacLaunch
 };
 cudaError_t launch_flac_measure(const FlacLaunch &p, uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs,
                                 cudaStream_t s);
+// words of global scratch the emit pass needs (0 when the bit buffer fits in shared memory)
+size_t flac_emit_scratch_words(uint64_t n_blocks, uint32_t max_ch, uint32_t max_bs, uint32_t max_frame_bytes,
+                               int sm_count);
 cudaError_t launch_flac_emit(const FlacLaunch &p, const uint8_t *rice_k, uint32_t max_ch, uint32_t max_bs,
                              uint32_t max_frame_bytes, const uint64_t *frame_off, uint8_t *out_arena,
-                             uint32_t **scratch_io, int sm_count, cudaStream_t s);
+                             uint32_t *scratch, int sm_count, cudaStream_t s);
 uint32_t flac_slot_bytes(uint32_t block_size, uint32_t channels);
 
 // ---- host-side plumbing shared by the API translation units ----
 glc_status set_error(glc_status st, const char *fmt, ...);
 void *pinned_alloc(glc_ctx *ctx, size_t bytes);
 void pinned_release(glc_ctx *ctx, void *p);
+cudaError_t dev_alloc(glc_ctx *ctx, void **out, size_t bytes, cudaStream_t s); // context-owned device pool
+void dev_free(glc_ctx *ctx, void *p, cudaStream_t s);
 int ctx_device(glc_ctx *ctx);
 cudaStream_t ctx_compute_stream(glc_ctx *ctx);
 void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n);
