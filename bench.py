@@ -343,12 +343,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     flops = rows * 2.0 * 1024 * 2048  # non-FMA FP32 lane operations (FMUL + FADD), SURVEY.md 8(d)
     achieved_tops = flops / (mdct_ms_per_step * 1e-3) / 1e12
     hbm_peak, peak_src = load_peaks()
-    # algorithmic bytes of the MDCT kernel: every new PCM sample once (4096 B per row) + the dense
+    # algorithmic bytes of the MDCT stage: every new PCM sample once (4096 B per row) + the dense
     # coefficient row it hands to quantize/pack (4096 B per row)
     mdct_bytes = rows * (4096.0 + 4096.0)
     hbm_gbs = mdct_bytes / (mdct_ms_per_step * 1e-3) / 1e9
     roofline = {
-        "kernel": "exact_gemm_kernel<MDCT> (fused window + direct-form MDCT, EXACT mode)",
+        "kernel": "exact_gemm_kernel<MDCT> (direct-form MDCT contraction, EXACT mode; operands by TMA bulk copy)",
         "bound": "fp32_issue", "achieved": achieved_tops, "peak": fp32_roof, "unit": "TFLOP/s",
         "frac": achieved_tops / fp32_roof if fp32_roof else None,
         "peak_source": "FMUL+FADD issue micro-benchmark on this GPU in this run (glc_measure_fp32_issue); "

@@ -62,8 +62,9 @@ class Context:
     def enable_kernel_timing(self, on: bool):
         self._lib.glc_stats_enable_kernel_timing(self.handle, int(on))
 
-    def set_tuning(self, gemm_variant: int = -1, wave_frames: int = 0):
-        check(self._lib.glc_ctx_set_tuning(self.handle, gemm_variant, wave_frames))
+    def set_tuning(self, reserved: int = 0, wave_rows: int = 0):
+        """wave_rows = frame-channel rows per encode pipeline wave (0 = automatic)."""
+        check(self._lib.glc_ctx_set_tuning(self.handle, reserved, wave_rows))
 
     def sync(self):
         check(self._lib.glc_ctx_sync(self.handle))

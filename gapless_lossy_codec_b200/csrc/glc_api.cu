@@ -357,9 +357,9 @@ extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
     c->gemm_variant = 0;
     if (const char *v = getenv("GLC_GEMM_VARIANT"))
         c->gemm_variant = atoi(v);
-    c->wave_frames = 8192;
-    if (const char *v = getenv("GLC_WAVE_FRAMES"))
-        c->wave_frames = (uint64_t)atoll(v) > 0 ? (uint64_t)atoll(v) : 8192;
+    c->wave_frames = 0; // 0 = automatic wave sizing (encode_core); otherwise rows per wave
+    if (const char *v = getenv("GLC_WAVE_ROWS"))
+        c->wave_frames = (uint64_t)atoll(v) > 0 ? (uint64_t)atoll(v) : 0;
     c->d_flush = nullptr;
     c->flush_floats = 0;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
@@ -377,9 +377,9 @@ extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
     CUDA_TRY(cudaMalloc(&c->d_window, sizeof(float) * kFrame));
     tile_table_for_mdct(c->host.cos_tab, tiled);
     CUDA_TRY(cudaMemcpy(c->d_tab_mdct, tiled, tab_bytes, cudaMemcpyHostToDevice));
-    tile_table_for_imdct(c->host.cos_tab, tiled);
-    CUDA_TRY(cudaMemcpy(c->d_tab_imdct, tiled, tab_bytes, cudaMemcpyHostToDevice));
     free(tiled);
+    // the IMDCT gathers rows k of the reference layout tab[k][i] directly
+    CUDA_TRY(cudaMemcpy(c->d_tab_imdct, c->host.cos_tab, tab_bytes, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->d_window, c->host.window, sizeof(float) * kFrame, cudaMemcpyHostToDevice));
     *out = c;
     return GLC_OK;
@@ -413,10 +413,8 @@ extern "C" glc_status glc_ctx_set_tuning(glc_ctx *c, int gemm_variant, uint64_t 
 {
     if (!c)
         return fail(GLC_ERR_INVALID_ARG, "ctx is null");
-    if (gemm_variant >= 0 && gemm_variant <= 2)
-        c->gemm_variant = gemm_variant;
-    if (wave_frames)
-        c->wave_frames = wave_frames;
+    (void)gemm_variant; // reserved: the packed f32x2 variants measured no faster and were removed
+    c->wave_frames = wave_frames; // rows per encode wave, 0 = automatic
     return GLC_OK;
 }
 
@@ -877,8 +875,15 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     CUDA_TRY(dmalloc(&d_slots, tot_rows * kHop, cs));
     CUDA_TRY(dmalloc(&d_raw_len, tot_frames, cs));
 
-    // wave plan: contiguous frame ranges; a wave never spans more rows than the coefficient scratch
-    const uint64_t wave_frames = std::max<uint64_t>(c->wave_frames, 1);
+    // Wave plan: contiguous frame ranges.  A wave's MDCT grid is (rows/128) x 8 CTAs and 2 x 148 CTAs
+    // are resident at a time, so waves are sized in multiples of 37 row tiles (4 736 rows): every
+    // resident slot then runs the same number of CTAs and no partial "CTA wave" idles the GPU.
+    // Host input: small waves so that the H2D of wave w+1 hides behind the MDCT of wave w.
+    // Device-resident input: large waves (fewer launches, scratch still bounded).
+    const uint64_t kRowQuantum = 37ull * kBM;
+    uint64_t target_rows = kRowQuantum * (host_pcm ? 4 : 32);
+    if (c->wave_frames)
+        target_rows = std::max<uint64_t>(c->wave_frames, 1); // explicit tuning: rows per wave
     uint64_t max_wave_rows = 0;
     struct Wave
     {
@@ -886,28 +891,42 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     };
     std::vector<Wave> waves;
     {
-        uint32_t fi = 0;
+        auto row_of_frame = [&](uint64_t fr) -> uint64_t {
+            if (fr >= tot_frames)
+                return tot_rows;
+            uint32_t lo = 0, hi = n_files - 1;
+            while (lo < hi)
+            {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (files[mid].first_frame <= fr)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            return files[lo].first_row + (fr - files[lo].first_frame) * files[lo].channels;
+        };
         uint64_t f = 0;
         while (f < tot_frames)
         {
-            const uint64_t f1 = std::min(tot_frames, f + wave_frames);
-            // rows of frames [f, f1)
-            auto row_of_frame = [&](uint64_t fr) -> uint64_t {
-                if (fr >= tot_frames)
-                    return tot_rows;
-                while (fi + 1 < n_files && files[fi + 1].first_frame <= fr)
-                    ++fi;
-                while (fi > 0 && files[fi].first_frame > fr)
-                    --fi;
-                return files[fi].first_row + (fr - files[fi].first_frame) * files[fi].channels;
-            };
-            Wave w{f, f1, row_of_frame(f), row_of_frame(f1)};
+            const uint64_t r0 = row_of_frame(f);
+            uint64_t lo = f + 1, hi = tot_frames; // largest f1 whose rows fit the target (at least one frame)
+            while (lo < hi)
+            {
+                const uint64_t mid = (lo + hi + 1) >> 1;
+                if (row_of_frame(mid) - r0 <= target_rows)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            Wave w{f, lo, r0, row_of_frame(lo)};
             max_wave_rows = std::max(max_wave_rows, w.r1 - w.r0);
             waves.push_back(w);
-            f = f1;
+            f = lo;
         }
     }
     CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
+    float *d_atiles = nullptr;
+    CUDA_TRY(dmalloc(&d_atiles, mdct_a_tile_floats(max_wave_rows), cs));
     tr.mark("alloc");
 
     // H2D plan: file i is needed by the first wave that touches it; copy whole files in order,
@@ -956,9 +975,9 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
                 CUDA_TRY(cudaStreamWaitEvent(cs, ev_copy, 0));
             }
         }
+        MdctLaunch m{};
         {
-            LaunchScope ls(c, GLC_K_MDCT_EXACT, cs);
-            MdctLaunch m{};
+            LaunchScope ls(c, GLC_K_WINDOW_TILE, cs);
             m.pcm_arena = d_arena;
             m.files = d_files;
             m.n_files = n_files;
@@ -968,7 +987,11 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             m.window = c->d_window;
             m.norm = c->host.norm;
             m.coefs = d_coefs - w.r0 * kHop; // kernels index coefficients by absolute row
-            m.variant = c->gemm_variant;
+            m.a_tiles = d_atiles;
+            CUDA_TRY(launch_window_tiles(m, cs));
+        }
+        {
+            LaunchScope ls(c, GLC_K_MDCT_EXACT, cs);
             CUDA_TRY(launch_mdct_exact(m, cs));
         }
         {
@@ -1030,6 +1053,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     dfree(d_slots, cs);
     dfree(d_raw_len, cs);
     dfree(d_coefs, cs);
+    dfree(d_atiles, cs);
     dfree(d_files, cs);
     tr.mark("free");
     *out = de;
@@ -1265,43 +1289,62 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     cudaStream_t cs = c->compute;
     const uint32_t n_files = (uint32_t)files.size();
     DecFileDesc *d_files = nullptr;
-    float *d_coefs = nullptr, *d_blocks = nullptr, *d_out = nullptr;
-    uint32_t *d_mask = nullptr;
-    const uint64_t n_tiles = (tot_rows + kBM - 1) / kBM;
+    float *d_atiles = nullptr, *d_blocks = nullptr, *d_out = nullptr;
+    uint32_t *d_flags = nullptr, *d_active = nullptr, *d_ntiles = nullptr, *d_nk = nullptr;
+    uint64_t *d_slot_off = nullptr;
+    int32_t *d_row_slot = nullptr;
+    uint16_t *d_klist = nullptr;
+    const uint64_t max_tiles = (tot_rows + kBM - 1) / kBM;
     PhaseTrace tr("decode", cs);
     CUDA_TRY(dmalloc(&d_files, n_files, cs));
     CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(DecFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
     c->stats.h2d_bytes += sizeof(DecFileDesc) * n_files;
-    CUDA_TRY(dmalloc(&d_coefs, tot_rows * kHop, cs));
-    CUDA_TRY(dmalloc(&d_blocks, tot_rows * kFrame, cs));
-    CUDA_TRY(dmalloc(&d_mask, n_tiles, cs));
+    // worst-case sizes (every row transformed, every k present): the live counts stay on the device,
+    // so the decode needs no host round trip
+    CUDA_TRY(dmalloc(&d_atiles, max_tiles * kHop * kBM, cs));
+    CUDA_TRY(dmalloc(&d_blocks, max_tiles * kBM * kFrame, cs));
+    CUDA_TRY(dmalloc(&d_flags, tot_rows, cs));
+    CUDA_TRY(dmalloc(&d_slot_off, tot_rows + 1, cs));
+    CUDA_TRY(dmalloc(&d_row_slot, tot_rows, cs));
+    CUDA_TRY(dmalloc(&d_active, tot_rows, cs));
+    CUDA_TRY(dmalloc(&d_ntiles, 1, cs));
+    CUDA_TRY(dmalloc(&d_nk, max_tiles, cs));
+    CUDA_TRY(dmalloc(&d_klist, max_tiles * kHop, cs));
     CUDA_TRY(dmalloc(&d_out, total_out, cs));
-    CUDA_TRY(cudaMemsetAsync(d_mask, 0, std::max<uint64_t>(n_tiles, 1) * 4, cs));
     tr.mark("alloc");
     {
-        LaunchScope ls(c, GLC_K_DEQUANT, cs);
+        LaunchScope ls(c, GLC_K_DEQUANT, cs, 4);
         DequantLaunch q{};
         q.pairs = d_pairs;
         q.pair_off = d_pair_off;
         q.scales = d_scales;
+        q.is_raw = d_is_raw;
+        q.files = d_files;
+        q.n_files = n_files;
         q.n_rows = tot_rows;
-        q.coefs = d_coefs;
-        q.stage_mask = d_mask;
+        q.flags = d_flags;
+        q.slot_off = d_slot_off;
+        q.row_slot = d_row_slot;
+        q.active_rows = d_active;
+        q.n_tiles = d_ntiles;
+        q.klist = d_klist;
+        q.n_k = d_nk;
+        q.a_tiles = d_atiles;
         CUDA_TRY(launch_dequant(q, cs));
     }
     tr.mark("dequant");
     {
         LaunchScope ls(c, GLC_K_IMDCT_EXACT, cs);
         ImdctLaunch m{};
-        m.coefs = d_coefs;
-        m.stage_mask = d_mask;
-        m.row_begin = 0;
-        m.row_end = tot_rows;
-        m.tab_tiled = c->d_tab_imdct;
+        m.a_tiles = d_atiles;
+        m.klist = d_klist;
+        m.n_k = d_nk;
+        m.n_tiles = d_ntiles;
+        m.max_slots = max_tiles * kBM;
+        m.tab = c->d_tab_imdct;
         m.window = c->d_window;
         m.norm = c->host.norm;
         m.blocks = d_blocks;
-        m.variant = c->gemm_variant;
         CUDA_TRY(launch_imdct_exact(m, cs));
     }
     tr.mark("imdct");
@@ -1309,6 +1352,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         LaunchScope ls(c, GLC_K_OLA, cs);
         OlaLaunch o{};
         o.blocks = d_blocks;
+        o.row_slot = d_row_slot;
         o.is_raw = d_is_raw;
         o.raw_off = d_raw_off;
         o.raw = d_raw;
@@ -1319,9 +1363,15 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         CUDA_TRY(launch_ola(o, cs));
     }
     tr.mark("ola");
-    dfree(d_coefs, cs);
+    dfree(d_atiles, cs);
     dfree(d_blocks, cs);
-    dfree(d_mask, cs);
+    dfree(d_flags, cs);
+    dfree(d_slot_off, cs);
+    dfree(d_row_slot, cs);
+    dfree(d_active, cs);
+    dfree(d_ntiles, cs);
+    dfree(d_nk, cs);
+    dfree(d_klist, cs);
     dfree(d_files, cs);
     tr.mark("free");
     (void)tot_frames;

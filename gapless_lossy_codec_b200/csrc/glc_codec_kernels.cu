@@ -282,61 +282,143 @@ __global__ void __launch_bounds__(256) gather_raw_kernel(const GatherLaunch p)
     }
 }
 
-// ---- dequant: one warp per row ----
-__global__ void __launch_bounds__(256) dequant_kernel(const DequantLaunch p)
+// ---- decode front end ------------------------------------------------------------------------
+// Which rows are transformed: sparse frames with at least one pair.  Raw frames bypass the IMDCT
+// (src/codec.rs:626-644) and an all-zero coefficient row gives an all +0.0 block, so neither needs
+// a slot in the transform.
+__global__ void __launch_bounds__(256) row_flag_kernel(const DequantLaunch p)
 {
-    const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= p.n_rows)
         return;
-    const int lane = threadIdx.x & 31;
-    float *dst = p.coefs + row * kHop;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < kHop / 4 / 32; ++j)
-        reinterpret_cast<float4 *>(dst)[j * 32 + lane] = z;
-    const uint64_t b = p.pair_off[row], e = p.pair_off[row + 1];
-    const uint32_t n = (uint32_t)(e - b);
-    if (n == 0)
+    uint32_t lo = 0, hi = p.n_files - 1;
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (p.files[mid].first_row <= row)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const DecFileDesc &fd = p.files[lo];
+    const uint64_t frame = fd.first_frame + (row - fd.first_row) / fd.channels;
+    p.flags[row] = (!p.is_raw[frame] && p.pair_off[row + 1] > p.pair_off[row]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) row_scatter_kernel(const DequantLaunch p)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row == 0)
+        *p.n_tiles = (uint32_t)((p.slot_off[p.n_rows] + kBM - 1) / kBM);
+    if (row >= p.n_rows)
         return;
-    __syncwarp();
-    const glc_pair *pr = p.pairs + b;
-    const float scale = fmaxf(p.scales[row], 1e-12f); // src/codec.rs:653
-    // "later duplicates overwrite" (src/codec.rs:659-665): parallel scatter is only safe when the
-    // indices are strictly ascending (what the encoder emits); otherwise lane 0 replays in order.
-    bool ascending = true;
-    for (uint32_t j = lane; j + 1 < n; j += 32)
-        ascending = ascending && (pr[j].idx < pr[j + 1].idx);
-    ascending = __all_sync(0xffffffffu, ascending);
-    uint32_t mask = 0;
-    if (ascending)
+    if (p.flags[row])
     {
-        for (uint32_t j = lane; j < n; j += 32)
+        const uint32_t slot = (uint32_t)p.slot_off[row];
+        p.active_rows[slot] = (uint32_t)row;
+        p.row_slot[row] = (int32_t)slot;
+    }
+    else
+        p.row_slot[row] = -1;
+}
+
+// One CTA per tile of kBM compacted rows: union of the coefficient indices present in the tile
+// (ascending), then the dequantised values (src/codec.rs:651-665) laid out as the A operand of the
+// IMDCT, [stage][kKC][kBM], over that union only.
+__global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p)
+{
+    __shared__ uint32_t s_bits[kHop / 32];
+    __shared__ uint32_t s_prefix[kHop / 32];
+    __shared__ uint32_t s_nk;
+    const uint64_t n_active = p.slot_off[p.n_rows];
+    const uint64_t tile = blockIdx.x;
+    if (tile * kBM >= n_active)
+        return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rows_here = (uint32_t)min((uint64_t)kBM, n_active - tile * kBM);
+    if (tid < kHop / 32)
+        s_bits[tid] = 0;
+    __syncthreads();
+
+    // pass 1: index union (any pair with idx < 1024 counts, also ones a later duplicate overwrites)
+    for (uint32_t r = warp; r < rows_here; r += 8)
+    {
+        const uint64_t row = p.active_rows[tile * kBM + r];
+        const uint64_t b = p.pair_off[row], e = p.pair_off[row + 1];
+        for (uint64_t j = b + lane; j < e; j += 32)
         {
-            const glc_pair q = pr[j];
-            if (q.idx < kHop)
-            {
-                dst[q.idx] = __fmul_rn(__fdiv_rn((float)q.q, 32768.0f), scale);
-                mask |= 1u << (q.idx / kKC);
-            }
+            const uint32_t idx = p.pairs[j].idx;
+            if (idx < kHop)
+                atomicOr(&s_bits[idx >> 5], 1u << (idx & 31));
         }
     }
-    else if (lane == 0)
+    __syncthreads();
+    if (warp == 0)
     {
-        for (uint32_t j = 0; j < n; ++j)
-        {
-            const glc_pair q = pr[j];
-            if (q.idx < kHop)
-            {
-                dst[q.idx] = __fmul_rn(__fdiv_rn((float)q.q, 32768.0f), scale);
-                mask |= 1u << (q.idx / kKC);
-            }
-        }
-    }
+        const uint32_t c = __popc(s_bits[lane]);
+        uint32_t incl = c;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        mask |= __shfl_xor_sync(0xffffffffu, mask, o);
-    if (lane == 0 && mask)
-        atomicOr(p.stage_mask + row / kBM, mask);
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        s_prefix[lane] = incl - c;
+        if (lane == 31)
+            s_nk = incl;
+    }
+    __syncthreads();
+    const uint32_t nk = s_nk;
+    const uint32_t nk_pad = (nk + kKC - 1) / kKC * kKC;
+    uint16_t *kl = p.klist + tile * kHop;
+    for (uint32_t k = tid; k < kHop; k += 256)
+    {
+        const uint32_t w = s_bits[k >> 5];
+        if ((w >> (k & 31)) & 1u)
+            kl[s_prefix[k >> 5] + __popc(w & ((1u << (k & 31)) - 1u))] = (uint16_t)k;
+    }
+    for (uint32_t j = nk + tid; j < nk_pad; j += 256)
+        kl[j] = 0; // padding steps multiply an all-zero A column: exact no-ops
+    if (tid == 0)
+        p.n_k[tile] = nk_pad;
+
+    // pass 2: zero the tile's A region, then scatter the values
+    float *a = p.a_tiles + tile * ((size_t)kHop * kBM);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t e = tid; e < nk_pad * (kBM / 4); e += 256)
+        reinterpret_cast<float4 *>(a)[e] = z;
+    __syncthreads();
+    for (uint32_t r = warp; r < rows_here; r += 8)
+    {
+        const uint64_t row = p.active_rows[tile * kBM + r];
+        const uint64_t b = p.pair_off[row];
+        const uint32_t n = (uint32_t)(p.pair_off[row + 1] - b);
+        const glc_pair *pr = p.pairs + b;
+        const float scale = fmaxf(p.scales[row], 1e-12f); // src/codec.rs:653
+        // "later duplicates overwrite" (src/codec.rs:659-665): the parallel scatter is only safe when
+        // the indices are strictly ascending (what the encoder emits); otherwise lane 0 replays in order.
+        bool ascending = true;
+        for (uint32_t j = lane; j + 1 < n; j += 32)
+            ascending = ascending && (pr[j].idx < pr[j + 1].idx);
+        ascending = __all_sync(0xffffffffu, ascending);
+        auto put = [&](uint32_t j) {
+            const glc_pair q = pr[j];
+            if (q.idx < kHop)
+            {
+                const uint32_t w = s_bits[q.idx >> 5];
+                const uint32_t pos = s_prefix[q.idx >> 5] + __popc(w & ((1u << (q.idx & 31)) - 1u));
+                a[(size_t)(pos / kKC) * (kKC * kBM) + (pos % kKC) * kBM + r] =
+                    __fmul_rn(__fdiv_rn((float)q.q, 32768.0f), scale);
+            }
+        };
+        if (ascending)
+            for (uint32_t j = lane; j < n; j += 32)
+                put(j);
+        else if (lane == 0)
+            for (uint32_t j = 0; j < n; ++j)
+                put(j);
+    }
 }
 
 // ---- overlap-add + interleave: one thread per output value ----
@@ -353,7 +435,10 @@ __device__ __forceinline__ float block_value(const OlaLaunch &p, const DecFileDe
             return __fdiv_rn((float)p.raw[b + si], 32767.0f);
         return 0.0f;
     }
-    return __ldg(p.blocks + (fd.first_row + lf * fd.channels + c) * kFrame + i);
+    const int32_t slot = p.row_slot[fd.first_row + lf * fd.channels + c];
+    if (slot < 0)
+        return 0.0f; // no coefficients: (0 * norm) * window[i] = +0.0
+    return __ldg(p.blocks + (size_t)slot * kFrame + i);
 }
 
 __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
@@ -478,7 +563,11 @@ cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s)
 {
     if (p.n_rows == 0)
         return cudaSuccess;
-    dequant_kernel<<<(unsigned)((p.n_rows + 7) / 8), 256, 0, s>>>(p);
+    const unsigned grid = (unsigned)((p.n_rows + 255) / 256);
+    row_flag_kernel<<<grid, 256, 0, s>>>(p);
+    scan_kernel<<<1, kScanThreads, 0, s>>>(p.flags, p.slot_off, p.n_rows);
+    row_scatter_kernel<<<grid, 256, 0, s>>>(p);
+    dequant_tile_kernel<<<(unsigned)((p.n_rows + kBM - 1) / kBM), 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

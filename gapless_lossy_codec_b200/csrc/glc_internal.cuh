@@ -58,7 +58,6 @@ void free_host_tables(HostTables *t);
 void build_host_perceptual(uint32_t sample_rate, HostPerceptual *p);
 // Re-tile the cosine table for the two transform kernels: [n_block][stage][kKC][kBN]
 void tile_table_for_mdct(const float *cos_tab, float *out);  // rows = i (2048), cols = k (1024)
-void tile_table_for_imdct(const float *cos_tab, float *out); // rows = k (1024), cols = i (2048)
 
 // Device-side perceptual model, passed by value-pointer to the quantize/pack kernel.
 struct DevPerceptual
@@ -81,24 +80,27 @@ struct MdctLaunch
     const FileDesc *files;
     uint32_t n_files;
     uint64_t row_begin, row_end; // rows (frame-channels) of the batch handled by this launch
-    const float *tab_tiled;
+    const float *tab_tiled;      // [n_block][stage][kKC][kBN]
     const float *window;
     float norm;
-    float *coefs; // [n_rows][1024], indexed by absolute row
-    int variant;  // 0 scalar FMUL/FADD, 1/2 packed f32x2
+    float *coefs;   // [n_rows][1024], indexed by absolute row
+    float *a_tiles; // scratch for the windowed A operand: mdct_a_tile_floats(row_end - row_begin) floats
 };
-cudaError_t launch_mdct_exact(const MdctLaunch &p, cudaStream_t s);
+size_t mdct_a_tile_floats(uint64_t n_rows);
+cudaError_t launch_window_tiles(const MdctLaunch &p, cudaStream_t s); // PCM -> a_tiles (padding + window)
+cudaError_t launch_mdct_exact(const MdctLaunch &p, cudaStream_t s);   // a_tiles x table -> coefs
 
 struct ImdctLaunch
 {
-    const float *coefs;        // dense [n_rows][1024]
-    const uint32_t *stage_mask;// [ceil(n_rows/kBM)] bit s set = some row has a non-zero in k-chunk s
-    uint64_t row_begin, row_end; // row_begin must be a multiple of kBM
-    const float *tab_tiled;
+    const float *a_tiles;    // [tile][stage][kKC][kBM] compacted dequantised coefficients (dequant_tile_kernel)
+    const uint16_t *klist;   // [tile][1024]
+    const uint32_t *n_k;     // [tile] reduction length (multiple of kKC)
+    const uint32_t *n_tiles; // device-side number of live tiles
+    uint64_t max_slots;      // worst-case number of compacted rows (sizes the grid and `blocks`)
+    const float *tab;        // natural layout [1024][2048]
     const float *window;
     float norm;
-    float *blocks; // [n_rows][2048] windowed IMDCT output
-    int variant;
+    float *blocks; // [slot][2048] windowed IMDCT output
 };
 cudaError_t launch_imdct_exact(const ImdctLaunch &p, cudaStream_t s);
 
@@ -138,16 +140,27 @@ struct GatherLaunch
 };
 cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s);
 
+// Decode front end: which rows go through the IMDCT at all (sparse frames with at least one pair),
+// their compaction into tiles of kBM rows, and per tile the ascending union of coefficient indices.
 struct DequantLaunch
 {
     const glc_pair *pairs;
     const uint64_t *pair_off; // [n_rows+1]
     const float *scales;
+    const uint8_t *is_raw;    // [n_frames_total]
+    const struct DecFileDesc *files;
+    uint32_t n_files;
     uint64_t n_rows;
-    float *coefs;         // [n_rows][1024], zero-filled here
-    uint32_t *stage_mask; // [ceil(n_rows/kBM)], zero-filled by caller
+    uint32_t *flags;          // [n_rows]   1 = row is transformed
+    uint64_t *slot_off;       // [n_rows+1] exclusive scan of flags
+    int32_t *row_slot;        // [n_rows]   compacted slot or -1
+    uint32_t *active_rows;    // [n_rows]   slot -> row
+    uint32_t *n_tiles;        // [1]
+    uint16_t *klist;          // [max_tiles][1024]
+    uint32_t *n_k;            // [max_tiles]
+    float *a_tiles;           // [max_tiles][1024][kBM]
 };
-cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s);
+cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s); // flags -> scan -> scatter -> tiles
 
 // One encoded stream inside a batched decode.
 struct DecFileDesc
@@ -162,7 +175,8 @@ struct DecFileDesc
 
 struct OlaLaunch
 {
-    const float *blocks;      // [n_rows][2048] windowed IMDCT output
+    const float *blocks;      // [slot][2048] windowed IMDCT output
+    const int32_t *row_slot;  // [n_rows] slot of a row in `blocks`, -1 = all-zero block
     const uint8_t *is_raw;    // [n_frames_total]
     const uint64_t *raw_off;  // [n_frames_total+1]
     const int16_t *raw;

@@ -32,7 +32,7 @@ extern "C" {
 #define GLC_FRAME_SIZE 2048u      /* src/codec.rs:15 */
 #define GLC_HOP_SIZE 1024u        /* src/codec.rs:16 */
 #define GLC_FRAMES_PER_CHUNK 500u /* src/codec.rs:18 */
-#define GLC_ABI_VERSION 1u
+#define GLC_ABI_VERSION 2u
 
 typedef enum glc_status
 {
@@ -104,9 +104,10 @@ glc_status glc_device_count(int *count);
  * host libm (MdctTables::new, src/codec.rs:326-356) and uploads them. */
 glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out);
 void glc_ctx_destroy(glc_ctx *ctx);
-/* Tuning knobs (defaults are the measured best): gemm_variant 0 = scalar FMUL+FADD, 1/2 = packed
- * f32x2 forms (all bit-identical); wave_frames = frames per H2D/compute pipeline wave (0 = keep). */
-glc_status glc_ctx_set_tuning(glc_ctx *ctx, int gemm_variant, uint64_t wave_frames);
+/* Tuning knobs: `reserved` is ignored (it selected packed f32x2 kernel variants that measured no
+ * faster than scalar FMUL+FADD and were removed); wave_rows = frame-channel rows per encode
+ * pipeline wave, 0 = automatic (multiples of 37 row tiles). */
+glc_status glc_ctx_set_tuning(glc_ctx *ctx, int reserved, uint64_t wave_rows);
 /* Pinned host memory for callers that want zero-staging transfers (optional). */
 glc_status glc_host_alloc(glc_ctx *ctx, size_t bytes, void **out);
 void glc_host_free(glc_ctx *ctx, void *p);
@@ -177,17 +178,19 @@ glc_status glc_encoded_from_bincode(glc_ctx *ctx, const uint8_t *bytes, uint64_t
 /* Kernel ids for glc_stats. */
 enum
 {
-    GLC_K_MDCT_EXACT = 0,   /* fused window + direct MDCT (dominant encode kernel) */
+    GLC_K_MDCT_EXACT = 0,   /* direct-form MDCT contraction (dominant encode kernel) */
     GLC_K_QUANT_PACK = 1,   /* scale, masking thresholds, quantize, ordered compaction, raw decision */
     GLC_K_SCAN = 2,
     GLC_K_GATHER = 3,       /* stream compaction + raw-PCM frames */
-    GLC_K_DEQUANT = 4,      /* sparse -> dense coefficient rows */
+    GLC_K_DEQUANT = 4,      /* row selection, per-tile index union, sparse -> compacted A tiles (4 launches) */
     GLC_K_IMDCT_EXACT = 5,  /* direct IMDCT + synthesis window (dominant decode kernel) */
     GLC_K_OLA = 6,          /* raw frames, overlap-add, interleave */
     GLC_K_FLAC_BLOCK = 7,   /* one CTA per FLAC block */
     GLC_K_FLAC_GATHER = 8,
     GLC_K_MISC = 9,
-    GLC_K_COUNT = 10
+    GLC_K_WINDOW_TILE = 10, /* padding + window -> tiled A operand of the MDCT */
+    GLC_K_RESERVED = 11,
+    GLC_K_COUNT = 12
 };
 
 typedef struct glc_stats

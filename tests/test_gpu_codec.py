@@ -51,14 +51,34 @@ def test_encode_decode_bit_exact(gpu_ctx, name, gen, ch, sr):
     _roundtrip_case(gpu_ctx, gen(), ch, sr, name)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
-def test_gemm_variants_identical(gpu_ctx, variant):
-    """scalar FMUL/FADD and the two packed f32x2 forms must give the same bits."""
+@pytest.mark.parametrize("wave_rows", [128, 1000, 4736, 0])
+def test_wave_size_does_not_change_bits(gpu_ctx, wave_rows):
+    """the encode pipeline is cut into waves of frames; any cut must give the same stream."""
     try:
-        gpu_ctx.set_tuning(variant, 0)
-        _roundtrip_case(gpu_ctx, signals.music_like(44100, 2, 1.5), 2, 44100, f"variant{variant}")
+        gpu_ctx.set_tuning(0, wave_rows)
+        _roundtrip_case(gpu_ctx, signals.music_like(44100, 2, 1.5), 2, 44100, f"wave_rows{wave_rows}")
+        _roundtrip_case(gpu_ctx, signals.sweep(100, 8000, 48000, 6, 0.4), 6, 48000, f"6ch wave_rows{wave_rows}")
     finally:
-        gpu_ctx.set_tuning(-1, 0)
+        gpu_ctx.set_tuning(0, 0)
+
+
+def test_sparse_union_decode_cases(gpu_ctx):
+    """the IMDCT reduces over the union of coefficient indices of 128-row tiles: exercise tiles with a
+    single index, tiles mixing raw / empty / dense rows, and more than one tile."""
+    from gapless_lossy_codec_b200 import Decoder
+
+    x = np.concatenate([signals.sine(440, 44100, 1, 1.0), np.zeros(20000, np.float32),
+                        signals.white_noise(44100, 1, 0.5, 3), signals.music_like(44100, 1, 2.0)])
+    _roundtrip_case(gpu_ctx, x, 1, 44100, "mono mixed (4 tiles)")
+    ref = oracle.encode(signals.sine(1000, 44100, 2, 0.5), 2, 44100)
+    # keep exactly one coefficient per row
+    keep = ref.pair_offset[:-1][ref.nnz > 0].astype(np.int64)
+    ref.pair_idx, ref.pair_q = ref.pair_idx[keep], ref.pair_q[keep]
+    ref.nnz = (ref.nnz > 0).astype(np.uint32)
+    ref.pair_offset = np.concatenate([[0], np.cumsum(ref.nnz)]).astype(np.uint64)
+    pcm = Decoder(2, 44100, gpu_ctx).decode(to_product(ref))
+    assert_pcm_bits_equal(pcm, oracle.decode(ref), "one coefficient per row")
+    assert_pcm_bits_equal(pcm, oracle.decode(ref, literal_imdct=True), "vs the reference's dense IMDCT loop")
 
 
 @pytest.mark.parametrize("n", [513, 514, 1023, 1024, 1025, 1535, 1536, 1537, 2048, 4097])
