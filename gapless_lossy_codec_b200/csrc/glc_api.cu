@@ -247,7 +247,7 @@ struct glc_ctx
 {
     int device;
     glc_mode mode;
-    cudaStream_t compute, copy;
+    cudaStream_t compute, copy, d2h;
     cudaEvent_t t0, t1;
     HostTables host;
     float *d_tab_mdct, *d_tab_imdct, *d_window;
@@ -364,6 +364,7 @@ extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
     c->flush_floats = 0;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->t0));
     CUDA_TRY(cudaEventCreate(&c->t1));
     // tables: host libm -> tiled copies -> device
@@ -406,6 +407,7 @@ extern "C" void glc_ctx_destroy(glc_ctx *c)
     cudaEventDestroy(c->t1);
     cudaStreamDestroy(c->compute);
     cudaStreamDestroy(c->copy);
+    cudaStreamDestroy(c->d2h);
     delete c;
 }
 
@@ -495,6 +497,7 @@ extern "C" glc_status glc_ctx_sync(glc_ctx *c)
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->copy));
     CUDA_TRY(cudaStreamSynchronize(c->compute));
+    CUDA_TRY(cudaStreamSynchronize(c->d2h));
     return GLC_OK;
 }
 
@@ -699,6 +702,57 @@ static bool is_device_accessible_host(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
+// Contiguous frame ranges of a batch ("waves"): f0..f1 frames, r0..r1 rows.  Waves are sized in
+// multiples of 37 row tiles so that the MDCT grids fill every resident CTA slot (see encode_core).
+struct Wave
+{
+    uint64_t f0, f1, r0, r1;
+};
+
+template <typename Desc>
+static std::vector<Wave> plan_waves(const std::vector<Desc> &files, uint64_t tot_frames, uint64_t tot_rows,
+                                    uint64_t target_rows, uint64_t *max_wave_rows)
+{
+    const uint32_t n_files = (uint32_t)files.size();
+    auto row_of_frame = [&](uint64_t fr) -> uint64_t {
+        if (fr >= tot_frames)
+            return tot_rows;
+        uint32_t lo = 0, hi = n_files - 1;
+        while (lo < hi)
+        {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (files[mid].first_frame <= fr)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        return files[lo].first_row + (fr - files[lo].first_frame) * files[lo].channels;
+    };
+    std::vector<Wave> waves;
+    uint64_t mx = 0, f = 0;
+    while (f < tot_frames)
+    {
+        const uint64_t r0 = row_of_frame(f);
+        uint64_t lo = f + 1, hi = tot_frames; // largest f1 whose rows fit the target (at least one frame)
+        while (lo < hi)
+        {
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (row_of_frame(mid) - r0 <= target_rows)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        Wave w{f, lo, r0, row_of_frame(lo)};
+        mx = std::max(mx, w.r1 - w.r0);
+        waves.push_back(w);
+        f = lo;
+    }
+    *max_wave_rows = mx;
+    return waves;
+}
+
+static const uint64_t kRowQuantum = 37ull * kBM;
+
 // ------------------------------------------------- device-resident objects
 
 struct glc_dev_pcm
@@ -880,50 +934,11 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     // resident slot then runs the same number of CTAs and no partial "CTA wave" idles the GPU.
     // Host input: small waves so that the H2D of wave w+1 hides behind the MDCT of wave w.
     // Device-resident input: large waves (fewer launches, scratch still bounded).
-    const uint64_t kRowQuantum = 37ull * kBM;
     uint64_t target_rows = kRowQuantum * (host_pcm ? 4 : 32);
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1); // explicit tuning: rows per wave
     uint64_t max_wave_rows = 0;
-    struct Wave
-    {
-        uint64_t f0, f1, r0, r1;
-    };
-    std::vector<Wave> waves;
-    {
-        auto row_of_frame = [&](uint64_t fr) -> uint64_t {
-            if (fr >= tot_frames)
-                return tot_rows;
-            uint32_t lo = 0, hi = n_files - 1;
-            while (lo < hi)
-            {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (files[mid].first_frame <= fr)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            return files[lo].first_row + (fr - files[lo].first_frame) * files[lo].channels;
-        };
-        uint64_t f = 0;
-        while (f < tot_frames)
-        {
-            const uint64_t r0 = row_of_frame(f);
-            uint64_t lo = f + 1, hi = tot_frames; // largest f1 whose rows fit the target (at least one frame)
-            while (lo < hi)
-            {
-                const uint64_t mid = (lo + hi + 1) >> 1;
-                if (row_of_frame(mid) - r0 <= target_rows)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            Wave w{f, lo, r0, row_of_frame(lo)};
-            max_wave_rows = std::max(max_wave_rows, w.r1 - w.r0);
-            waves.push_back(w);
-            f = lo;
-        }
-    }
+    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows);
     CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
     float *d_atiles = nullptr;
     CUDA_TRY(dmalloc(&d_atiles, mdct_a_tile_floats(max_wave_rows), cs));
@@ -1273,18 +1288,28 @@ static glc_status validate_encoded(const glc_encoded *e, uint32_t idx)
     return GLC_OK;
 }
 
-struct DecodeOut
+// Host side of a decode whose streams and output live in host memory: per wave, the pairs / raw
+// frames go up on the copy stream and the finished PCM comes down on the d2h stream while the
+// compute stream works on the waves in between.
+struct DecodeHostIO
 {
-    float *d_out;
-    uint64_t total_out;
-    std::vector<DecFileDesc> files;
+    const glc_encoded *const *enc;  // [n_files]
+    const uint64_t *h_pair_off;     // [rows+1] batch-wide exclusive scan (host copy)
+    const uint64_t *h_raw_off;      // [frames+1]
+    float *const *h_out;            // [n_files] pinned outputs
+    const uint64_t *win_off;        // [n_files] first untrimmed value that is kept (gapless trim)
+    const uint64_t *win_len;        // [n_files] number of values kept
+    glc_pair *d_pairs;              // device arrays being filled wave by wave
+    int16_t *d_raw;
 };
 
-// Device part of a batched decode.  The stream arrays are already on the device.
+// Device part of a batched decode.  With io == nullptr the stream arrays are already on the device
+// and the output stays there.
 static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files, uint64_t tot_rows,
                               uint64_t tot_frames, uint64_t total_out, const uint8_t *d_is_raw,
                               const uint64_t *d_pair_off, const glc_pair *d_pairs, const float *d_scales,
-                              const uint64_t *d_raw_off, const int16_t *d_raw, float **d_out_ret)
+                              const uint64_t *d_raw_off, const int16_t *d_raw, const DecodeHostIO *io,
+                              float **d_out_ret)
 {
     cudaStream_t cs = c->compute;
     const uint32_t n_files = (uint32_t)files.size();
@@ -1294,75 +1319,181 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     uint64_t *d_slot_off = nullptr;
     int32_t *d_row_slot = nullptr;
     uint16_t *d_klist = nullptr;
-    const uint64_t max_tiles = (tot_rows + kBM - 1) / kBM;
     PhaseTrace tr("decode", cs);
+
+    uint64_t target_rows = kRowQuantum * (io ? 4 : 32);
+    if (c->wave_frames)
+        target_rows = std::max<uint64_t>(c->wave_frames, 1);
+    uint64_t max_wave_rows = 0;
+    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows);
+    const uint64_t wave_tiles = (max_wave_rows + kBM - 1) / kBM;
+
     CUDA_TRY(dmalloc(&d_files, n_files, cs));
     CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(DecFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
     c->stats.h2d_bytes += sizeof(DecFileDesc) * n_files;
-    // worst-case sizes (every row transformed, every k present): the live counts stay on the device,
-    // so the decode needs no host round trip
-    CUDA_TRY(dmalloc(&d_atiles, max_tiles * kHop * kBM, cs));
-    CUDA_TRY(dmalloc(&d_blocks, max_tiles * kBM * kFrame, cs));
-    CUDA_TRY(dmalloc(&d_flags, tot_rows, cs));
-    CUDA_TRY(dmalloc(&d_slot_off, tot_rows + 1, cs));
+    // Worst-case sizes (every row transformed, every k present); the live counts stay on the device,
+    // so the decode needs no host round trip.  `blocks` holds every row of the batch (+1 tile of
+    // slack for the clipped last tile of a wave) because hop h needs frames h-1 and h.
+    CUDA_TRY(dmalloc(&d_atiles, wave_tiles * kHop * kBM, cs));
+    CUDA_TRY(dmalloc(&d_blocks, (tot_rows + kBM) * kFrame, cs));
+    CUDA_TRY(dmalloc(&d_flags, max_wave_rows, cs));
+    CUDA_TRY(dmalloc(&d_slot_off, max_wave_rows + 1, cs));
     CUDA_TRY(dmalloc(&d_row_slot, tot_rows, cs));
-    CUDA_TRY(dmalloc(&d_active, tot_rows, cs));
+    CUDA_TRY(dmalloc(&d_active, max_wave_rows, cs));
     CUDA_TRY(dmalloc(&d_ntiles, 1, cs));
-    CUDA_TRY(dmalloc(&d_nk, max_tiles, cs));
-    CUDA_TRY(dmalloc(&d_klist, max_tiles * kHop, cs));
+    CUDA_TRY(dmalloc(&d_nk, wave_tiles, cs));
+    CUDA_TRY(dmalloc(&d_klist, wave_tiles * kHop, cs));
     CUDA_TRY(dmalloc(&d_out, total_out, cs));
     tr.mark("alloc");
+
+    auto out_index = [&](uint64_t fr) -> uint64_t { // first output value that needs frame `fr`
+        if (fr >= tot_frames)
+            return total_out;
+        uint32_t lo = 0, hi = n_files - 1;
+        while (lo < hi)
+        {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (files[mid].first_frame <= fr)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        return files[lo].out_off + (fr - files[lo].first_frame) * kHop * files[lo].channels;
+    };
+
+    std::vector<cudaEvent_t> used_events;
+    if (io)
     {
-        LaunchScope ls(c, GLC_K_DEQUANT, cs, 4);
-        DequantLaunch q{};
-        q.pairs = d_pairs;
-        q.pair_off = d_pair_off;
-        q.scales = d_scales;
-        q.is_raw = d_is_raw;
-        q.files = d_files;
-        q.n_files = n_files;
-        q.n_rows = tot_rows;
-        q.flags = d_flags;
-        q.slot_off = d_slot_off;
-        q.row_slot = d_row_slot;
-        q.active_rows = d_active;
-        q.n_tiles = d_ntiles;
-        q.klist = d_klist;
-        q.n_k = d_nk;
-        q.a_tiles = d_atiles;
-        CUDA_TRY(launch_dequant(q, cs));
+        // the copy stream writes buffers that were handed out in compute-stream order
+        cudaEvent_t ev = get_event(c);
+        used_events.push_back(ev);
+        CUDA_TRY(cudaEventRecord(ev, cs));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy, ev, 0));
     }
-    tr.mark("dequant");
+    for (size_t wi = 0; wi < waves.size(); ++wi)
     {
-        LaunchScope ls(c, GLC_K_IMDCT_EXACT, cs);
-        ImdctLaunch m{};
-        m.a_tiles = d_atiles;
-        m.klist = d_klist;
-        m.n_k = d_nk;
-        m.n_tiles = d_ntiles;
-        m.max_slots = max_tiles * kBM;
-        m.tab = c->d_tab_imdct;
-        m.window = c->d_window;
-        m.norm = c->host.norm;
-        m.blocks = d_blocks;
-        CUDA_TRY(launch_imdct_exact(m, cs));
+        const Wave &w = waves[wi];
+        if (io)
+        {
+            // H2D of this wave's pairs and raw frames, file segment by file segment
+            bool any = false;
+            for (uint32_t i = 0; i < n_files; ++i)
+            {
+                const DecFileDesc &f = files[i];
+                const uint64_t fr_rows = f.n_frames * f.channels;
+                const uint64_t a = std::max(w.r0, f.first_row), b = std::min(w.r1, f.first_row + fr_rows);
+                if (a < b)
+                {
+                    const uint64_t p0 = io->h_pair_off[a], p1 = io->h_pair_off[b], pf = io->h_pair_off[f.first_row];
+                    if (p1 > p0)
+                    {
+                        CUDA_TRY(cudaMemcpyAsync(io->d_pairs + p0, io->enc[i]->pairs + (p0 - pf), (p1 - p0) * 4,
+                                                 cudaMemcpyHostToDevice, c->copy));
+                        c->stats.h2d_bytes += (p1 - p0) * 4;
+                        any = true;
+                    }
+                }
+                const uint64_t fa = std::max(w.f0, f.first_frame), fb = std::min(w.f1, f.first_frame + f.n_frames);
+                if (fa < fb)
+                {
+                    const uint64_t q0 = io->h_raw_off[fa], q1 = io->h_raw_off[fb], qf = io->h_raw_off[f.first_frame];
+                    if (q1 > q0)
+                    {
+                        CUDA_TRY(cudaMemcpyAsync(io->d_raw + q0, io->enc[i]->raw + (q0 - qf), (q1 - q0) * 2,
+                                                 cudaMemcpyHostToDevice, c->copy));
+                        c->stats.h2d_bytes += (q1 - q0) * 2;
+                        any = true;
+                    }
+                }
+            }
+            if (any || wi == 0)
+            {
+                cudaEvent_t ev = get_event(c);
+                used_events.push_back(ev);
+                CUDA_TRY(cudaEventRecord(ev, c->copy));
+                CUDA_TRY(cudaStreamWaitEvent(cs, ev, 0));
+            }
+        }
+        {
+            LaunchScope ls(c, GLC_K_DEQUANT, cs, 4);
+            DequantLaunch q{};
+            q.pairs = d_pairs;
+            q.pair_off = d_pair_off;
+            q.scales = d_scales;
+            q.is_raw = d_is_raw;
+            q.files = d_files;
+            q.n_files = n_files;
+            q.row_begin = w.r0;
+            q.row_end = w.r1;
+            q.slot_base = w.r0; // slots <= rows, so a wave's slots fit behind its first row index
+            q.row_slot = d_row_slot;
+            q.flags = d_flags;
+            q.slot_off = d_slot_off;
+            q.active_rows = d_active;
+            q.n_tiles = d_ntiles;
+            q.klist = d_klist;
+            q.n_k = d_nk;
+            q.a_tiles = d_atiles;
+            CUDA_TRY(launch_dequant(q, cs));
+        }
+        {
+            LaunchScope ls(c, GLC_K_IMDCT_EXACT, cs);
+            ImdctLaunch m{};
+            m.a_tiles = d_atiles;
+            m.klist = d_klist;
+            m.n_k = d_nk;
+            m.n_tiles = d_ntiles;
+            m.max_slots = (w.r1 - w.r0 + kBM - 1) / kBM * kBM;
+            m.tab = c->d_tab_imdct;
+            m.window = c->d_window;
+            m.norm = c->host.norm;
+            m.blocks = d_blocks + w.r0 * kFrame;
+            CUDA_TRY(launch_imdct_exact(m, cs));
+        }
+        const uint64_t o0 = out_index(w.f0), o1 = out_index(w.f1);
+        {
+            LaunchScope ls(c, GLC_K_OLA, cs);
+            OlaLaunch o{};
+            o.blocks = d_blocks;
+            o.row_slot = d_row_slot;
+            o.is_raw = d_is_raw;
+            o.raw_off = d_raw_off;
+            o.raw = d_raw;
+            o.files = d_files;
+            o.n_files = n_files;
+            o.out_begin = o0;
+            o.out_end = o1;
+            o.out = d_out;
+            CUDA_TRY(launch_ola(o, cs));
+        }
+        if (io)
+        {
+            // D2H of the finished range, clipped to every file's gapless window
+            cudaEvent_t ev = get_event(c);
+            used_events.push_back(ev);
+            CUDA_TRY(cudaEventRecord(ev, cs));
+            CUDA_TRY(cudaStreamWaitEvent(c->d2h, ev, 0));
+            for (uint32_t i = 0; i < n_files; ++i)
+            {
+                const uint64_t w0 = files[i].out_off + io->win_off[i], w1 = w0 + io->win_len[i];
+                const uint64_t a = std::max(o0, w0), b = std::min(o1, w1);
+                if (a < b)
+                {
+                    CUDA_TRY(cudaMemcpyAsync(io->h_out[i] + (a - w0), d_out + a, (b - a) * 4, cudaMemcpyDeviceToHost,
+                                             c->d2h));
+                    c->stats.d2h_bytes += (b - a) * 4;
+                }
+            }
+        }
     }
-    tr.mark("imdct");
+    tr.mark("waves");
+    if (io)
     {
-        LaunchScope ls(c, GLC_K_OLA, cs);
-        OlaLaunch o{};
-        o.blocks = d_blocks;
-        o.row_slot = d_row_slot;
-        o.is_raw = d_is_raw;
-        o.raw_off = d_raw_off;
-        o.raw = d_raw;
-        o.files = d_files;
-        o.n_files = n_files;
-        o.total_out = total_out;
-        o.out = d_out;
-        CUDA_TRY(launch_ola(o, cs));
+        CUDA_TRY(cudaStreamSynchronize(c->d2h));
+        CUDA_TRY(cudaStreamSynchronize(cs));
     }
-    tr.mark("ola");
+    for (cudaEvent_t e : used_events)
+        c->ev_free.push_back(e);
     dfree(d_atiles, cs);
     dfree(d_blocks, cs);
     dfree(d_flags, cs);
@@ -1374,7 +1505,6 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     dfree(d_klist, cs);
     dfree(d_files, cs);
     tr.mark("free");
-    (void)tot_frames;
     *d_out_ret = d_out;
     return GLC_OK;
 }
@@ -1422,24 +1552,47 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
         npairs += e->n_frames ? e->pair_offset[r] : 0;
         nraw += e->n_frames ? e->raw_offset[e->n_frames] : 0;
     }
-    // ---- stage the streams: concatenate into pinned buffers, then one H2D each ----
-    uint8_t *h_is_raw = (uint8_t *)c->pool.alloc(frames);
-    uint64_t *h_pair_off = (uint64_t *)c->pool.alloc((rows + 1) * 8);
-    float *h_scales = (float *)c->pool.alloc(rows * 4);
-    uint64_t *h_raw_off = (uint64_t *)c->pool.alloc((frames + 1) * 8);
+    // ---- everything this call owns, released on every exit path ----
+    std::vector<void *> pinned_tmp, dev_tmp;
+    std::vector<float *> h_out(n_files, nullptr);
+    auto cleanup = [&](bool keep_outputs) {
+        for (void *p : pinned_tmp)
+            c->pool.release(p);
+        for (void *p : dev_tmp)
+            dfree(p, cs);
+        if (!keep_outputs)
+            for (float *p : h_out)
+                if (p)
+                    c->pool.release(p);
+    };
+    auto pin = [&](size_t bytes) -> void * {
+        void *p = c->pool.alloc(bytes);
+        if (p)
+            pinned_tmp.push_back(p);
+        return p;
+    };
+#define DEC_TRY(expr)                                                                                      \
+    do                                                                                                     \
+    {                                                                                                      \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+        {                                                                                                  \
+            cleanup(false);                                                                                \
+            return fail(GLC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                        __LINE__);                                                                         \
+        }                                                                                                  \
+    } while (0)
+
+    // ---- small per-row / per-frame metadata: concatenate into pinned buffers, one H2D each ----
+    uint8_t *h_is_raw = (uint8_t *)pin(frames);
+    uint64_t *h_pair_off = (uint64_t *)pin((rows + 1) * 8);
+    float *h_scales = (float *)pin(rows * 4);
+    uint64_t *h_raw_off = (uint64_t *)pin((frames + 1) * 8);
     if (!h_is_raw || !h_pair_off || !h_scales || !h_raw_off)
+    {
+        cleanup(false);
         return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
-    uint8_t *d_is_raw = nullptr;
-    uint64_t *d_pair_off = nullptr, *d_raw_off = nullptr;
-    glc_pair *d_pairs = nullptr;
-    float *d_scales = nullptr;
-    int16_t *d_raw = nullptr;
-    CUDA_TRY(dmalloc(&d_is_raw, frames, cs));
-    CUDA_TRY(dmalloc(&d_pair_off, rows + 1, cs));
-    CUDA_TRY(dmalloc(&d_scales, rows, cs));
-    CUDA_TRY(dmalloc(&d_raw_off, frames + 1, cs));
-    CUDA_TRY(dmalloc(&d_pairs, npairs, cs));
-    CUDA_TRY(dmalloc(&d_raw, nraw, cs));
+    }
     {
         uint64_t pb = 0, rb = 0;
         for (uint32_t i = 0; i < n_files; ++i)
@@ -1457,82 +1610,99 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
                 h_pair_off[f.first_row + k] = pb + e->pair_offset[k];
                 if (e->pair_offset[k + 1] < e->pair_offset[k] ||
                     e->pair_offset[k + 1] - e->pair_offset[k] != e->nnz[k])
+                {
+                    cleanup(false);
                     return fail(GLC_ERR_CORRUPT, "stream %u: pair_offset/nnz mismatch at row %llu", i,
                                 (unsigned long long)k);
+                }
             }
             for (uint64_t k = 0; k < e->n_frames; ++k)
             {
                 h_raw_off[f.first_frame + k] = rb + e->raw_offset[k];
-                if (e->raw_offset[k + 1] < e->raw_offset[k])
-                    return fail(GLC_ERR_CORRUPT, "stream %u: raw_offset not monotone", i);
                 const uint64_t rl = e->raw_offset[k + 1] - e->raw_offset[k];
-                if ((e->frame_is_raw[k] != 0) != (rl != 0))
+                if (e->raw_offset[k + 1] < e->raw_offset[k] || (e->frame_is_raw[k] != 0) != (rl != 0))
+                {
+                    cleanup(false);
                     return fail(GLC_ERR_CORRUPT, "stream %u: frame %llu raw flag/length mismatch", i,
                                 (unsigned long long)k);
+                }
             }
-            const uint64_t np = e->pair_offset[r], nr = e->raw_offset[e->n_frames];
-            // payloads go straight from the caller's arrays (pinned when they came from glc_encode)
-            if (np)
-                CUDA_TRY(cudaMemcpyAsync(d_pairs + pb, e->pairs, np * 4, cudaMemcpyHostToDevice, cs));
-            if (nr)
-                CUDA_TRY(cudaMemcpyAsync(d_raw + rb, e->raw, nr * 2, cudaMemcpyHostToDevice, cs));
-            pb += np;
-            rb += nr;
+            pb += e->pair_offset[r];
+            rb += e->raw_offset[e->n_frames];
         }
         h_pair_off[rows] = pb;
         h_raw_off[frames] = rb;
     }
-    CUDA_TRY(cudaMemcpyAsync(d_is_raw, h_is_raw, frames, cudaMemcpyHostToDevice, cs));
-    CUDA_TRY(cudaMemcpyAsync(d_pair_off, h_pair_off, (rows + 1) * 8, cudaMemcpyHostToDevice, cs));
-    CUDA_TRY(cudaMemcpyAsync(d_scales, h_scales, rows * 4, cudaMemcpyHostToDevice, cs));
-    CUDA_TRY(cudaMemcpyAsync(d_raw_off, h_raw_off, (frames + 1) * 8, cudaMemcpyHostToDevice, cs));
-    c->stats.h2d_bytes += frames + (rows + 1) * 8 + rows * 4 + (frames + 1) * 8 + npairs * 4 + nraw * 2;
+    uint8_t *d_is_raw = nullptr;
+    uint64_t *d_pair_off = nullptr, *d_raw_off = nullptr;
+    glc_pair *d_pairs = nullptr;
+    float *d_scales = nullptr;
+    int16_t *d_raw = nullptr;
+    auto dev = [&](auto **pp, size_t count) -> cudaError_t {
+        cudaError_t e = dmalloc(pp, count, cs);
+        if (e == cudaSuccess)
+            dev_tmp.push_back((void *)*pp);
+        return e;
+    };
+    DEC_TRY(dev(&d_is_raw, frames));
+    DEC_TRY(dev(&d_pair_off, rows + 1));
+    DEC_TRY(dev(&d_scales, rows));
+    DEC_TRY(dev(&d_raw_off, frames + 1));
+    DEC_TRY(dev(&d_pairs, npairs));
+    DEC_TRY(dev(&d_raw, nraw));
+    DEC_TRY(cudaMemcpyAsync(d_is_raw, h_is_raw, frames, cudaMemcpyHostToDevice, cs));
+    DEC_TRY(cudaMemcpyAsync(d_pair_off, h_pair_off, (rows + 1) * 8, cudaMemcpyHostToDevice, cs));
+    DEC_TRY(cudaMemcpyAsync(d_scales, h_scales, rows * 4, cudaMemcpyHostToDevice, cs));
+    DEC_TRY(cudaMemcpyAsync(d_raw_off, h_raw_off, (frames + 1) * 8, cudaMemcpyHostToDevice, cs));
+    c->stats.h2d_bytes += frames + (rows + 1) * 8 + rows * 4 + (frames + 1) * 8;
 
-    float *d_out = nullptr;
-    glc_status st = decode_core(c, files, rows, frames, outv, d_is_raw, d_pair_off, d_pairs, d_scales, d_raw_off,
-                                d_raw, &d_out);
-    if (st == GLC_OK)
+    // ---- outputs: the gapless trim is a window on each file's untrimmed stream ----
+    std::vector<uint64_t> win_off(n_files), win_len(n_files);
+    for (uint32_t i = 0; i < n_files; ++i)
     {
-        // D2H with the gapless trim folded into the copy window
-        for (uint32_t i = 0; i < n_files && st == GLC_OK; ++i)
+        const glc_encoded *e = enc[i];
+        const uint64_t untrimmed = (e->n_frames + 1) * kHop * e->channels;
+        win_off[i] = 0;
+        win_len[i] = untrimmed;
+        if (trim)
+            trim_window(untrimmed, e->encoder_delay, e->original_length, &win_off[i], &win_len[i]);
+        h_out[i] = (float *)c->pool.alloc(win_len[i] * 4);
+        if (!h_out[i])
         {
-            const glc_encoded *e = enc[i];
-            const uint64_t untrimmed = (e->n_frames + 1) * kHop * e->channels;
-            uint64_t off = 0, len = untrimmed;
-            if (trim)
-                trim_window(untrimmed, e->encoder_delay, e->original_length, &off, &len);
-            float *h = (float *)c->pool.alloc(len * 4);
-            if (!h)
-            {
-                st = fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
-                break;
-            }
-            if (len)
-            {
-                cudaError_t ce = cudaMemcpyAsync(h, d_out + files[i].out_off + off, len * 4, cudaMemcpyDeviceToHost, cs);
-                if (ce != cudaSuccess)
-                    st = fail(GLC_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(ce));
-            }
-            c->stats.d2h_bytes += len * 4;
-            pcm[i] = h;
-            n_out[i] = len;
+            cleanup(false);
+            return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
         }
     }
-    cudaError_t se = cudaStreamSynchronize(cs);
+    DecodeHostIO io{};
+    io.enc = enc;
+    io.h_pair_off = h_pair_off;
+    io.h_raw_off = h_raw_off;
+    io.h_out = h_out.data();
+    io.win_off = win_off.data();
+    io.win_len = win_len.data();
+    io.d_pairs = d_pairs;
+    io.d_raw = d_raw;
+    float *d_out = nullptr;
+    glc_status st = decode_core(c, files, rows, frames, outv, d_is_raw, d_pair_off, d_pairs, d_scales, d_raw_off,
+                                d_raw, &io, &d_out);
+    cudaError_t se = cudaStreamSynchronize(c->d2h);
+    if (se == cudaSuccess)
+        se = cudaStreamSynchronize(cs);
+    if (se == cudaSuccess)
+        se = cudaStreamSynchronize(c->copy);
     if (st == GLC_OK && se != cudaSuccess)
         st = fail(GLC_ERR_CUDA, "decode failed: %s", cudaGetErrorString(se));
-    c->pool.release(h_is_raw);
-    c->pool.release(h_pair_off);
-    c->pool.release(h_scales);
-    c->pool.release(h_raw_off);
-    dfree(d_out, cs);
-    dfree(d_is_raw, cs);
-    dfree(d_pair_off, cs);
-    dfree(d_scales, cs);
-    dfree(d_raw_off, cs);
-    dfree(d_pairs, cs);
-    dfree(d_raw, cs);
+    if (d_out)
+        dfree(d_out, cs);
+    cleanup(st == GLC_OK);
+    if (st == GLC_OK)
+        for (uint32_t i = 0; i < n_files; ++i)
+        {
+            pcm[i] = h_out[i];
+            n_out[i] = win_len[i];
+        }
     return st;
+#undef DEC_TRY
 }
 
 extern "C" glc_status glc_decode_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
@@ -1571,7 +1741,7 @@ extern "C" glc_status glc_dev_decode(glc_decoder *dec, const glc_dev_encoded *de
     const uint64_t untrimmed = ((uint64_t)fd.n_frames + 1) * kHop * fd.channels;
     float *d_out = nullptr;
     GLC_TRY(decode_core(c, files, de->n_rows, de->n_frames, untrimmed, de->d_is_raw, de->d_pair_off, de->d_pairs,
-                        de->d_scales, de->d_raw_off, de->d_raw, &d_out));
+                        de->d_scales, de->d_raw_off, de->d_raw, nullptr, &d_out));
     glc_dev_pcm *p = new glc_dev_pcm();
     p->ctx = c;
     p->d = d_out;

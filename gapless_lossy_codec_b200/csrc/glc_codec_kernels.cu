@@ -288,8 +288,9 @@ __global__ void __launch_bounds__(256) gather_raw_kernel(const GatherLaunch p)
 // a slot in the transform.
 __global__ void __launch_bounds__(256) row_flag_kernel(const DequantLaunch p)
 {
-    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= p.n_rows)
+    const uint64_t local = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t row = p.row_begin + local;
+    if (row >= p.row_end)
         return;
     uint32_t lo = 0, hi = p.n_files - 1;
     while (lo < hi)
@@ -302,21 +303,22 @@ __global__ void __launch_bounds__(256) row_flag_kernel(const DequantLaunch p)
     }
     const DecFileDesc &fd = p.files[lo];
     const uint64_t frame = fd.first_frame + (row - fd.first_row) / fd.channels;
-    p.flags[row] = (!p.is_raw[frame] && p.pair_off[row + 1] > p.pair_off[row]) ? 1u : 0u;
+    p.flags[local] = (!p.is_raw[frame] && p.pair_off[row + 1] > p.pair_off[row]) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(256) row_scatter_kernel(const DequantLaunch p)
 {
-    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row == 0)
-        *p.n_tiles = (uint32_t)((p.slot_off[p.n_rows] + kBM - 1) / kBM);
-    if (row >= p.n_rows)
+    const uint64_t local = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t row = p.row_begin + local;
+    if (local == 0)
+        *p.n_tiles = (uint32_t)((p.slot_off[p.row_end - p.row_begin] + kBM - 1) / kBM);
+    if (row >= p.row_end)
         return;
-    if (p.flags[row])
+    if (p.flags[local])
     {
-        const uint32_t slot = (uint32_t)p.slot_off[row];
+        const uint32_t slot = (uint32_t)p.slot_off[local];
         p.active_rows[slot] = (uint32_t)row;
-        p.row_slot[row] = (int32_t)slot;
+        p.row_slot[row] = (int32_t)(p.slot_base + slot);
     }
     else
         p.row_slot[row] = -1;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
     __shared__ uint32_t s_bits[kHop / 32];
     __shared__ uint32_t s_prefix[kHop / 32];
     __shared__ uint32_t s_nk;
-    const uint64_t n_active = p.slot_off[p.n_rows];
+    const uint64_t n_active = p.slot_off[p.row_end - p.row_begin];
     const uint64_t tile = blockIdx.x;
     if (tile * kBM >= n_active)
         return;
@@ -443,8 +445,8 @@ __device__ __forceinline__ float block_value(const OlaLaunch &p, const DecFileDe
 
 __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
 {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.total_out)
+    const uint64_t idx = p.out_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.out_end)
         return;
     uint32_t lo = 0, hi = p.n_files - 1;
     while (lo < hi)
@@ -561,21 +563,22 @@ cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s)
 
 cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s)
 {
-    if (p.n_rows == 0)
+    if (p.row_end <= p.row_begin)
         return cudaSuccess;
-    const unsigned grid = (unsigned)((p.n_rows + 255) / 256);
+    const uint64_t n = p.row_end - p.row_begin;
+    const unsigned grid = (unsigned)((n + 255) / 256);
     row_flag_kernel<<<grid, 256, 0, s>>>(p);
-    scan_kernel<<<1, kScanThreads, 0, s>>>(p.flags, p.slot_off, p.n_rows);
+    scan_kernel<<<1, kScanThreads, 0, s>>>(p.flags, p.slot_off, n);
     row_scatter_kernel<<<grid, 256, 0, s>>>(p);
-    dequant_tile_kernel<<<(unsigned)((p.n_rows + kBM - 1) / kBM), 256, 0, s>>>(p);
+    dequant_tile_kernel<<<(unsigned)((n + kBM - 1) / kBM), 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s)
 {
-    if (p.total_out == 0)
+    if (p.out_end <= p.out_begin)
         return cudaSuccess;
-    ola_kernel<<<(unsigned)((p.total_out + 255) / 256), 256, 0, s>>>(p);
+    ola_kernel<<<(unsigned)((p.out_end - p.out_begin + 255) / 256), 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

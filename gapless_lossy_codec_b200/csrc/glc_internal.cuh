@@ -150,11 +150,13 @@ struct DequantLaunch
     const uint8_t *is_raw;    // [n_frames_total]
     const struct DecFileDesc *files;
     uint32_t n_files;
-    uint64_t n_rows;
-    uint32_t *flags;          // [n_rows]   1 = row is transformed
-    uint64_t *slot_off;       // [n_rows+1] exclusive scan of flags
-    int32_t *row_slot;        // [n_rows]   compacted slot or -1
-    uint32_t *active_rows;    // [n_rows]   slot -> row
+    uint64_t row_begin, row_end; // rows of this wave (absolute batch rows)
+    uint64_t slot_base;       // first slot of this wave in the batch-wide `blocks` array
+    int32_t *row_slot;        // [batch rows] absolute slot of a row or -1 (indexed by absolute row)
+    // wave-local scratch, indexed from 0 = row_begin / tile 0 of the wave:
+    uint32_t *flags;          // [n]   1 = row is transformed
+    uint64_t *slot_off;       // [n+1] exclusive scan of flags
+    uint32_t *active_rows;    // [n]   local slot -> absolute row
     uint32_t *n_tiles;        // [1]
     uint16_t *klist;          // [max_tiles][1024]
     uint32_t *n_k;            // [max_tiles]
@@ -182,7 +184,7 @@ struct OlaLaunch
     const int16_t *raw;
     const DecFileDesc *files;
     uint32_t n_files;
-    uint64_t total_out;       // sum over files of (n_frames+1)*1024*ch
+    uint64_t out_begin, out_end; // range of output values produced by this launch
     float *out;               // per file interleaved, (n_frames+1)*1024*ch values at out_off
 };
 cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s);
