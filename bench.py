@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=3600.0, help="audio seconds per GPU per step")
     ap.add_argument("--ref-seconds", type=float, default=30.0,
                     help="audio seconds per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"],
+                    help="transform mode: exact = bit-exact with the reference (default, parity-gated); "
+                         "fast = FFT-based true MDCT (tolerance class, HBM-roofline showcase)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flac", action="store_true")
     ap.add_argument("--flac-seconds", type=float, default=600.0)
@@ -235,7 +238,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ctx = Context(local_rank)  # raises GlcError when the CUDA library / device is missing: no fallback
+    fast = args.mode == "fast"
+    ctx = Context(local_rank, mode=1 if fast else 0)  # raises GlcError when the CUDA library / device is missing: no fallback
     L = ctx._lib
     chk = _ffi.check
 
@@ -276,6 +280,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         chk(L.glc_decode(dec_h, out, C.byref(p), C.byref(n)))
         got = n.value
         first = float(p[0]) if got else 0.0  # the step's result is read on the host
+        e = out.contents
+        host_step.pairs = int(e.pair_offset[int(e.n_frames) * int(e.channels)]) if e.n_frames else 0
+        host_step.raw = int(e.raw_offset[int(e.n_frames)]) if e.n_frames else 0
         L.glc_free(ctx.handle, p)
         L.glc_encoded_free(ctx.handle, out)
         return got, first
@@ -341,13 +348,28 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     k_n = st["launches"]
     mdct_ms_per_step = k_ms["mdct_exact"] / args.steps
     flops = rows * 2.0 * 1024 * 2048  # non-FMA FP32 lane operations (FMUL + FADD), SURVEY.md 8(d)
-    achieved_tops = flops / (mdct_ms_per_step * 1e-3) / 1e12
+    achieved_tops = flops / (mdct_ms_per_step * 1e-3) / 1e12 if mdct_ms_per_step else 0.0
     hbm_peak, peak_src = load_peaks()
     # algorithmic bytes of the MDCT stage: every new PCM sample once (4096 B per row) + the dense
     # coefficient row it hands to quantize/pack (4096 B per row)
     mdct_bytes = rows * (4096.0 + 4096.0)
-    hbm_gbs = mdct_bytes / (mdct_ms_per_step * 1e-3) / 1e9
-    roofline = {
+    hbm_gbs = mdct_bytes / (mdct_ms_per_step * 1e-3) / 1e9 if mdct_ms_per_step else 0.0
+    if fast:
+        # FAST mode: the fused window + FFT-MDCT + quantise + pack kernel is HBM-bound by design.
+        # Algorithmic bytes per launch: every PCM sample once (4096 B per frame-channel)
+        # + the pairs it emits (4 B each) + scale and count (8 B per frame-channel).
+        fe_ms = k_ms["fast_encode"] / max(k_n["fast_encode"], 1)
+        fe_bytes = rows * 4096.0 + host_step.pairs * 4.0 + rows * 8.0
+        fe_gbs = fe_bytes / (fe_ms * 1e-3) / 1e9
+        roofline = {
+            "kernel": "fast_encode_kernel (fused window + fold + 512-point FFT DCT-IV + thresholds + quantise + ordered pack)",
+            "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fe_gbs / hbm_peak,
+            "peak_source": peak_src, "traffic": None, "launches_per_step": k_n["fast_encode"] / args.steps,
+            "ms_per_launch": fe_ms, "algorithmic_bytes_per_launch": fe_bytes,
+            "kernel_ms_per_step": {k: v / args.steps for k, v in k_ms.items() if v},
+        }
+    else:
+      roofline = {
         "kernel": "exact_gemm_kernel<MDCT> (direct-form MDCT contraction, EXACT mode; operands by TMA bulk copy)",
         "bound": "fp32_issue", "achieved": achieved_tops, "peak": fp32_roof, "unit": "TFLOP/s",
         "frac": achieved_tops / fp32_roof if fp32_roof else None,
@@ -359,7 +381,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                 "peak_source": peak_src, "algorithmic_bytes_per_frame_channel": 8192},
         "kernel_ms_per_step": {k: v / args.steps for k, v in k_ms.items() if v},
-    }
+      }
 
     line = {
         "metric": METRIC, "value": total_secs / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -368,7 +390,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "data": "synthetic",
         "config": {"workload": f"batched encode+decode of {secs:.0f} s synthetic 44.1 kHz stereo PCM per GPU "
                                f"({n_frames} frames, {rows} frame-channels; ~30 % raw-PCM frames)",
-                   "mode": "EXACT (bit-exact with the reference arithmetic)", "sharding": f"by file, {world} rank(s), no collective",
+                   "mode": ("FAST (FFT-based true MDCT, tolerance class -- NOT bit-exact with the reference)" if fast
+                            else "EXACT (bit-exact with the reference arithmetic)"), "sharding": f"by file, {world} rank(s), no collective",
                    "l2": f"inputs larger than L2 ({xp.size * 4 / 1e6:.0f} MB PCM per step vs 126 MB)"},
         "encode_value": total_secs / (enc_ms_max * 1e-3), "decode_value": total_secs / (dec_ms_max * 1e-3),
         "e2e": {"value": total_secs / (e2e_ms * 1e-3), "unit": UNIT,

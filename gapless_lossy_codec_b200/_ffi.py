@@ -19,7 +19,7 @@ STATUS_NAMES = {
     8: "GLC_ERR_CORRUPT", 9: "GLC_ERR_UNSUPPORTED",
 }
 K_NAMES = ["mdct_exact", "quant_pack", "scan", "gather", "dequant", "imdct_exact", "ola",
-           "flac_block", "flac_gather", "misc", "window_tile", "reserved"]
+           "flac_block", "flac_gather", "misc", "window_tile", "fast_encode", "fast_decode"]
 K_COUNT = len(K_NAMES)
 
 

@@ -36,12 +36,15 @@ _ctxs: dict = {}
 class Context:
     """One CUDA device (glc_ctx): streams, pinned pools, device tables."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, mode: int = 0):
+        """mode 0 = GLC_MODE_EXACT (bit-exact with the reference, default); 1 = GLC_MODE_FAST (FFT-based
+        transform, tolerance class)."""
         self._lib = _ffi.load()
         h = C.c_void_p()
-        check(self._lib.glc_ctx_create(device, 0, C.byref(h)))
+        check(self._lib.glc_ctx_create(device, int(mode), C.byref(h)))
         self.handle = h
         self.device = device
+        self.mode = int(mode)
 
     def close(self):
         if self.handle:

@@ -339,8 +339,8 @@ extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
     GLC_TRY(glc_device_count(&n));
     if (device < 0 || device >= n)
         return fail(GLC_ERR_INVALID_ARG, "device %d out of range (have %d)", device, n);
-    if (mode != GLC_MODE_EXACT)
-        return fail(GLC_ERR_UNSUPPORTED, "only GLC_MODE_EXACT is implemented in this build");
+    if (mode != GLC_MODE_EXACT && mode != GLC_MODE_FAST)
+        return fail(GLC_ERR_INVALID_ARG, "unknown transform mode %d", (int)mode);
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -934,14 +934,34 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     // resident slot then runs the same number of CTAs and no partial "CTA wave" idles the GPU.
     // Host input: small waves so that the H2D of wave w+1 hides behind the MDCT of wave w.
     // Device-resident input: large waves (fewer launches, scratch still bounded).
+    const bool fast = c->mode == GLC_MODE_FAST;
     uint64_t target_rows = kRowQuantum * (host_pcm ? 4 : 32);
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1); // explicit tuning: rows per wave
+    if (fast)
+        target_rows = UINT64_MAX; // the fused FFT kernel takes the whole batch in one launch
     uint64_t max_wave_rows = 0;
     const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows);
-    CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
     float *d_atiles = nullptr;
-    CUDA_TRY(dmalloc(&d_atiles, mdct_a_tile_floats(max_wave_rows), cs));
+    uint64_t *d_first_group = nullptr;
+    uint64_t n_groups = 0;
+    if (!fast)
+    {
+        CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
+        CUDA_TRY(dmalloc(&d_atiles, mdct_a_tile_floats(max_wave_rows), cs));
+    }
+    else
+    {
+        std::vector<uint64_t> first_group(n_files);
+        for (uint32_t i = 0; i < n_files; ++i)
+        {
+            first_group[i] = n_groups;
+            n_groups += fast_groups_for(files[i].n_frames, files[i].channels);
+        }
+        CUDA_TRY(dmalloc(&d_first_group, n_files, cs));
+        CUDA_TRY(cudaMemcpyAsync(d_first_group, first_group.data(), 8 * n_files, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaStreamSynchronize(cs)); // first_group is a stack vector
+    }
     tr.mark("alloc");
 
     // H2D plan: file i is needed by the first wave that touches it; copy whole files in order,
@@ -989,6 +1009,27 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
                 CUDA_TRY(cudaEventRecord(ev_copy, c->copy));
                 CUDA_TRY(cudaStreamWaitEvent(cs, ev_copy, 0));
             }
+        }
+        if (fast)
+        {
+            LaunchScope ls(c, GLC_K_FAST_ENCODE, cs);
+            FastEncodeLaunch fe{};
+            fe.pcm_arena = d_arena;
+            fe.files = d_files;
+            fe.n_files = n_files;
+            fe.first_group = d_first_group;
+            fe.group_begin = 0;
+            fe.group_end = n_groups;
+            fe.window = c->d_window;
+            fe.norm = c->host.norm;
+            fe.perc = enc->d_perc;
+            fe.slots = d_slots;
+            fe.nnz = de->d_nnz;
+            fe.scales = de->d_scales;
+            fe.is_raw = de->d_is_raw;
+            fe.raw_len = d_raw_len;
+            CUDA_TRY(launch_fast_encode(fe, cs));
+            continue;
         }
         MdctLaunch m{};
         {
@@ -1069,6 +1110,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     dfree(d_raw_len, cs);
     dfree(d_coefs, cs);
     dfree(d_atiles, cs);
+    dfree(d_first_group, cs);
     dfree(d_files, cs);
     tr.mark("free");
     *out = de;
@@ -1414,6 +1456,25 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
                 CUDA_TRY(cudaStreamWaitEvent(cs, ev, 0));
             }
         }
+        if (c->mode == GLC_MODE_FAST)
+        {
+            LaunchScope ls(c, GLC_K_FAST_DECODE, cs);
+            FastDecodeLaunch fdl{};
+            fdl.pairs = d_pairs;
+            fdl.pair_off = d_pair_off;
+            fdl.scales = d_scales;
+            fdl.is_raw = d_is_raw;
+            fdl.files = d_files;
+            fdl.n_files = n_files;
+            fdl.row_begin = w.r0;
+            fdl.row_end = w.r1;
+            fdl.window = c->d_window;
+            fdl.norm = c->host.norm;
+            fdl.row_slot = d_row_slot;
+            fdl.blocks = d_blocks;
+            CUDA_TRY(launch_fast_decode(fdl, cs));
+        }
+        else
         {
             LaunchScope ls(c, GLC_K_DEQUANT, cs, 4);
             DequantLaunch q{};
@@ -1436,6 +1497,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             q.a_tiles = d_atiles;
             CUDA_TRY(launch_dequant(q, cs));
         }
+        if (c->mode != GLC_MODE_FAST)
         {
             LaunchScope ls(c, GLC_K_IMDCT_EXACT, cs);
             ImdctLaunch m{};

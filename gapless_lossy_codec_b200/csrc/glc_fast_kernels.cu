@@ -1,0 +1,506 @@
+// glc_fast_kernels.cu -- FAST transform mode (GLC_MODE_FAST): FFT-based MDCT / IMDCT fused with the
+// quantiser (encode) and the dequantiser + synthesis window (decode), sm_100a.
+//
+// This is the "fused MDCT+quantize kernel" of BASELINE.json's north_star: window -> fold -> DCT-IV
+// by a 512-point complex FFT (warp-level, register radix butterflies, one shared-memory exchange)
+// -> scale / masking thresholds / quantise / ordered compaction, one pass over the PCM.  It computes
+// the TRUE MDCT, whereas the reference multiplies by an f32 table that is up to 6.85e-4 away from
+// the true basis and accumulates sequentially, so its parity class is
+// TOLERANCE, not bit-exact: EXACT mode (glc_exact_gemm.cu) stays the parity-gated default.  The
+// stream layout, frame counts, gapless metadata and sample counts are identical in both modes.
+//
+// Transform (N = 1024 coefficients from 2N windowed samples b[i] = x[i]*w[i]):
+//   fold      u[m]      = -b[3N/2-1-m] - b[3N/2+m]          m <  N/2
+//             u[N/2+m]  =  b[m]        - b[N-1-m]
+//   DCT-IV    z[n] = (u[2n] + i u[N-1-2n]) * exp(-i pi (4n+1)/(4N)),  Z = FFT_512(z),
+//             y[k] = Z[k] * exp(-i pi k/N),  X[2k] = Re y[k],  X[N-1-2k] = -Im y[k]
+//   (the IMDCT is the transpose: v = DCT-IV(c), then the fold is undone with the same signs)
+// FFT_512 = 16 x 32: n = n1 + 32 n2, k = k2 + 16 k1.  A warp transforms TWO frame-channels at once:
+//   pass 1  lane = n1: 16-point FFT over n2 in registers (one per frame-channel), times
+//           T[k2] = exp(-i pi (4 n1+1)/(4N)) * w512^(n1 k2) (per-lane constants), to shared memory;
+//   pass 2  lane = (frame-channel, k2): 32-point FFT over n1 in registers, post-twiddle, results
+//           to shared memory in natural coefficient order.
+// Compiled with FMA contraction ON (this file only).
+#include "glc_fft_gen.cuh"
+#include "glc_internal.cuh"
+
+namespace glc
+{
+
+namespace
+{
+
+constexpr int kFastThreads = 128;            // 4 warps
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastFcs = 8;                  // frame-channels per CTA (4 pairs)
+constexpr int kXchStride = 33;               // float2 per (fc,k2) row of the exchange buffer (bank skew)
+constexpr int kXchFloat2 = 2 * 16 * kXchStride; // per warp: 2 frame-channels x 16 rows
+constexpr int kCoefStride = 1025;            // floats per frame-channel in the coefficient buffer (bank skew)
+
+struct FastSmem
+{
+    float2 u[kFastFcs][kHop / 2];        // folded + windowed input as (u[2n], u[N-1-2n]) pairs, 32 KiB
+    float2 xch[kFastWarps][kXchFloat2];  // per-warp exchange buffer, reused as coefficient buffer (8448 B each)
+    float inv_w[kHop];
+    float band_base[kFastWarps][kMaxBands];
+    uint8_t band_of[kHop];
+    uint32_t frame_nnz[kFastFcs];
+};
+static_assert(sizeof(float2) * kXchFloat2 >= sizeof(float) * 2 * kCoefStride, "coefficient buffer must fit the exchange buffer");
+
+// per-lane twiddle constants, computed once per thread
+struct LaneTw
+{
+    float2 t[16]; // pass-1 output twiddle for lane n1, k2 = 0..15
+    float2 qb;    // post-twiddle base for k2 = lane & 15, times `norm`
+};
+
+__device__ __forceinline__ void make_lane_tw(LaneTw &tw, int lane, float norm)
+{
+    const int n1 = lane;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2)
+    {
+        // exp(-i pi (4 n1 + 1)/4096) * exp(-2 pi i n1 k2 / 512)
+        const double a = -((4.0 * n1 + 1.0) / 4096.0 + (2.0 * n1 * k2) / 512.0);
+        double s, c;
+        sincospi(a, &s, &c);
+        tw.t[k2] = make_float2((float)c, (float)s);
+    }
+    double s, c;
+    sincospi(-(double)(lane & 15) / 1024.0, &s, &c);
+    tw.qb = make_float2((float)(c * (double)norm), (float)(s * (double)norm));
+}
+
+// DCT-IV of two frame-channels whose (u[2n], u[N-1-2n]) pairs are in u_a / u_b (shared memory).
+// Results (times `norm`) land in coef[0..1023] (first) and coef[kCoefStride..] (second), which
+// alias the warp's exchange buffer.  All 32 lanes must call.
+__device__ __forceinline__ void dct4_pair(const float2 *u_a, const float2 *u_b, const LaneTw &tw, float2 *xch, int lane)
+{
+    using namespace fastfft;
+    // ---- pass 1: lane = n1, 16-point FFT over n2 for each of the two inputs ----
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+    {
+        const float2 *u = f ? u_b : u_a;
+        float re[16], im[16];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2)
+        {
+            const float2 v = u[lane + 32 * n2];
+            re[n2] = v.x * kPreStepRe[n2] - v.y * kPreStepIm[n2];
+            im[n2] = v.x * kPreStepIm[n2] + v.y * kPreStepRe[n2];
+        }
+        fft16(re, im);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2)
+        {
+            const int s = kBitrev16[k2];
+            xch[(f * 16 + k2) * kXchStride + lane] =
+                make_float2(re[s] * tw.t[k2].x - im[s] * tw.t[k2].y, re[s] * tw.t[k2].y + im[s] * tw.t[k2].x);
+        }
+    }
+    __syncwarp();
+    // ---- pass 2: lane = (f, k2), 32-point FFT over n1 ----
+    const int f = lane >> 4, k2 = lane & 15;
+    float re[32], im[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1)
+    {
+        const float2 v = xch[(f * 16 + k2) * kXchStride + n1];
+        re[n1] = v.x;
+        im[n1] = v.y;
+    }
+    fft32(re, im);
+    __syncwarp(); // every lane has its column: the buffer can be overwritten with coefficients
+    float *coef = reinterpret_cast<float *>(xch) + f * kCoefStride;
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1)
+    {
+        const int s = kBitrev32[k1];
+        // post-twiddle exp(-i pi k/N) * norm, k = k2 + 16 k1
+        const float qr = kPostStepRe[k1] * tw.qb.x - kPostStepIm[k1] * tw.qb.y;
+        const float qi = kPostStepRe[k1] * tw.qb.y + kPostStepIm[k1] * tw.qb.x;
+        const float yr = re[s] * qr - im[s] * qi;
+        const float yi = re[s] * qi + im[s] * qr;
+        const int k = k2 + 16 * k1;
+        coef[2 * k] = yr;
+        coef[kHop - 1 - 2 * k] = -yi;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ float warp_max_f(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct GroupGeom
+{
+    uint32_t file;
+    uint32_t n_frames; // frames of this group (<= frames_per_group)
+    uint64_t frame0;   // first frame of the group, local to the file
+};
+
+__device__ __forceinline__ GroupGeom locate_group(const uint64_t *first_group, const FileDesc *files, uint32_t n_files,
+                                                  uint64_t g)
+{
+    uint32_t lo = 0, hi = n_files - 1;
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (first_group[mid] <= g)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    GroupGeom gg;
+    gg.file = lo;
+    const uint32_t ch = files[lo].channels;
+    const uint32_t fpg = kFastFcs / ch ? kFastFcs / ch : 1u;
+    gg.frame0 = (g - first_group[lo]) * fpg;
+    const uint64_t left = files[lo].n_frames - gg.frame0;
+    gg.n_frames = (uint32_t)(left < fpg ? left : fpg);
+    return gg;
+}
+
+// ------------------------------------------------------------------ encode
+
+__global__ void __launch_bounds__(kFastThreads) fast_encode_kernel(const FastEncodeLaunch p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevPerceptual &pm = *p.perc;
+
+    const GroupGeom gg = locate_group(p.first_group, p.files, p.n_files, p.group_begin + blockIdx.x);
+    const FileDesc fd = p.files[gg.file];
+    const uint32_t ch = fd.channels;
+    const uint32_t n_fc = gg.n_frames * ch; // may exceed kFastFcs only when ch > 8 (then processed in rounds)
+
+    for (int k = tid; k < kHop; k += kFastThreads)
+    {
+        sm.inv_w[k] = pm.inv_w[k];
+        sm.band_of[k] = pm.band_of[k];
+    }
+    if (tid < kFastFcs)
+        sm.frame_nnz[tid] = 0;
+    LaneTw tw;
+    make_lane_tw(tw, lane, p.norm);
+    const float *src = p.pcm_arena + fd.pcm_off;
+    const long long len = (long long)fd.len;
+
+    for (uint32_t fc0 = 0; fc0 < n_fc; fc0 += kFastFcs)
+    {
+        const uint32_t fcs_here = min((uint32_t)kFastFcs, n_fc - fc0);
+        __syncthreads();
+        // ---- stage: fold + window, (u[2n], u[N-1-2n]) per n, over the reference's padded signal
+        //      (512 zeros + data + zero tail, src/codec.rs:433-447) ----
+        for (uint32_t e = tid; e < fcs_here * (kHop / 2); e += kFastThreads)
+        {
+            const uint32_t fc = e >> 9, n = e & 511;
+            const uint32_t lf = (fc0 + fc) / ch, c = (fc0 + fc) - lf * ch;
+            const long long base = (long long)((gg.frame0 + lf) * kHop) - kHop / 2; // sample index of i = 0
+            auto smp = [&](int i) -> float {
+                const long long pos = base + i;
+                return (pos >= 0 && pos < len) ? __ldg(src + pos * ch + c) : 0.0f;
+            };
+            // window symmetry w[2047-i] = w[i] leaves two distinct values per n
+            const float wa = __ldg(p.window + 512 + 2 * n);
+            float u0, u1;
+            if (n < 256)
+            {
+                const float wb = __ldg(p.window + 511 - 2 * n);
+                u0 = -smp(1535 - 2 * n) * wa - smp(1536 + 2 * n) * wb;
+                u1 = smp(511 - 2 * n) * wb - smp(512 + 2 * n) * wa;
+            }
+            else
+            {
+                const float wc = __ldg(p.window + 2 * n - 512);
+                u0 = smp(2 * n - 512) * wc - smp(1535 - 2 * n) * wa;
+                u1 = -smp(512 + 2 * n) * wa - smp(2559 - 2 * n) * wc;
+            }
+            sm.u[fc][n] = make_float2(u0, u1);
+        }
+        __syncthreads();
+
+        for (uint32_t pr = warp; pr * 2 < fcs_here; pr += kFastWarps)
+        {
+            const uint32_t fa = pr * 2, fb = min(pr * 2 + 1, fcs_here - 1);
+            dct4_pair(sm.u[fa], sm.u[fb], tw, sm.xch[warp], lane);
+            const uint32_t n_here = (pr * 2 + 1 < fcs_here) ? 2u : 1u;
+            for (uint32_t h = 0; h < n_here; ++h)
+            {
+                const float *coef = reinterpret_cast<const float *>(sm.xch[warp]) + h * kCoefStride;
+                const uint32_t fc = fc0 + fa + h;
+                const uint32_t lf = fc / ch;
+                const uint64_t row = fd.first_row + (gg.frame0 + lf) * ch + (fc - lf * ch);
+                // scale = max|c| .max(1e-10)                                  src/codec.rs:488-489
+                float m = 0.0f;
+#pragma unroll 8
+                for (int t = 0; t < kHop / 32; ++t)
+                    m = fmaxf(m, fabsf(coef[lane + 32 * t]));
+                const float gmax = fmaxf(warp_max_f(m), 1e-10f);
+                const float scale = gmax;
+                // band energies -> per-band base threshold                  src/codec.rs:205-224
+                const int n_bands = pm.n_edges - 1;
+                for (int b0 = 0; b0 < n_bands; b0 += 32)
+                {
+                    const int b = b0 + lane;
+                    int lo = 0, hi = 0;
+                    if (b < n_bands)
+                    {
+                        lo = pm.band_edges[b];
+                        hi = pm.band_edges[b + 1];
+                    }
+                    const bool wide = (hi - lo) > 32;
+                    float acc = 0.0f;
+                    if (!wide)
+                        for (int k = lo; k < hi; ++k)
+                            acc = fmaf(coef[k], coef[k], acc);
+                    unsigned wide_mask = __ballot_sync(0xffffffffu, wide);
+                    while (wide_mask)
+                    {
+                        const int src_lane = __ffs(wide_mask) - 1;
+                        wide_mask &= wide_mask - 1;
+                        const int wlo = __shfl_sync(0xffffffffu, lo, src_lane), whi = __shfl_sync(0xffffffffu, hi, src_lane);
+                        float part = 0.0f;
+                        for (int k = wlo + lane; k < whi; k += 32)
+                            part = fmaf(coef[k], coef[k], part);
+                        part = warp_sum_f(part);
+                        if (lane == src_lane)
+                            acc = part;
+                    }
+                    if (b < n_bands)
+                    {
+                        const float energy = sqrtf(acc / pm.band_cnt[b]);
+                        // thresholds are later multiplied by scale (src/codec.rs:288): fold it in here
+                        sm.band_base[warp][b] = energy * 0.01f * pm.cf * pm.band_pf[b] * scale;
+                    }
+                }
+                __syncwarp();
+                // thresholds + quantiser + ordered compaction               src/codec.rs:226-235, 277-307
+                const float nf = pm.noise_floor_factor * scale;
+                const float peak_gate = 0.3f * gmax;
+                const float peak_cap = 0.05f * gmax * scale;
+                const float qmul = 32768.0f / scale;
+                glc_pair *dst = p.slots + row * kHop;
+                uint32_t count = 0;
+#pragma unroll 4
+                for (int t = 0; t < kHop / 32; ++t)
+                {
+                    const int k = lane + 32 * t;
+                    const float v = coef[k];
+                    const float a = fabsf(v);
+                    float th = sm.band_base[warp][sm.band_of[k]] * sm.inv_w[k];
+                    if (a > peak_gate)
+                        th = fminf(th, peak_cap);
+                    int q = 0;
+                    if (a > fmaxf(nf, th))
+                    {
+                        const float qf = fminf(fmaxf(roundf(v * qmul), -32768.0f), 32767.0f);
+                        q = __float2int_rz(qf);
+                    }
+                    const unsigned keep = __ballot_sync(0xffffffffu, q != 0);
+                    if (q != 0)
+                    {
+                        glc_pair pr2;
+                        pr2.idx = (uint16_t)k;
+                        pr2.q = (int16_t)q;
+                        dst[count + __popc(keep & ((1u << lane) - 1u))] = pr2;
+                    }
+                    count += __popc(keep);
+                }
+                if (lane == 0)
+                {
+                    p.nnz[row] = count;
+                    p.scales[row] = scale;
+                    atomicAdd(&sm.frame_nnz[lf], count); // lf < frames per group <= kFastFcs
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    // raw-PCM / sparse decision per frame                                 src/codec.rs:505-540
+    if (tid < gg.n_frames)
+    {
+        const uint64_t frame = fd.first_frame + gg.frame0 + tid;
+        const uint64_t row_f = fd.first_row + (gg.frame0 + tid) * ch;
+        const uint64_t compressed = (uint64_t)ch * 8 + (uint64_t)sm.frame_nnz[tid] * 4 + 8 + (uint64_t)ch * 4 + 64;
+        const float rhs = (float)((uint64_t)kFrame * ch * 2) * 0.85f;
+        const bool raw = (float)compressed >= rhs;
+        p.is_raw[frame] = raw ? 1 : 0;
+        p.raw_len[frame] = raw ? (uint32_t)(kFrame * ch) : 0u;
+        if (raw)
+            for (uint32_t c = 0; c < ch; ++c)
+            {
+                p.nnz[row_f + c] = 0;
+                p.scales[row_f + c] = 0.0f;
+            }
+    }
+}
+
+// ------------------------------------------------------------------ decode
+
+// One CTA per 8 rows: dequantise into the (c[2n], c[N-1-2n]) layout, DCT-IV, unfold, synthesis window.
+__global__ void __launch_bounds__(kFastThreads) fast_decode_kernel(const FastDecodeLaunch p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t row0 = p.row_begin + (uint64_t)blockIdx.x * kFastFcs;
+    if (row0 >= p.row_end)
+        return;
+    const uint32_t rows_here = (uint32_t)min((uint64_t)kFastFcs, p.row_end - row0);
+    __shared__ int s_live[kFastFcs];
+
+    // which rows are transformed: sparse frames with at least one pair
+    if (tid < kFastFcs)
+    {
+        int live = 0;
+        if ((uint32_t)tid < rows_here)
+        {
+            const uint64_t row = row0 + tid;
+            uint32_t lo = 0, hi = p.n_files - 1;
+            while (lo < hi)
+            {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (p.files[mid].first_row <= row)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const DecFileDesc &fd = p.files[lo];
+            const uint64_t frame = fd.first_frame + (row - fd.first_row) / fd.channels;
+            live = (!p.is_raw[frame] && p.pair_off[row + 1] > p.pair_off[row]) ? 1 : 0;
+            p.row_slot[row] = live ? (int32_t)row : -1;
+        }
+        s_live[tid] = live;
+    }
+    for (uint32_t e = tid; e < rows_here * (kHop / 2); e += kFastThreads)
+        sm.u[e >> 9][e & 511] = make_float2(0.f, 0.f);
+    __syncthreads();
+    // dequantise (src/codec.rs:651-665).  "Later duplicates overwrite": lane-ordered replay when the
+    // indices are not strictly ascending.
+    for (uint32_t r = warp; r < rows_here; r += kFastWarps)
+    {
+        if (!s_live[r])
+            continue;
+        const uint64_t row = row0 + r;
+        const uint64_t b = p.pair_off[row];
+        const uint32_t n = (uint32_t)(p.pair_off[row + 1] - b);
+        const glc_pair *pr = p.pairs + b;
+        const float scale = fmaxf(p.scales[row], 1e-12f) * (1.0f / 32768.0f);
+        bool ascending = true;
+        for (uint32_t j = lane; j + 1 < n; j += 32)
+            ascending = ascending && (pr[j].idx < pr[j + 1].idx);
+        ascending = __all_sync(0xffffffffu, ascending);
+        float *uf = reinterpret_cast<float *>(sm.u[r]);
+        auto put = [&](uint32_t j) {
+            const glc_pair q = pr[j];
+            if (q.idx < kHop)
+            {
+                const uint32_t k = q.idx;
+                // c[2n] -> u[n].x ; c[N-1-2n] -> u[n].y
+                const uint32_t slot = (k & 1u) ? (((kHop - 1 - k) >> 1) * 2 + 1) : ((k >> 1) * 2);
+                uf[slot] = (float)q.q * scale;
+            }
+        };
+        if (ascending)
+            for (uint32_t j = lane; j < n; j += 32)
+                put(j);
+        else if (lane == 0)
+            for (uint32_t j = 0; j < n; ++j)
+                put(j);
+    }
+    __syncthreads();
+    LaneTw tw;
+    make_lane_tw(tw, lane, p.norm);
+    for (uint32_t prn = warp; prn * 2 < rows_here; prn += kFastWarps)
+    {
+        const uint32_t fa = prn * 2, fb = min(prn * 2 + 1, rows_here - 1);
+        if (!s_live[fa] && !s_live[fb])
+            continue;
+        dct4_pair(sm.u[fa], sm.u[fb], tw, sm.xch[warp], lane);
+        const uint32_t n_here = (prn * 2 + 1 < rows_here) ? 2u : 1u;
+        for (uint32_t h = 0; h < n_here; ++h)
+        {
+            if (!s_live[fa + h])
+                continue;
+            const float *v = reinterpret_cast<const float *>(sm.xch[warp]) + h * kCoefStride;
+            float *out = p.blocks + (row0 + fa + h) * kFrame;
+            // unfold (transpose of the fold) + synthesis window           src/codec.rs:672-675
+#pragma unroll 4
+            for (int i = lane; i < kFrame; i += 32)
+            {
+                float val;
+                if (i < 512)
+                    val = v[512 + i];
+                else if (i < 1024)
+                    val = -v[512 + (1023 - i)];
+                else if (i < 1536)
+                    val = -v[1535 - i];
+                else
+                    val = -v[i - 1536];
+                out[i] = val * __ldg(p.window + i);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace
+
+uint64_t fast_groups_for(uint32_t n_frames, uint32_t channels)
+{
+    const uint32_t fpg = kFastFcs / channels ? kFastFcs / channels : 1u;
+    return ((uint64_t)n_frames + fpg - 1) / fpg;
+}
+
+cudaError_t launch_fast_encode(const FastEncodeLaunch &p, cudaStream_t s)
+{
+    if (p.group_end <= p.group_begin)
+        return cudaSuccess;
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaError_t e = cudaFuncSetAttribute(fast_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FastSmem));
+        if (e != cudaSuccess)
+            return e;
+        configured = true;
+    }
+    fast_encode_kernel<<<(unsigned)(p.group_end - p.group_begin), kFastThreads, sizeof(FastSmem), s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fast_decode(const FastDecodeLaunch &p, cudaStream_t s)
+{
+    if (p.row_end <= p.row_begin)
+        return cudaSuccess;
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaError_t e = cudaFuncSetAttribute(fast_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FastSmem));
+        if (e != cudaSuccess)
+            return e;
+        configured = true;
+    }
+    const uint64_t n = p.row_end - p.row_begin;
+    fast_decode_kernel<<<(unsigned)((n + kFastFcs - 1) / kFastFcs), kFastThreads, sizeof(FastSmem), s>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace glc

@@ -189,6 +189,42 @@ struct OlaLaunch
 };
 cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s);
 
+// ---- FAST transform mode (FFT-based, tolerance class; glc_fast_kernels.cu) ----
+struct FastEncodeLaunch
+{
+    const float *pcm_arena;
+    const FileDesc *files;
+    uint32_t n_files;
+    const uint64_t *first_group; // [n_files] first CTA group of each file (fast_groups_for per file, scanned)
+    uint64_t group_begin, group_end;
+    const float *window;
+    float norm;
+    const DevPerceptual *perc;
+    glc_pair *slots;   // [n_rows][1024]
+    uint32_t *nnz;     // [n_rows]
+    float *scales;     // [n_rows]
+    uint8_t *is_raw;   // [n_frames_total]
+    uint32_t *raw_len; // [n_frames_total]
+};
+uint64_t fast_groups_for(uint32_t n_frames, uint32_t channels);
+cudaError_t launch_fast_encode(const FastEncodeLaunch &p, cudaStream_t s);
+
+struct FastDecodeLaunch
+{
+    const glc_pair *pairs;
+    const uint64_t *pair_off;
+    const float *scales;
+    const uint8_t *is_raw;
+    const DecFileDesc *files;
+    uint32_t n_files;
+    uint64_t row_begin, row_end;
+    const float *window;
+    float norm;
+    int32_t *row_slot; // [batch rows] row itself when transformed, -1 otherwise
+    float *blocks;     // [batch rows][2048]
+};
+cudaError_t launch_fast_decode(const FastDecodeLaunch &p, cudaStream_t s);
+
 cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s);
 cudaError_t launch_fp32_issue_bench(int packed, int iters, float *sink, int blocks, cudaStream_t s);
 

@@ -32,7 +32,7 @@ extern "C" {
 #define GLC_FRAME_SIZE 2048u      /* src/codec.rs:15 */
 #define GLC_HOP_SIZE 1024u        /* src/codec.rs:16 */
 #define GLC_FRAMES_PER_CHUNK 500u /* src/codec.rs:18 */
-#define GLC_ABI_VERSION 2u
+#define GLC_ABI_VERSION 3u
 
 typedef enum glc_status
 {
@@ -50,8 +50,11 @@ typedef enum glc_status
 } glc_status;
 
 /* Transform arithmetic.  EXACT reproduces the reference's table-driven direct-form MDCT/IMDCT
- * operation by operation (src/codec.rs:359-390) and is the parity-gated default.  FAST is reserved
- * for the FFT-based transform named in BASELINE.json (tolerance class, not bit-exact). */
+ * operation by operation (src/codec.rs:359-390) and is the parity-gated default.  FAST is the
+ * FFT-based true MDCT/IMDCT named in BASELINE.json, fused with the quantiser: same stream layout,
+ * frame counts, gapless metadata and sample counts, but a TOLERANCE parity class (the reference's
+ * f32 table is not the true MDCT basis).  FLAC and the container are
+ * integer paths and identical in both modes. */
 typedef enum glc_mode
 {
     GLC_MODE_EXACT = 0,
@@ -189,8 +192,9 @@ enum
     GLC_K_FLAC_GATHER = 8,
     GLC_K_MISC = 9,
     GLC_K_WINDOW_TILE = 10, /* padding + window -> tiled A operand of the MDCT */
-    GLC_K_RESERVED = 11,
-    GLC_K_COUNT = 12
+    GLC_K_FAST_ENCODE = 11, /* FAST mode: fused window + FFT MDCT + quantise + pack */
+    GLC_K_FAST_DECODE = 12, /* FAST mode: fused dequantise + FFT IMDCT + synthesis window */
+    GLC_K_COUNT = 13
 };
 
 typedef struct glc_stats
