@@ -250,7 +250,7 @@ struct glc_ctx
     cudaStream_t compute, copy, d2h;
     cudaEvent_t t0, t1;
     HostTables host;
-    float *d_tab_mdct, *d_tab_imdct, *d_window;
+    float *d_tab_mdct, *d_tab_imdct, *d_window, *d_fast_tw;
     PinnedPool pool;
     DevicePool dpool;
     glc_stats stats;
@@ -382,6 +382,12 @@ extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
     // the IMDCT gathers rows k of the reference layout tab[k][i] directly
     CUDA_TRY(cudaMemcpy(c->d_tab_imdct, c->host.cos_tab, tab_bytes, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->d_window, c->host.window, sizeof(float) * kFrame, cudaMemcpyHostToDevice));
+    {
+        float tw[kFastTwiddleFloats];
+        fast_twiddle_table(c->host.norm, tw);
+        CUDA_TRY(cudaMalloc(&c->d_fast_tw, sizeof tw));
+        CUDA_TRY(cudaMemcpy(c->d_fast_tw, tw, sizeof tw, cudaMemcpyHostToDevice));
+    }
     *out = c;
     return GLC_OK;
 }
@@ -398,6 +404,7 @@ extern "C" void glc_ctx_destroy(glc_ctx *c)
     cudaFree(c->d_tab_mdct);
     cudaFree(c->d_tab_imdct);
     cudaFree(c->d_window);
+    cudaFree(c->d_fast_tw);
     if (c->d_flush)
         cudaFree(c->d_flush);
     c->pool.destroy();
@@ -1021,6 +1028,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             fe.group_begin = 0;
             fe.group_end = n_groups;
             fe.window = c->d_window;
+            fe.twiddles = reinterpret_cast<const float2 *>(c->d_fast_tw);
             fe.norm = c->host.norm;
             fe.perc = enc->d_perc;
             fe.slots = d_slots;
@@ -1469,6 +1477,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             fdl.row_begin = w.r0;
             fdl.row_end = w.r1;
             fdl.window = c->d_window;
+            fdl.twiddles = reinterpret_cast<const float2 *>(c->d_fast_tw);
             fdl.norm = c->host.norm;
             fdl.row_slot = d_row_slot;
             fdl.blocks = d_blocks;

@@ -21,6 +21,8 @@
 //   pass 2  lane = (frame-channel, k2): 32-point FFT over n1 in registers, post-twiddle, results
 //           to shared memory in natural coefficient order.
 // Compiled with FMA contraction ON (this file only).
+#include <math.h>
+
 #include "glc_fft_gen.cuh"
 #include "glc_internal.cuh"
 
@@ -55,21 +57,14 @@ struct LaneTw
     float2 qb;    // post-twiddle base for k2 = lane & 15, times `norm`
 };
 
-__device__ __forceinline__ void make_lane_tw(LaneTw &tw, int lane, float norm)
+// The table is built on the host in double precision (fast_twiddle_table) and uploaded once per
+// context: [32 lanes][16] pass-1 twiddles, then [16] post-twiddle bases (times norm).
+__device__ __forceinline__ void load_lane_tw(LaneTw &tw, const float2 *table, int lane)
 {
-    const int n1 = lane;
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2)
-    {
-        // exp(-i pi (4 n1 + 1)/4096) * exp(-2 pi i n1 k2 / 512)
-        const double a = -((4.0 * n1 + 1.0) / 4096.0 + (2.0 * n1 * k2) / 512.0);
-        double s, c;
-        sincospi(a, &s, &c);
-        tw.t[k2] = make_float2((float)c, (float)s);
-    }
-    double s, c;
-    sincospi(-(double)(lane & 15) / 1024.0, &s, &c);
-    tw.qb = make_float2((float)(c * (double)norm), (float)(s * (double)norm));
+        tw.t[k2] = __ldg(table + lane * 16 + k2);
+    tw.qb = __ldg(table + 32 * 16 + (lane & 15));
 }
 
 // DCT-IV of two frame-channels whose (u[2n], u[N-1-2n]) pairs are in u_a / u_b (shared memory).
@@ -176,7 +171,7 @@ __device__ __forceinline__ GroupGeom locate_group(const uint64_t *first_group, c
 
 // ------------------------------------------------------------------ encode
 
-__global__ void __launch_bounds__(kFastThreads) fast_encode_kernel(const FastEncodeLaunch p)
+__global__ void __launch_bounds__(kFastThreads, 3) fast_encode_kernel(const FastEncodeLaunch p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
@@ -196,7 +191,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_encode_kernel(const FastEnc
     if (tid < kFastFcs)
         sm.frame_nnz[tid] = 0;
     LaneTw tw;
-    make_lane_tw(tw, lane, p.norm);
+    load_lane_tw(tw, p.twiddles, lane);
     const float *src = p.pcm_arena + fd.pcm_off;
     const long long len = (long long)fd.len;
 
@@ -206,31 +201,67 @@ __global__ void __launch_bounds__(kFastThreads) fast_encode_kernel(const FastEnc
         __syncthreads();
         // ---- stage: fold + window, (u[2n], u[N-1-2n]) per n, over the reference's padded signal
         //      (512 zeros + data + zero tail, src/codec.rs:433-447) ----
-        for (uint32_t e = tid; e < fcs_here * (kHop / 2); e += kFastThreads)
+        for (uint32_t fc = 0; fc < fcs_here; ++fc)
         {
-            const uint32_t fc = e >> 9, n = e & 511;
             const uint32_t lf = (fc0 + fc) / ch, c = (fc0 + fc) - lf * ch;
             const long long base = (long long)((gg.frame0 + lf) * kHop) - kHop / 2; // sample index of i = 0
-            auto smp = [&](int i) -> float {
-                const long long pos = base + i;
-                return (pos >= 0 && pos < len) ? __ldg(src + pos * ch + c) : 0.0f;
-            };
-            // window symmetry w[2047-i] = w[i] leaves two distinct values per n
-            const float wa = __ldg(p.window + 512 + 2 * n);
-            float u0, u1;
-            if (n < 256)
+            const bool interior = base >= 0 && base + kFrame <= len;               // no padding inside this frame
+            const float *fb = src + base * (long long)ch + c;                        // only dereferenced in range
+            const int ich = (int)ch;
+#pragma unroll
+            for (int it = 0; it < (kHop / 2) / kFastThreads; ++it)
             {
-                const float wb = __ldg(p.window + 511 - 2 * n);
-                u0 = -smp(1535 - 2 * n) * wa - smp(1536 + 2 * n) * wb;
-                u1 = smp(511 - 2 * n) * wb - smp(512 + 2 * n) * wa;
+                const int n = tid + it * kFastThreads;
+                // window symmetry w[2047-i] = w[i] leaves two distinct values per n
+                const float wa = __ldg(p.window + 512 + 2 * n);
+                const float wo = __ldg(p.window + (n < 256 ? 511 - 2 * n : 2 * n - 512));
+                int i0, i1, i2, i3;
+                if (n < 256)
+                {
+                    i0 = 1535 - 2 * n; // u0 = -b[i0] - b[i1], u1 = b[i2] - b[i3]
+                    i1 = 1536 + 2 * n;
+                    i2 = 511 - 2 * n;
+                    i3 = 512 + 2 * n;
+                }
+                else
+                {
+                    i0 = 2 * n - 512;  // u0 = b[i0] - b[i1], u1 = -b[i2] - b[i3]
+                    i1 = 1535 - 2 * n;
+                    i2 = 512 + 2 * n;
+                    i3 = 2559 - 2 * n;
+                }
+                float x0, x1, x2, x3;
+                if (interior)
+                {
+                    x0 = __ldg(fb + i0 * ich);
+                    x1 = __ldg(fb + i1 * ich);
+                    x2 = __ldg(fb + i2 * ich);
+                    x3 = __ldg(fb + i3 * ich);
+                }
+                else
+                {
+                    auto smp = [&](int i) -> float {
+                        const long long pos = base + i;
+                        return (pos >= 0 && pos < len) ? __ldg(fb + (long long)i * ich) : 0.0f;
+                    };
+                    x0 = smp(i0);
+                    x1 = smp(i1);
+                    x2 = smp(i2);
+                    x3 = smp(i3);
+                }
+                float u0, u1;
+                if (n < 256)
+                {
+                    u0 = -x0 * wa - x1 * wo; // windows: w[i0] = wa, w[i1] = wo, w[i2] = wo, w[i3] = wa
+                    u1 = x2 * wo - x3 * wa;
+                }
+                else
+                {
+                    u0 = x0 * wo - x1 * wa;  // windows: w[i0] = wo, w[i1] = wa, w[i2] = wa, w[i3] = wo
+                    u1 = -x2 * wa - x3 * wo;
+                }
+                sm.u[fc][n] = make_float2(u0, u1);
             }
-            else
-            {
-                const float wc = __ldg(p.window + 2 * n - 512);
-                u0 = smp(2 * n - 512) * wc - smp(1535 - 2 * n) * wa;
-                u1 = -smp(512 + 2 * n) * wa - smp(2559 - 2 * n) * wc;
-            }
-            sm.u[fc][n] = make_float2(u0, u1);
         }
         __syncthreads();
 
@@ -308,8 +339,9 @@ __global__ void __launch_bounds__(kFastThreads) fast_encode_kernel(const FastEnc
                     int q = 0;
                     if (a > fmaxf(nf, th))
                     {
-                        const float qf = fminf(fmaxf(roundf(v * qmul), -32768.0f), 32767.0f);
-                        q = __float2int_rz(qf);
+                        // round half away from zero (f32::round) as trunc(x + copysign(0.5, x))
+                        const float x = v * qmul;
+                        q = __float2int_rz(fminf(fmaxf(x + copysignf(0.5f, x), -32768.0f), 32767.0f));
                     }
                     const unsigned keep = __ballot_sync(0xffffffffu, q != 0);
                     if (q != 0)
@@ -354,7 +386,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_encode_kernel(const FastEnc
 // ------------------------------------------------------------------ decode
 
 // One CTA per 8 rows: dequantise into the (c[2n], c[N-1-2n]) layout, DCT-IV, unfold, synthesis window.
-__global__ void __launch_bounds__(kFastThreads) fast_decode_kernel(const FastDecodeLaunch p)
+__global__ void __launch_bounds__(kFastThreads, 3) fast_decode_kernel(const FastDecodeLaunch p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
@@ -426,7 +458,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_decode_kernel(const FastDec
     }
     __syncthreads();
     LaneTw tw;
-    make_lane_tw(tw, lane, p.norm);
+    load_lane_tw(tw, p.twiddles, lane);
     for (uint32_t prn = warp; prn * 2 < rows_here; prn += kFastWarps)
     {
         const uint32_t fa = prn * 2, fb = min(prn * 2 + 1, rows_here - 1);
@@ -461,6 +493,25 @@ __global__ void __launch_bounds__(kFastThreads) fast_decode_kernel(const FastDec
 }
 
 } // namespace
+
+void fast_twiddle_table(float norm, float *out /* kFastTwiddleFloats */)
+{
+    const double pi = 3.14159265358979323846;
+    for (int n1 = 0; n1 < 32; ++n1)
+        for (int k2 = 0; k2 < 16; ++k2)
+        {
+            // exp(-i pi (4 n1 + 1)/4096) * exp(-2 pi i n1 k2 / 512)
+            const double a = -pi * ((4.0 * n1 + 1.0) / 4096.0 + (2.0 * n1 * k2) / 512.0);
+            out[2 * (n1 * 16 + k2)] = (float)cos(a);
+            out[2 * (n1 * 16 + k2) + 1] = (float)sin(a);
+        }
+    for (int k2 = 0; k2 < 16; ++k2)
+    {
+        const double a = -pi * k2 / 1024.0; // exp(-i pi k2/N), times norm
+        out[2 * (512 + k2)] = (float)(cos(a) * (double)norm);
+        out[2 * (512 + k2) + 1] = (float)(sin(a) * (double)norm);
+    }
+}
 
 uint64_t fast_groups_for(uint32_t n_frames, uint32_t channels)
 {

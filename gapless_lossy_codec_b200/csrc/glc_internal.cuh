@@ -198,6 +198,7 @@ struct FastEncodeLaunch
     const uint64_t *first_group; // [n_files] first CTA group of each file (fast_groups_for per file, scanned)
     uint64_t group_begin, group_end;
     const float *window;
+    const float2 *twiddles; // fast_twiddle_table
     float norm;
     const DevPerceptual *perc;
     glc_pair *slots;   // [n_rows][1024]
@@ -206,6 +207,8 @@ struct FastEncodeLaunch
     uint8_t *is_raw;   // [n_frames_total]
     uint32_t *raw_len; // [n_frames_total]
 };
+constexpr int kFastTwiddleFloats = 2 * (32 * 16 + 16);
+void fast_twiddle_table(float norm, float *out); // host, double precision
 uint64_t fast_groups_for(uint32_t n_frames, uint32_t channels);
 cudaError_t launch_fast_encode(const FastEncodeLaunch &p, cudaStream_t s);
 
@@ -219,6 +222,7 @@ struct FastDecodeLaunch
     uint32_t n_files;
     uint64_t row_begin, row_end;
     const float *window;
+    const float2 *twiddles;
     float norm;
     int32_t *row_slot; // [batch rows] row itself when transformed, -1 otherwise
     float *blocks;     // [batch rows][2048]
