@@ -785,7 +785,20 @@ struct glc_dev_encoded
     float *d_scales;
     uint64_t *d_raw_off;
     int16_t *d_raw;
-    uint64_t n_pairs, n_raw;
+    uint64_t n_pairs, n_raw; // valid once totals_known
+    bool totals_known;
+};
+
+// Pinned host copies of the two variable-length arrays, filled wave by wave while later waves are
+// still being computed (host-input encodes only).  The arenas grow like a vector: the first wave's
+// density sizes them, a later overflow reallocates and copies.
+struct EncodeHostOut
+{
+    glc_pair *h_pairs = nullptr;
+    uint64_t pairs_cap = 0;
+    int16_t *h_raw = nullptr;
+    uint64_t raw_cap = 0;
+    uint64_t n_pairs = 0, n_raw = 0;
 };
 
 extern "C" void glc_dev_pcm_free(glc_dev_pcm *p)
@@ -905,7 +918,7 @@ static glc_status build_file_table(uint32_t n_files, const uint64_t *n_samples, 
 // is already fully resident; otherwise the H2D copies are issued here, wave by wave.
 static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &files, uint64_t tot_rows,
                               uint64_t tot_frames, float *d_arena, const float *const *host_pcm,
-                              const uint64_t *n_samples, glc_dev_encoded **out)
+                              const uint64_t *n_samples, EncodeHostOut *ho, glc_dev_encoded **out)
 {
     glc_ctx *c = enc->ctx;
     cudaStream_t cs = c->compute;
@@ -925,6 +938,8 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     de->n_frames = tot_frames;
     de->d_pairs = nullptr;
     de->d_raw = nullptr;
+    de->n_pairs = de->n_raw = 0;
+    de->totals_known = false;
     glc_pair *d_slots = nullptr;
     uint32_t *d_raw_len = nullptr;
     float *d_coefs = nullptr;
@@ -935,6 +950,10 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     CUDA_TRY(dmalloc(&de->d_raw_off, tot_frames + 1, cs));
     CUDA_TRY(dmalloc(&d_slots, tot_rows * kHop, cs));
     CUDA_TRY(dmalloc(&d_raw_len, tot_frames, cs));
+    // the compact outputs are produced wave by wave, so they are sized for the worst case
+    // (every coefficient kept / every frame raw); the live totals stay on the device
+    CUDA_TRY(dmalloc(&de->d_pairs, tot_rows * kHop, cs));
+    CUDA_TRY(dmalloc(&de->d_raw, tot_rows * kFrame, cs));
 
     // Wave plan: contiguous frame ranges.  A wave's MDCT grid is (rows/128) x 8 CTAs and 2 x 148 CTAs
     // are resident at a time, so waves are sized in multiples of 37 row tiles (4 736 rows): every
@@ -976,6 +995,52 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     cudaEvent_t ev_copy = nullptr;
     if (host_pcm)
         ev_copy = get_event(c);
+    // host output: per-wave D2H of the compacted pairs / raw bodies on the d2h stream
+    uint64_t *h_tot = nullptr; // [2 * waves] running totals after each wave (pinned)
+    std::vector<cudaEvent_t> wave_done;
+    if (ho)
+    {
+        h_tot = (uint64_t *)c->pool.alloc(16 * waves.size());
+        if (!h_tot)
+            return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+    }
+    auto grow = [&](void **buf, uint64_t *cap, uint64_t need, uint64_t keep, size_t elem, uint64_t rows_done) -> bool {
+        if (need <= *cap)
+            return true;
+        // density so far extrapolated to the whole batch, +25 % and 1 Mi elements of slack
+        const double dens = rows_done ? (double)need / (double)rows_done : 0.0;
+        uint64_t ncap = std::max<uint64_t>(need, (uint64_t)(dens * (double)tot_rows * 1.25) + (1u << 20));
+        void *nb = c->pool.alloc(ncap * elem);
+        if (!nb)
+            return false;
+        if (keep)
+        {
+            cudaStreamSynchronize(c->d2h); // earlier waves must have landed before they are moved
+            memcpy(nb, *buf, keep * elem);
+        }
+        if (*buf)
+            c->pool.release(*buf);
+        *buf = nb;
+        *cap = ncap;
+        return true;
+    };
+    auto drain_wave = [&](size_t w) -> glc_status {
+        CUDA_TRY(cudaEventSynchronize(wave_done[w]));
+        const uint64_t p1 = h_tot[2 * w], q1 = h_tot[2 * w + 1];
+        const uint64_t p0 = w ? h_tot[2 * (w - 1)] : 0, q0 = w ? h_tot[2 * (w - 1) + 1] : 0;
+        if (!grow((void **)&ho->h_pairs, &ho->pairs_cap, p1, p0, sizeof(glc_pair), waves[w].r1) ||
+            !grow((void **)&ho->h_raw, &ho->raw_cap, q1, q0, sizeof(int16_t), waves[w].r1))
+            return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+        CUDA_TRY(cudaStreamWaitEvent(c->d2h, wave_done[w], 0));
+        if (p1 > p0)
+            CUDA_TRY(cudaMemcpyAsync(ho->h_pairs + p0, de->d_pairs + p0, (p1 - p0) * sizeof(glc_pair),
+                                     cudaMemcpyDeviceToHost, c->d2h));
+        if (q1 > q0)
+            CUDA_TRY(cudaMemcpyAsync(ho->h_raw + q0, de->d_raw + q0, (q1 - q0) * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                                     c->d2h));
+        c->stats.d2h_bytes += (p1 - p0) * sizeof(glc_pair) + (q1 - q0) * sizeof(int16_t);
+        return GLC_OK;
+    };
     uint32_t copy_file = 0;      // next file with bytes left to copy
     uint64_t copy_done = 0;      // interleaved samples of copy_file already enqueued
     for (size_t wi = 0; wi < waves.size(); ++wi)
@@ -1037,9 +1102,9 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             fe.is_raw = de->d_is_raw;
             fe.raw_len = d_raw_len;
             CUDA_TRY(launch_fast_encode(fe, cs));
-            continue;
         }
         MdctLaunch m{};
+        if (!fast)
         {
             LaunchScope ls(c, GLC_K_WINDOW_TILE, cs);
             m.pcm_arena = d_arena;
@@ -1054,10 +1119,12 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             m.a_tiles = d_atiles;
             CUDA_TRY(launch_window_tiles(m, cs));
         }
+        if (!fast)
         {
             LaunchScope ls(c, GLC_K_MDCT_EXACT, cs);
             CUDA_TRY(launch_mdct_exact(m, cs));
         }
+        if (!fast)
         {
             LaunchScope ls(c, GLC_K_QUANT_PACK, cs);
             QuantPackLaunch q{};
@@ -1074,46 +1141,61 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             q.raw_len = d_raw_len;
             CUDA_TRY(launch_quant_pack(q, cs));
         }
+        // ---- variable-length layout of this wave: the scans continue from the previous wave's totals ----
+        {
+            LaunchScope ls(c, GLC_K_SCAN, cs, 2);
+            CUDA_TRY(launch_scan_u32_u64(de->d_nnz + w.r0, de->d_pair_off + w.r0, w.r1 - w.r0, cs,
+                                         wi ? de->d_pair_off + w.r0 : nullptr));
+            CUDA_TRY(launch_scan_u32_u64(d_raw_len + w.f0, de->d_raw_off + w.f0, w.f1 - w.f0, cs,
+                                         wi ? de->d_raw_off + w.f0 : nullptr));
+        }
+        {
+            LaunchScope ls(c, GLC_K_GATHER, cs, 2);
+            GatherLaunch g{};
+            g.slots = d_slots;
+            g.nnz = de->d_nnz;
+            g.pair_off = de->d_pair_off;
+            g.pairs = de->d_pairs;
+            g.is_raw = de->d_is_raw;
+            g.raw_off = de->d_raw_off;
+            g.raw = de->d_raw;
+            g.pcm_arena = d_arena;
+            g.files = d_files;
+            g.n_files = n_files;
+            g.window = c->d_window;
+            g.row_begin = w.r0;
+            g.row_end = w.r1;
+            g.frame_begin = w.f0;
+            g.frame_end = w.f1;
+            CUDA_TRY(launch_gather(g, cs));
+        }
+        if (ho)
+        {
+            CUDA_TRY(cudaMemcpyAsync(h_tot + 2 * wi, de->d_pair_off + w.r1, 8, cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaMemcpyAsync(h_tot + 2 * wi + 1, de->d_raw_off + w.f1, 8, cudaMemcpyDeviceToHost, cs));
+            cudaEvent_t ev = get_event(c);
+            wave_done.push_back(ev);
+            CUDA_TRY(cudaEventRecord(ev, cs));
+            if (wi >= 1)
+                GLC_TRY(drain_wave(wi - 1)); // one wave behind: the GPU already has wave wi queued
+        }
+    }
+    if (ho)
+    {
+        GLC_TRY(drain_wave(waves.size() - 1));
+        ho->n_pairs = h_tot[2 * (waves.size() - 1)];
+        ho->n_raw = h_tot[2 * (waves.size() - 1) + 1];
+        de->n_pairs = ho->n_pairs;
+        de->n_raw = ho->n_raw;
+        de->totals_known = true;
+        c->stats.d2h_bytes += 16 * waves.size();
+        c->pool.release(h_tot);
+        for (cudaEvent_t e : wave_done)
+            c->ev_free.push_back(e);
     }
     if (ev_copy)
         c->ev_free.push_back(ev_copy);
     tr.mark("waves");
-
-    {
-        LaunchScope ls(c, GLC_K_SCAN, cs, 2);
-        CUDA_TRY(launch_scan_u32_u64(de->d_nnz, de->d_pair_off, tot_rows, cs));
-        CUDA_TRY(launch_scan_u32_u64(d_raw_len, de->d_raw_off, tot_frames, cs));
-    }
-    uint64_t totals[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(&totals[0], de->d_pair_off + tot_rows, 8, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaMemcpyAsync(&totals[1], de->d_raw_off + tot_frames, 8, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    c->stats.d2h_bytes += 16;
-    de->n_pairs = totals[0];
-    de->n_raw = totals[1];
-    tr.mark("scan+totals");
-    CUDA_TRY(dmalloc(&de->d_pairs, de->n_pairs, cs));
-    CUDA_TRY(dmalloc(&de->d_raw, de->n_raw, cs));
-    tr.mark("alloc out");
-    {
-        LaunchScope ls(c, GLC_K_GATHER, cs, 2);
-        GatherLaunch g{};
-        g.slots = d_slots;
-        g.nnz = de->d_nnz;
-        g.pair_off = de->d_pair_off;
-        g.pairs = de->d_pairs;
-        g.is_raw = de->d_is_raw;
-        g.raw_off = de->d_raw_off;
-        g.raw = de->d_raw;
-        g.pcm_arena = d_arena;
-        g.files = d_files;
-        g.n_files = n_files;
-        g.window = c->d_window;
-        g.n_rows = tot_rows;
-        g.n_frames_total = tot_frames;
-        CUDA_TRY(launch_gather(g, cs));
-    }
-    tr.mark("gather");
     dfree(d_slots, cs);
     dfree(d_raw_len, cs);
     dfree(d_coefs, cs);
@@ -1146,11 +1228,21 @@ extern "C" void glc_encoded_free(glc_ctx *c, glc_encoded *e)
     delete box;
 }
 
-static glc_status download_encoded(const glc_dev_encoded *de, glc_encoded **out /* [n_files] */)
+static glc_status download_encoded(glc_dev_encoded *de, EncodeHostOut *ho, glc_encoded **out /* [n_files] */)
 {
     glc_ctx *c = de->ctx;
     cudaStream_t cs = c->compute;
     const uint64_t R = de->n_rows, F = de->n_frames;
+    if (!de->totals_known)
+    {
+        uint64_t totals[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(&totals[0], de->d_pair_off + R, 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(&totals[1], de->d_raw_off + F, 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        de->n_pairs = totals[0];
+        de->n_raw = totals[1];
+        de->totals_known = true;
+    }
     EncodedBlock *blk = new EncodedBlock();
     blk->ctx = c;
     blk->refs = 0;
@@ -1163,10 +1255,26 @@ static glc_status download_encoded(const glc_dev_encoded *de, glc_encoded **out 
     uint8_t *h_is_raw = (uint8_t *)pin(F);
     uint32_t *h_nnz = (uint32_t *)pin(R * 4);
     uint64_t *h_pair_off = (uint64_t *)pin((R + 1) * 8);
-    glc_pair *h_pairs = (glc_pair *)pin(de->n_pairs * 4);
+    // the two big arrays may already have come down wave by wave (host-input encode)
+    glc_pair *h_pairs = nullptr;
+    int16_t *h_raw = nullptr;
+    if (ho && ho->h_pairs && ho->h_raw)
+    {
+        h_pairs = ho->h_pairs;
+        h_raw = ho->h_raw;
+        blk->pinned.push_back(h_pairs);
+        blk->pinned.push_back(h_raw);
+        ho->h_pairs = nullptr;
+        ho->h_raw = nullptr;
+    }
+    else
+    {
+        ho = nullptr;
+        h_pairs = (glc_pair *)pin(de->n_pairs * 4);
+        h_raw = (int16_t *)pin(de->n_raw * 2);
+    }
     float *h_scales = (float *)pin(R * 4);
     uint64_t *h_raw_off = (uint64_t *)pin((F + 1) * 8);
-    int16_t *h_raw = (int16_t *)pin(de->n_raw * 2);
     if (!h_is_raw || !h_nnz || !h_pair_off || !h_pairs || !h_scales || !h_raw_off || !h_raw)
     {
         blk->refs = 1;
@@ -1178,12 +1286,17 @@ static glc_status download_encoded(const glc_dev_encoded *de, glc_encoded **out 
     CUDA_TRY(cudaMemcpyAsync(h_pair_off, de->d_pair_off, (R + 1) * 8, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync(h_scales, de->d_scales, R * 4, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync(h_raw_off, de->d_raw_off, (F + 1) * 8, cudaMemcpyDeviceToHost, cs));
-    if (de->n_pairs)
-        CUDA_TRY(cudaMemcpyAsync(h_pairs, de->d_pairs, de->n_pairs * 4, cudaMemcpyDeviceToHost, cs));
-    if (de->n_raw)
-        CUDA_TRY(cudaMemcpyAsync(h_raw, de->d_raw, de->n_raw * 2, cudaMemcpyDeviceToHost, cs));
+    if (!ho)
+    {
+        if (de->n_pairs)
+            CUDA_TRY(cudaMemcpyAsync(h_pairs, de->d_pairs, de->n_pairs * 4, cudaMemcpyDeviceToHost, cs));
+        if (de->n_raw)
+            CUDA_TRY(cudaMemcpyAsync(h_raw, de->d_raw, de->n_raw * 2, cudaMemcpyDeviceToHost, cs));
+        c->stats.d2h_bytes += de->n_pairs * 4 + de->n_raw * 2;
+    }
     CUDA_TRY(cudaStreamSynchronize(cs));
-    c->stats.d2h_bytes += F + R * 4 + (R + 1) * 8 + R * 4 + (F + 1) * 8 + de->n_pairs * 4 + de->n_raw * 2;
+    CUDA_TRY(cudaStreamSynchronize(c->d2h));
+    c->stats.d2h_bytes += F + R * 4 + (R + 1) * 8 + R * 4 + (F + 1) * 8;
 
     const size_t nf = de->files.size();
     for (size_t i = 0; i < nf; ++i)
@@ -1250,9 +1363,15 @@ extern "C" glc_status glc_encode_batch(glc_encoder *enc, uint32_t n_files, const
     float *d_arena = nullptr;
     CUDA_TRY(dmalloc(&d_arena, tot_pcm, c->copy));
     glc_dev_encoded *de = nullptr;
-    glc_status st = encode_core(enc, files, rows, frames, d_arena, pcm, n_samples, &de);
+    EncodeHostOut ho;
+    glc_status st = encode_core(enc, files, rows, frames, d_arena, pcm, n_samples, &ho, &de);
     if (st == GLC_OK)
-        st = download_encoded(de, out);
+        st = download_encoded(de, &ho, out);
+    cudaStreamSynchronize(c->d2h);
+    if (ho.h_pairs)
+        c->pool.release(ho.h_pairs);
+    if (ho.h_raw)
+        c->pool.release(ho.h_raw);
     if (de)
         glc_dev_encoded_free(de);
     cudaStreamSynchronize(c->compute);
@@ -1300,7 +1419,7 @@ extern "C" glc_status glc_dev_encode(glc_encoder *enc, const glc_dev_pcm *pcm, g
     const uint64_t n = pcm->n;
     const uint16_t ch = pcm->channels;
     GLC_TRY(build_file_table(1, &n, &ch, files, &rows, &frames, &tot_pcm));
-    return encode_core(enc, files, rows, frames, pcm->d + pcm->trim_off, nullptr, nullptr, out);
+    return encode_core(enc, files, rows, frames, pcm->d + pcm->trim_off, nullptr, nullptr, nullptr, out);
 }
 
 extern "C" glc_status glc_dev_encoded_download(const glc_dev_encoded *de, glc_encoded **out)
@@ -1308,7 +1427,7 @@ extern "C" glc_status glc_dev_encoded_download(const glc_dev_encoded *de, glc_en
     if (!de || !out)
         return fail(GLC_ERR_INVALID_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(de->ctx->device));
-    return download_encoded(de, out);
+    return download_encoded(const_cast<glc_dev_encoded *>(de), nullptr, out);
 }
 
 // ------------------------------------------------------------------ decoder

@@ -188,14 +188,15 @@ __global__ void __launch_bounds__(kQPThreads) quant_pack_kernel(const QuantPackL
 constexpr int kScanThreads = 1024;
 constexpr int kScanItems = 8;
 
-__global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint32_t *__restrict__ in, uint64_t *__restrict__ out,
-                                                            uint64_t n)
+// `base` (nullable) is the running total of everything before in[0]; it may alias out[0].
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint32_t *in, uint64_t *out, uint64_t n,
+                                                            const uint64_t *base)
 {
     __shared__ uint64_t s_warp[kScanThreads / 32];
     __shared__ uint64_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0)
-        s_carry = 0;
+        s_carry = base ? *base : 0;
     __syncthreads();
     const uint64_t per_iter = (uint64_t)kScanThreads * kScanItems;
     for (uint64_t base = 0; base < n; base += per_iter)
@@ -243,8 +244,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint32_t *__re
 // ---- gather: one warp per row copies its pairs into the compact stream ----
 __global__ void __launch_bounds__(256) gather_pairs_kernel(const GatherLaunch p)
 {
-    const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= p.n_rows)
+    const uint64_t row = p.row_begin + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= p.row_end)
         return;
     const int lane = threadIdx.x & 31;
     const uint32_t n = p.nnz[row];
@@ -257,8 +258,8 @@ __global__ void __launch_bounds__(256) gather_pairs_kernel(const GatherLaunch p)
 // ---- raw-PCM frame bodies: ((x*w)*32767).clamp(-32768,32767) as i16, planar [ch][2048] ----
 __global__ void __launch_bounds__(256) gather_raw_kernel(const GatherLaunch p)
 {
-    const uint64_t frame = blockIdx.x;
-    if (frame >= p.n_frames_total || !p.is_raw[frame])
+    const uint64_t frame = p.frame_begin + blockIdx.x;
+    if (frame >= p.frame_end || !p.is_raw[frame])
         return;
     const FileDesc &fd = find_file_by_frame(p.files, p.n_files, frame, nullptr);
     const uint32_t ch = fd.channels;
@@ -546,18 +547,18 @@ cudaError_t launch_quant_pack(const QuantPackLaunch &p, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan_u32_u64(const uint32_t *in, uint64_t *out, uint64_t n, cudaStream_t s)
+cudaError_t launch_scan_u32_u64(const uint32_t *in, uint64_t *out, uint64_t n, cudaStream_t s, const uint64_t *base)
 {
-    scan_kernel<<<1, kScanThreads, 0, s>>>(in, out, n);
+    scan_kernel<<<1, kScanThreads, 0, s>>>(in, out, n, base);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s)
 {
-    if (p.n_rows)
-        gather_pairs_kernel<<<(unsigned)((p.n_rows + 7) / 8), 256, 0, s>>>(p);
-    if (p.n_frames_total)
-        gather_raw_kernel<<<(unsigned)p.n_frames_total, 256, 0, s>>>(p);
+    if (p.row_end > p.row_begin)
+        gather_pairs_kernel<<<(unsigned)((p.row_end - p.row_begin + 7) / 8), 256, 0, s>>>(p);
+    if (p.frame_end > p.frame_begin)
+        gather_raw_kernel<<<(unsigned)(p.frame_end - p.frame_begin), 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -568,7 +569,7 @@ cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s)
     const uint64_t n = p.row_end - p.row_begin;
     const unsigned grid = (unsigned)((n + 255) / 256);
     row_flag_kernel<<<grid, 256, 0, s>>>(p);
-    scan_kernel<<<1, kScanThreads, 0, s>>>(p.flags, p.slot_off, n);
+    scan_kernel<<<1, kScanThreads, 0, s>>>(p.flags, p.slot_off, n, nullptr);
     row_scatter_kernel<<<grid, 256, 0, s>>>(p);
     dequant_tile_kernel<<<(unsigned)((n + kBM - 1) / kBM), 256, 0, s>>>(p);
     return cudaGetLastError();

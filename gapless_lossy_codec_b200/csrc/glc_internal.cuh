@@ -120,7 +120,9 @@ struct QuantPackLaunch
 cudaError_t launch_quant_pack(const QuantPackLaunch &p, cudaStream_t s);
 
 // exclusive scans: u32 -> u64, n+1 outputs
-cudaError_t launch_scan_u32_u64(const uint32_t *in, uint64_t *out, uint64_t n, cudaStream_t s);
+// (`base`, nullable device pointer: running total before in[0]; may alias out[0])
+cudaError_t launch_scan_u32_u64(const uint32_t *in, uint64_t *out, uint64_t n, cudaStream_t s,
+                                const uint64_t *base = nullptr);
 
 struct GatherLaunch
 {
@@ -135,8 +137,8 @@ struct GatherLaunch
     const FileDesc *files;
     uint32_t n_files;
     const float *window;
-    uint64_t n_rows;
-    uint64_t n_frames_total;
+    uint64_t row_begin, row_end;     // rows whose pairs are compacted by this launch
+    uint64_t frame_begin, frame_end; // frames whose raw bodies are produced by this launch
 };
 cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s);
 
