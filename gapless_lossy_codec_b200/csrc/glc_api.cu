@@ -774,11 +774,25 @@ struct Wave
     uint64_t f0, f1, r0, r1;
 };
 
+// With group_align, wave boundaries inside a file fall on multiples of that file's frame-group size
+// (quant_frames_per_group), so that the per-group kernels never see half a group.
 template <typename Desc>
 static std::vector<Wave> plan_waves(const std::vector<Desc> &files, uint64_t tot_frames, uint64_t tot_rows,
-                                    uint64_t target_rows, uint64_t *max_wave_rows)
+                                    uint64_t target_rows, uint64_t *max_wave_rows, bool group_align = false)
 {
     const uint32_t n_files = (uint32_t)files.size();
+    auto file_of_frame = [&](uint64_t fr) -> uint32_t {
+        uint32_t lo = 0, hi = n_files - 1;
+        while (lo < hi)
+        {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (files[mid].first_frame <= fr)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        return lo;
+    };
     auto row_of_frame = [&](uint64_t fr) -> uint64_t {
         if (fr >= tot_frames)
             return tot_rows;
@@ -806,6 +820,17 @@ static std::vector<Wave> plan_waves(const std::vector<Desc> &files, uint64_t tot
                 lo = mid;
             else
                 hi = mid - 1;
+        }
+        if (group_align && lo < tot_frames)
+        {
+            const uint32_t fi = file_of_frame(lo);
+            const uint64_t fpg = quant_frames_per_group(files[fi].channels);
+            const uint64_t local = lo - files[fi].first_frame;
+            uint64_t aligned = files[fi].first_frame + local / fpg * fpg;
+            if (aligned <= f) // would make an empty wave: round up instead (never past the file's end)
+                aligned = std::min<uint64_t>(files[fi].first_frame + (local / fpg + 1) * fpg,
+                                             files[fi].first_frame + files[fi].n_frames);
+            lo = aligned;
         }
         Wave w{f, lo, r0, row_of_frame(lo)};
         mx = std::max(mx, w.r1 - w.r0);
@@ -1025,26 +1050,38 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     if (fast)
         target_rows = UINT64_MAX; // the fused FFT kernel takes the whole batch in one launch
     uint64_t max_wave_rows = 0;
-    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows);
+    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, true);
     float *d_atiles = nullptr;
     uint64_t *d_first_group = nullptr;
+    // frame groups (max(1, 8/ch) frames of one file): the unit of work of quant_pack and of the FAST kernel
+    std::vector<uint64_t> first_group(n_files + 1);
     uint64_t n_groups = 0;
+    for (uint32_t i = 0; i < n_files; ++i)
+    {
+        first_group[i] = n_groups;
+        n_groups += quant_groups_for(files[i].n_frames, files[i].channels);
+    }
+    first_group[n_files] = n_groups;
+    auto group_of_frame = [&](uint64_t fr) -> uint64_t { // fr is group-aligned or a file boundary
+        if (fr >= tot_frames)
+            return n_groups;
+        uint32_t lo = 0, hi = n_files - 1;
+        while (lo < hi)
+        {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (files[mid].first_frame <= fr)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        return first_group[lo] + (fr - files[lo].first_frame) / quant_frames_per_group(files[lo].channels);
+    };
+    CUDA_TRY(dmalloc(&d_first_group, n_files + 1, cs));
+    CUDA_TRY(cudaMemcpyAsync(d_first_group, first_group.data(), 8 * (n_files + 1), cudaMemcpyHostToDevice, cs));
     if (!fast)
     {
         CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
         CUDA_TRY(dmalloc(&d_atiles, mdct_a_tile_floats(max_wave_rows), cs));
-    }
-    else
-    {
-        std::vector<uint64_t> first_group(n_files);
-        for (uint32_t i = 0; i < n_files; ++i)
-        {
-            first_group[i] = n_groups;
-            n_groups += fast_groups_for(files[i].n_frames, files[i].channels);
-        }
-        CUDA_TRY(dmalloc(&d_first_group, n_files, cs));
-        CUDA_TRY(cudaMemcpyAsync(d_first_group, first_group.data(), 8 * n_files, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaStreamSynchronize(cs)); // first_group is a stack vector
     }
     tr.mark("alloc");
 
@@ -1191,8 +1228,9 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             q.coefs = d_coefs - w.r0 * kHop;
             q.files = d_files;
             q.n_files = n_files;
-            q.frame_begin = w.f0;
-            q.frame_end = w.f1;
+            q.first_group = d_first_group;
+            q.group_begin = group_of_frame(w.f0);
+            q.group_end = group_of_frame(w.f1);
             q.perc = enc->d_perc;
             q.slots = d_slots;
             q.nnz = de->d_nnz;
@@ -1592,6 +1630,20 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         return files[lo].out_off + (fr - files[lo].first_frame) * kHop * files[lo].channels;
     };
 
+    auto hop_id = [&](uint64_t fr) -> uint64_t { // batch-wide hop number of the hop that starts at frame `fr`
+        if (fr >= tot_frames)
+            return tot_frames + n_files;
+        uint32_t lo = 0, hi = n_files - 1;
+        while (lo < hi)
+        {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (files[mid].first_frame <= fr)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        return fr + lo;
+    };
     std::vector<cudaEvent_t> used_events;
     if (io)
     {
@@ -1713,8 +1765,8 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             o.raw = d_raw;
             o.files = d_files;
             o.n_files = n_files;
-            o.out_begin = o0;
-            o.out_end = o1;
+            o.hop_begin = hop_id(w.f0);
+            o.hop_end = hop_id(w.f1);
             o.out = d_out;
             CUDA_TRY(launch_ola(o, cs));
         }

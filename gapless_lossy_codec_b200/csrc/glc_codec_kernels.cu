@@ -43,132 +43,152 @@ __device__ __forceinline__ float warp_max(float v)
 }
 
 constexpr int kQPThreads = 256;
+constexpr int kQPWarps = kQPThreads / 32;
 
-// One CTA per frame; loops over the frame's channels (the raw/sparse decision needs all of them).
+// One WARP per frame-channel row, one CTA per group of frames (rows of a group <= 8 when ch <= 8).
+// The psychoacoustic stage has a long strictly sequential reduction (the top "critical band" is
+// 650-850 bins wide and Rust sums it left to right, src/codec.rs:212-215); a row therefore has a
+// ~2 us latency floor that no amount of parallelism inside the row removes.  Mapping a row to a warp
+// keeps up to 64 such chains in flight per SM instead of 8.
+//   lane l holds bins 128 j + 4 l + {0..3}, j = 0..7 (eight float4 loads), so the ordered compaction
+//   is a warp scan per j.
 __global__ void __launch_bounds__(kQPThreads) quant_pack_kernel(const QuantPackLaunch p)
 {
-    __shared__ float s_sq[kHop];
-    __shared__ float s_base[kMaxBands];
-    __shared__ float s_red[kQPThreads / 32];
-    __shared__ uint32_t s_cnt[kQPThreads / 32];
-    __shared__ uint32_t s_total_nnz;
+    __shared__ float s_sq[kQPWarps][kHop];
+    __shared__ float s_base[kQPWarps][kMaxBands];
+    __shared__ uint32_t s_frame_nnz[kQPWarps];
 
-    const uint64_t frame = p.frame_begin + blockIdx.x;
-    if (frame >= p.frame_end)
-        return;
-    const FileDesc &fd = find_file_by_frame(p.files, p.n_files, frame, nullptr);
-    const uint32_t ch = fd.channels;
-    const uint64_t row_f = fd.first_row + (frame - fd.first_frame) * ch;
-    const DevPerceptual &pm = *p.perc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0)
-        s_total_nnz = 0;
-
-    for (uint32_t c = 0; c < ch; ++c)
+    const DevPerceptual &pm = *p.perc;
+    // group -> (file, first frame of the group)
+    const uint64_t g = p.group_begin + blockIdx.x;
+    uint32_t lo = 0, hi = p.n_files - 1;
+    while (lo < hi)
     {
-        const uint64_t row = row_f + c;
-        const float4 cv = __ldg(reinterpret_cast<const float4 *>(p.coefs + row * kHop) + tid);
-        const float cf4[4] = {cv.x, cv.y, cv.z, cv.w};
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (p.first_group[mid] <= g)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const FileDesc &fd = p.files[lo];
+    const uint32_t ch = fd.channels;
+    const uint32_t fpg = kQPWarps / ch ? kQPWarps / ch : 1u;
+    const uint64_t lf0 = (g - p.first_group[lo]) * fpg;
+    const uint32_t n_frames = (uint32_t)min((uint64_t)fpg, fd.n_frames - lf0);
+    const uint32_t n_rows = n_frames * ch;
+    if (tid < kQPWarps)
+        s_frame_nnz[tid] = 0;
+    __syncthreads();
 
-        // scale = max_k |c[k]| .max(1e-10)        (order-free, src/codec.rs:488)
-        float m = fmaxf(fmaxf(fabsf(cf4[0]), fabsf(cf4[1])), fmaxf(fabsf(cf4[2]), fabsf(cf4[3])));
-        m = warp_max(m);
-        __syncthreads(); // previous channel finished with shared scratch
-        if (lane == 0)
-            s_red[warp] = m;
+    for (uint32_t r = warp; r < n_rows; r += kQPWarps)
+    {
+        const uint32_t lf = r / ch;
+        const uint64_t row = fd.first_row + (lf0 + lf) * ch + (r - lf * ch);
+        const float4 *src = reinterpret_cast<const float4 *>(p.coefs + row * kHop);
+        float cf[8][4];
+        float m = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            s_sq[tid * 4 + j] = __fmul_rn(cf4[j], cf4[j]);
-        __syncthreads();
-        float gmax = s_red[0];
-#pragma unroll
-        for (int w = 1; w < kQPThreads / 32; ++w)
-            gmax = fmaxf(gmax, s_red[w]);
-        gmax = fmaxf(gmax, 1e-10f);
-        const float scale = gmax;
-
-        // band energies: strictly left-to-right sums (src/codec.rs:212-215), one thread per band
-        const int n_bands = pm.n_edges - 1;
-        if (tid < n_bands)
+        for (int j = 0; j < 8; ++j)
         {
-            const int lo = pm.band_edges[tid], hi = pm.band_edges[tid + 1];
-            float acc = 0.0f;
-            for (int k = lo; k < hi; ++k)
-                acc = __fadd_rn(acc, s_sq[k]);
-            const float energy = sqrtf(__fdiv_rn(acc, pm.band_cnt[tid]));
-            // energy * 0.01 * compression_factor * perceptual_factor, left to right (:223)
-            float b = __fmul_rn(energy, 0.01f);
-            b = __fmul_rn(b, pm.cf);
-            b = __fmul_rn(b, pm.band_pf[tid]);
-            s_base[tid] = b;
+            const float4 v = __ldg(src + j * 32 + lane);
+            cf[j][0] = v.x;
+            cf[j][1] = v.y;
+            cf[j][2] = v.z;
+            cf[j][3] = v.w;
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            *reinterpret_cast<float4 *>(&s_sq[warp][j * 128 + lane * 4]) =
+                make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w));
         }
-        __syncthreads();
-
-        // thresholds + quantizer (src/codec.rs:226-235, 277-307)
+        // scale = max_k |c[k]| .max(1e-10)        (order-free, src/codec.rs:488)
+        const float gmax = fmaxf(warp_max(m), 1e-10f);
+        const float scale = gmax;
+        __syncwarp();
+        // band energies: strictly left-to-right sums (src/codec.rs:212-215), one lane per band
+        const int n_bands = pm.n_edges - 1;
+        for (int b = lane; b < n_bands; b += 32)
+        {
+            const int blo = pm.band_edges[b], bhi = pm.band_edges[b + 1];
+            float acc = 0.0f;
+            for (int k = blo; k < bhi; ++k)
+                acc = __fadd_rn(acc, s_sq[warp][k]);
+            const float energy = sqrtf(__fdiv_rn(acc, pm.band_cnt[b]));
+            // energy * 0.01 * compression_factor * perceptual_factor, left to right (:223)
+            float bs = __fmul_rn(energy, 0.01f);
+            bs = __fmul_rn(bs, pm.cf);
+            bs = __fmul_rn(bs, pm.band_pf[b]);
+            s_base[warp][b] = bs;
+        }
+        __syncwarp();
+        // thresholds + quantizer (src/codec.rs:226-235, 277-307) + ordered compaction
         const float nf = __fmul_rn(pm.noise_floor_factor, scale);
         const float peak_gate = __fmul_rn(gmax, 0.3f);
         const float peak_cap = __fmul_rn(gmax, 0.05f);
-        glc_pair mine[4];
-        uint32_t cnt = 0;
+        glc_pair *dst = p.slots + row * kHop;
+        uint32_t total = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 8; ++j)
         {
-            const int k = tid * 4 + j;
-            const float v = cf4[j];
-            const float a = fabsf(v);
-            float th = __fmul_rn(s_base[pm.band_of[k]], pm.inv_w[k]);
-            if (a > peak_gate)
-                th = fminf(th, peak_cap);
-            const float th_s = __fmul_rn(th, scale);
-            if (a > nf && a > th_s)
+            // bins 128 j + 4 lane + {0..3}: their inverse weights and band ids are one 16-byte / 4-byte load
+            const float4 iw4 = __ldg(reinterpret_cast<const float4 *>(pm.inv_w) + j * 32 + lane);
+            const uchar4 bo4 = __ldg(reinterpret_cast<const uchar4 *>(pm.band_of) + j * 32 + lane);
+            const float iw[4] = {iw4.x, iw4.y, iw4.z, iw4.w};
+            const unsigned bo[4] = {bo4.x, bo4.y, bo4.z, bo4.w};
+            int qv[4];
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
             {
-                const float qf = roundf(__fmul_rn(__fdiv_rn(v, scale), 32768.0f));
-                const float cl = fminf(fmaxf(qf, -32768.0f), 32767.0f);
-                const int q = __float2int_rz(cl);
-                if (q != 0)
+                const float v = cf[j][e];
+                const float a = fabsf(v);
+                float th = __fmul_rn(s_base[warp][bo[e]], iw[e]);
+                if (a > peak_gate)
+                    th = fminf(th, peak_cap);
+                const float th_s = __fmul_rn(th, scale);
+                int q = 0;
+                if (a > nf && a > th_s)
                 {
-                    mine[cnt].idx = (uint16_t)k;
-                    mine[cnt].q = (int16_t)q;
-                    ++cnt;
+                    const float qf = roundf(__fmul_rn(__fdiv_rn(v, scale), 32768.0f));
+                    q = __float2int_rz(fminf(fmaxf(qf, -32768.0f), 32767.0f));
                 }
+                qv[e] = q;
+                cnt += q != 0;
             }
-        }
-        // ordered compaction: exclusive scan of per-thread counts (thread t owns bins 4t..4t+3)
-        uint32_t incl = cnt;
+            uint32_t incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += n;
-        }
-        if (lane == 31)
-            s_cnt[warp] = incl;
-        __syncthreads();
-        uint32_t warp_off = 0, total = 0;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += n;
+            }
+            uint32_t pos = total + (incl - cnt);
 #pragma unroll
-        for (int w = 0; w < kQPThreads / 32; ++w)
-        {
-            const uint32_t v = s_cnt[w];
-            if (w < warp)
-                warp_off += v;
-            total += v;
+            for (int e = 0; e < 4; ++e)
+                if (qv[e] != 0)
+                {
+                    glc_pair pr;
+                    pr.idx = (uint16_t)(j * 128 + lane * 4 + e);
+                    pr.q = (int16_t)qv[e];
+                    dst[pos++] = pr;
+                }
+            total += __shfl_sync(0xffffffffu, incl, 31);
         }
-        glc_pair *dst = p.slots + row * kHop + warp_off + (incl - cnt);
-        for (uint32_t j = 0; j < cnt; ++j)
-            dst[j] = mine[j];
-        if (tid == 0)
+        if (lane == 0)
         {
             p.nnz[row] = total;
             p.scales[row] = scale;
-            s_total_nnz += total;
+            atomicAdd(&s_frame_nnz[lf % kQPWarps], total);
         }
+        __syncwarp();
     }
     __syncthreads();
-    if (tid == 0)
+    if (tid < (int)n_frames)
     {
         // src/codec.rs:505-521: sum(8 + 4*nnz_c) + 8 + 4*ch + 64  >=  (2048*ch*2) * 0.85
-        const uint64_t compressed = (uint64_t)ch * 8 + (uint64_t)s_total_nnz * 4 + 8 + (uint64_t)ch * 4 + 64;
+        const uint64_t frame = fd.first_frame + lf0 + tid;
+        const uint64_t row_f = fd.first_row + (lf0 + tid) * ch;
+        const uint64_t compressed = (uint64_t)ch * 8 + (uint64_t)s_frame_nnz[tid] * 4 + 8 + (uint64_t)ch * 4 + 64;
         const uint64_t raw_size = (uint64_t)kFrame * ch * 2;
         const float lhs = (float)compressed;
         const float rhs = __fmul_rn((float)raw_size, 0.85f);
@@ -444,35 +464,40 @@ __device__ __forceinline__ float block_value(const OlaLaunch &p, const DecFileDe
     return __ldg(p.blocks + (size_t)slot * kFrame + i);
 }
 
+// One CTA per output hop (1024 sample frames x channels).  Hop h of a file is
+// overlap[ch][i] + block_h[ch][i] (src/codec.rs:695) with overlap = second half of block h-1; the hop after
+// the last frame is the final overlap pushed as is (:723-729).  Hops are numbered batch-wide:
+// hop id = frame index + file index (every file has n_frames + 1 hops).
 __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
 {
-    const uint64_t idx = p.out_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.out_end)
-        return;
+    const uint64_t hop_id = p.hop_begin + blockIdx.x;
     uint32_t lo = 0, hi = p.n_files - 1;
     while (lo < hi)
     {
         const uint32_t mid = (lo + hi + 1) >> 1;
-        if (p.files[mid].out_off <= idx)
+        if (p.files[mid].first_frame + mid <= hop_id)
             lo = mid;
         else
             hi = mid - 1;
     }
     const DecFileDesc fd = p.files[lo];
-    const uint64_t local = idx - fd.out_off;
-    const uint32_t c = (uint32_t)(local % fd.channels);
-    const uint64_t t = local / fd.channels;
-    const uint32_t i = (uint32_t)(t % kHop);
-    const uint64_t h = t / kHop;
-    float v;
-    if (h == fd.n_frames)
-        v = (h == 0) ? 0.0f : block_value(p, fd, h - 1, c, i + kHop); // final overlap, pushed as is (:723-729)
-    else
+    const uint64_t h = hop_id - (fd.first_frame + lo);
+    const uint32_t ch = fd.channels;
+    float *out = p.out + fd.out_off + h * kHop * ch;
+    const bool has_prev = h > 0, has_cur = h < fd.n_frames;
+    for (uint32_t e = threadIdx.x; e < kHop * ch; e += blockDim.x)
     {
-        const float prev = (h == 0) ? 0.0f : block_value(p, fd, h - 1, c, i + kHop);
-        v = __fadd_rn(prev, block_value(p, fd, h, c, i)); // overlap[ch][i] + block[ch][i] (:695)
+        const uint32_t i = e / ch, c = e - i * ch;
+        float v;
+        if (!has_cur)
+            v = has_prev ? block_value(p, fd, h - 1, c, i + kHop) : 0.0f;
+        else
+        {
+            const float prev = has_prev ? block_value(p, fd, h - 1, c, i + kHop) : 0.0f;
+            v = __fadd_rn(prev, block_value(p, fd, h, c, i));
+        }
+        out[e] = v;
     }
-    p.out[idx] = v;
 }
 
 __global__ void fill_kernel(float *p, uint64_t n, float v)
@@ -538,12 +563,20 @@ __global__ void __launch_bounds__(256) fp32x2_issue_kernel(int iters, float *sin
 
 } // namespace
 
+// Frames are grouped per file so that a CTA (8 warps, one row each) never straddles two files:
+// frames per group = max(1, 8 / channels).
+uint64_t quant_groups_for(uint32_t n_frames, uint32_t channels)
+{
+    const uint32_t fpg = kQPWarps / channels ? kQPWarps / channels : 1u;
+    return ((uint64_t)n_frames + fpg - 1) / fpg;
+}
+uint32_t quant_frames_per_group(uint32_t channels) { return kQPWarps / channels ? kQPWarps / channels : 1u; }
+
 cudaError_t launch_quant_pack(const QuantPackLaunch &p, cudaStream_t s)
 {
-    if (p.frame_end <= p.frame_begin)
+    if (p.group_end <= p.group_begin)
         return cudaSuccess;
-    const uint64_t n = p.frame_end - p.frame_begin;
-    quant_pack_kernel<<<(unsigned)n, kQPThreads, 0, s>>>(p);
+    quant_pack_kernel<<<(unsigned)(p.group_end - p.group_begin), kQPThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -577,9 +610,9 @@ cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s)
 
 cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s)
 {
-    if (p.out_end <= p.out_begin)
+    if (p.hop_end <= p.hop_begin)
         return cudaSuccess;
-    ola_kernel<<<(unsigned)((p.out_end - p.out_begin + 255) / 256), 256, 0, s>>>(p);
+    ola_kernel<<<(unsigned)(p.hop_end - p.hop_begin), 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

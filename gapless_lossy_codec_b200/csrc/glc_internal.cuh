@@ -106,10 +106,11 @@ cudaError_t launch_imdct_exact(const ImdctLaunch &p, cudaStream_t s);
 
 struct QuantPackLaunch
 {
-    const float *coefs; // [n_rows][1024]
+    const float *coefs; // [n_rows][1024], indexed by absolute row
     const FileDesc *files;
     uint32_t n_files;
-    uint64_t frame_begin, frame_end; // batch-wide frame range handled by this launch
+    const uint64_t *first_group;     // [n_files] first frame group of each file (quant_groups_for, scanned)
+    uint64_t group_begin, group_end; // groups handled by this launch
     const DevPerceptual *perc;
     glc_pair *slots;    // [n_rows][1024]
     uint32_t *nnz;      // [n_rows]
@@ -117,6 +118,8 @@ struct QuantPackLaunch
     uint8_t *is_raw;    // [n_frames_total]
     uint32_t *raw_len;  // [n_frames_total] 0 or 2048*ch
 };
+uint64_t quant_groups_for(uint32_t n_frames, uint32_t channels);
+uint32_t quant_frames_per_group(uint32_t channels);
 cudaError_t launch_quant_pack(const QuantPackLaunch &p, cudaStream_t s);
 
 // exclusive scans: u32 -> u64, n+1 outputs
@@ -186,7 +189,7 @@ struct OlaLaunch
     const int16_t *raw;
     const DecFileDesc *files;
     uint32_t n_files;
-    uint64_t out_begin, out_end; // range of output values produced by this launch
+    uint64_t hop_begin, hop_end; // batch-wide hop ids (frame index + file index) produced by this launch
     float *out;               // per file interleaved, (n_frames+1)*1024*ch values at out_off
 };
 cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s);
