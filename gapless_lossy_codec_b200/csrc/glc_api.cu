@@ -631,6 +631,7 @@ cudaError_t dev_alloc(glc_ctx *ctx, void **out, size_t bytes, cudaStream_t s) { 
 void dev_free(glc_ctx *ctx, void *p, cudaStream_t s) { ctx->dpool.release(p, s); }
 int ctx_device(glc_ctx *ctx) { return ctx->device; }
 cudaStream_t ctx_compute_stream(glc_ctx *ctx) { return ctx->compute; }
+cudaStream_t ctx_d2h_stream(glc_ctx *ctx) { return ctx->d2h; }
 void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n) { ctx->stats.launches[kernel_id] += n; }
 void ctx_count_bytes(glc_ctx *ctx, uint64_t h2d, uint64_t d2h)
 {

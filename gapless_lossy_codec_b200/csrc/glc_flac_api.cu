@@ -39,52 +39,89 @@ struct Md5
     uint8_t buf[64];
     uint32_t fill = 0;
     static inline uint32_t rol(uint32_t x, int s) { return (x << s) | (x >> (32 - s)); }
+    // RFC 1321 compression function, fully unrolled (the chain a->d->c->b is the serial critical path
+    // of the whole FLAC encode of one file: about 5 cycles per step)
     void block(const uint8_t *p)
     {
-        static const uint32_t K[64] = {
-            0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
-            0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
-            0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
-            0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
-            0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
-            0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
-            0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
-            0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
-        static const int S[4][4] = {{7, 12, 17, 22}, {5, 9, 14, 20}, {4, 11, 16, 23}, {6, 10, 15, 21}};
         uint32_t x[16];
         memcpy(x, p, 64); // little-endian host
         uint32_t a = st[0], b = st[1], c = st[2], d = st[3];
-        for (int i = 0; i < 64; ++i)
-        {
-            uint32_t f;
-            int g;
-            const int r = i >> 4;
-            if (r == 0)
-            {
-                f = (b & c) | (~b & d);
-                g = i;
-            }
-            else if (r == 1)
-            {
-                f = (d & b) | (~d & c);
-                g = (5 * i + 1) & 15;
-            }
-            else if (r == 2)
-            {
-                f = b ^ c ^ d;
-                g = (3 * i + 5) & 15;
-            }
-            else
-            {
-                f = c ^ (b | ~d);
-                g = (7 * i) & 15;
-            }
-            const uint32_t t = d;
-            d = c;
-            c = b;
-            b = b + rol(a + f + K[i] + x[g], S[r][i & 3]);
-            a = t;
-        }
+#define MD5_F(b, c, d) ((d) ^ ((b) & ((c) ^ (d))))
+#define MD5_G(b, c, d) ((c) ^ ((d) & ((b) ^ (c))))
+#define MD5_H(b, c, d) ((b) ^ (c) ^ (d))
+#define MD5_I(b, c, d) ((c) ^ ((b) | ~(d)))
+#define MD5_STEP(f, a, b, c, d, xk, s, k) \
+    a += f(b, c, d) + (xk) + (k);          \
+    a = rol(a, s) + b;
+        MD5_STEP(MD5_F, a, b, c, d, x[0], 7, 0xd76aa478u)
+        MD5_STEP(MD5_F, d, a, b, c, x[1], 12, 0xe8c7b756u)
+        MD5_STEP(MD5_F, c, d, a, b, x[2], 17, 0x242070dbu)
+        MD5_STEP(MD5_F, b, c, d, a, x[3], 22, 0xc1bdceeeu)
+        MD5_STEP(MD5_F, a, b, c, d, x[4], 7, 0xf57c0fafu)
+        MD5_STEP(MD5_F, d, a, b, c, x[5], 12, 0x4787c62au)
+        MD5_STEP(MD5_F, c, d, a, b, x[6], 17, 0xa8304613u)
+        MD5_STEP(MD5_F, b, c, d, a, x[7], 22, 0xfd469501u)
+        MD5_STEP(MD5_F, a, b, c, d, x[8], 7, 0x698098d8u)
+        MD5_STEP(MD5_F, d, a, b, c, x[9], 12, 0x8b44f7afu)
+        MD5_STEP(MD5_F, c, d, a, b, x[10], 17, 0xffff5bb1u)
+        MD5_STEP(MD5_F, b, c, d, a, x[11], 22, 0x895cd7beu)
+        MD5_STEP(MD5_F, a, b, c, d, x[12], 7, 0x6b901122u)
+        MD5_STEP(MD5_F, d, a, b, c, x[13], 12, 0xfd987193u)
+        MD5_STEP(MD5_F, c, d, a, b, x[14], 17, 0xa679438eu)
+        MD5_STEP(MD5_F, b, c, d, a, x[15], 22, 0x49b40821u)
+        MD5_STEP(MD5_G, a, b, c, d, x[1], 5, 0xf61e2562u)
+        MD5_STEP(MD5_G, d, a, b, c, x[6], 9, 0xc040b340u)
+        MD5_STEP(MD5_G, c, d, a, b, x[11], 14, 0x265e5a51u)
+        MD5_STEP(MD5_G, b, c, d, a, x[0], 20, 0xe9b6c7aau)
+        MD5_STEP(MD5_G, a, b, c, d, x[5], 5, 0xd62f105du)
+        MD5_STEP(MD5_G, d, a, b, c, x[10], 9, 0x02441453u)
+        MD5_STEP(MD5_G, c, d, a, b, x[15], 14, 0xd8a1e681u)
+        MD5_STEP(MD5_G, b, c, d, a, x[4], 20, 0xe7d3fbc8u)
+        MD5_STEP(MD5_G, a, b, c, d, x[9], 5, 0x21e1cde6u)
+        MD5_STEP(MD5_G, d, a, b, c, x[14], 9, 0xc33707d6u)
+        MD5_STEP(MD5_G, c, d, a, b, x[3], 14, 0xf4d50d87u)
+        MD5_STEP(MD5_G, b, c, d, a, x[8], 20, 0x455a14edu)
+        MD5_STEP(MD5_G, a, b, c, d, x[13], 5, 0xa9e3e905u)
+        MD5_STEP(MD5_G, d, a, b, c, x[2], 9, 0xfcefa3f8u)
+        MD5_STEP(MD5_G, c, d, a, b, x[7], 14, 0x676f02d9u)
+        MD5_STEP(MD5_G, b, c, d, a, x[12], 20, 0x8d2a4c8au)
+        MD5_STEP(MD5_H, a, b, c, d, x[5], 4, 0xfffa3942u)
+        MD5_STEP(MD5_H, d, a, b, c, x[8], 11, 0x8771f681u)
+        MD5_STEP(MD5_H, c, d, a, b, x[11], 16, 0x6d9d6122u)
+        MD5_STEP(MD5_H, b, c, d, a, x[14], 23, 0xfde5380cu)
+        MD5_STEP(MD5_H, a, b, c, d, x[1], 4, 0xa4beea44u)
+        MD5_STEP(MD5_H, d, a, b, c, x[4], 11, 0x4bdecfa9u)
+        MD5_STEP(MD5_H, c, d, a, b, x[7], 16, 0xf6bb4b60u)
+        MD5_STEP(MD5_H, b, c, d, a, x[10], 23, 0xbebfbc70u)
+        MD5_STEP(MD5_H, a, b, c, d, x[13], 4, 0x289b7ec6u)
+        MD5_STEP(MD5_H, d, a, b, c, x[0], 11, 0xeaa127fau)
+        MD5_STEP(MD5_H, c, d, a, b, x[3], 16, 0xd4ef3085u)
+        MD5_STEP(MD5_H, b, c, d, a, x[6], 23, 0x04881d05u)
+        MD5_STEP(MD5_H, a, b, c, d, x[9], 4, 0xd9d4d039u)
+        MD5_STEP(MD5_H, d, a, b, c, x[12], 11, 0xe6db99e5u)
+        MD5_STEP(MD5_H, c, d, a, b, x[15], 16, 0x1fa27cf8u)
+        MD5_STEP(MD5_H, b, c, d, a, x[2], 23, 0xc4ac5665u)
+        MD5_STEP(MD5_I, a, b, c, d, x[0], 6, 0xf4292244u)
+        MD5_STEP(MD5_I, d, a, b, c, x[7], 10, 0x432aff97u)
+        MD5_STEP(MD5_I, c, d, a, b, x[14], 15, 0xab9423a7u)
+        MD5_STEP(MD5_I, b, c, d, a, x[5], 21, 0xfc93a039u)
+        MD5_STEP(MD5_I, a, b, c, d, x[12], 6, 0x655b59c3u)
+        MD5_STEP(MD5_I, d, a, b, c, x[3], 10, 0x8f0ccc92u)
+        MD5_STEP(MD5_I, c, d, a, b, x[10], 15, 0xffeff47du)
+        MD5_STEP(MD5_I, b, c, d, a, x[1], 21, 0x85845dd1u)
+        MD5_STEP(MD5_I, a, b, c, d, x[8], 6, 0x6fa87e4fu)
+        MD5_STEP(MD5_I, d, a, b, c, x[15], 10, 0xfe2ce6e0u)
+        MD5_STEP(MD5_I, c, d, a, b, x[6], 15, 0xa3014314u)
+        MD5_STEP(MD5_I, b, c, d, a, x[13], 21, 0x4e0811a1u)
+        MD5_STEP(MD5_I, a, b, c, d, x[4], 6, 0xf7537e82u)
+        MD5_STEP(MD5_I, d, a, b, c, x[11], 10, 0xbd3af235u)
+        MD5_STEP(MD5_I, c, d, a, b, x[2], 15, 0x2ad7d2bbu)
+        MD5_STEP(MD5_I, b, c, d, a, x[9], 21, 0xeb86d391u)
+#undef MD5_STEP
+#undef MD5_F
+#undef MD5_G
+#undef MD5_H
+#undef MD5_I
         st[0] += a;
         st[1] += b;
         st[2] += c;
@@ -131,35 +168,6 @@ struct Md5
         memcpy(out, st, 16);
     }
 };
-
-// MD5 over ((s*32767).clamp(-32768,32767) as i16) little-endian, src/flac.rs:955-958, 305-318
-void md5_of_pcm(const float *pcm, uint64_t n, uint8_t out[16])
-{
-    Md5 m;
-    int16_t chunk[4096];
-    uint64_t i = 0;
-    while (i < n)
-    {
-        const uint64_t take = std::min<uint64_t>(4096, n - i);
-        for (uint64_t j = 0; j < take; ++j)
-        {
-            const float v = pcm[i + j] * 32767.0f;
-            int16_t q;
-            if (v != v)
-                q = 0;
-            else if (v <= -32768.0f)
-                q = -32768;
-            else if (v >= 32767.0f)
-                q = 32767;
-            else
-                q = (int16_t)(int32_t)v;
-            chunk[j] = q;
-        }
-        m.update(reinterpret_cast<const uint8_t *>(chunk), take * 2);
-        i += take;
-    }
-    m.finish(out);
-}
 
 struct BitOut
 {
@@ -226,18 +234,20 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
         max_bs = std::max<uint32_t>(max_bs, (uint32_t)bs);
     }
 
-    // ---- MD5 on host threads, overlapped with everything below ----
+    // ---- MD5 (src/flac.rs:1004 -> :305-318) is a serial chain per file.  The f32 -> i16 conversion is
+    //      already done by pass A on the device, so the converted samples come back in 32 MB chunks on
+    //      the d2h stream while pass B runs, and host threads (one per file) hash each chunk as soon
+    //      as its event fires: the hash is the only thing left on the host's critical path. ----
     std::vector<std::vector<uint8_t>> md5(n_files, std::vector<uint8_t>(16));
     std::vector<std::thread> workers;
+    struct CopyOp
     {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned nthreads = std::min<unsigned>(hw, n_files);
-        for (unsigned t = 0; t < nthreads; ++t)
-            workers.emplace_back([&, t]() {
-                for (uint32_t i = t; i < n_files; i += nthreads)
-                    md5_of_pcm(pcm[i], n_samples[i], md5[i].data());
-            });
-    }
+        uint64_t off, cnt; // samples within the file
+        uint32_t event;    // index of the event that covers this chunk
+    };
+    std::vector<std::vector<CopyOp>> ops(n_files);
+    std::vector<cudaEvent_t> chunk_events;
+    int16_t *h_i16 = nullptr;
     auto join_all = [&]() {
         for (auto &w : workers)
             if (w.joinable())
@@ -300,6 +310,68 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
         ctx_time_begin(ctx, GLC_K_SCAN, &tok);
         FL_STEP(launch_scan_u32_u64(d_fbytes, d_foff, tot_blocks, cs));
         ctx_time_end(ctx, tok);
+
+        {
+            // converted samples -> pinned host memory, chunk by chunk, behind pass A
+            const uint64_t kChunk = 16ull << 20; // samples (32 MB)
+            h_i16 = (int16_t *)pinned_alloc(ctx, std::max<uint64_t>(tot_pcm, 1) * 2);
+            if (!h_i16)
+            {
+                st = set_error(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+                break;
+            }
+            cudaStream_t ds = ctx_d2h_stream(ctx);
+            cudaEvent_t ev_a;
+            FL_STEP(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+            chunk_events.push_back(ev_a);
+            FL_STEP(cudaEventRecord(ev_a, cs));
+            FL_STEP(cudaStreamWaitEvent(ds, ev_a, 0));
+            uint64_t pending = 0;
+            bool bad2 = false;
+            for (uint32_t i = 0; i < n_files && !bad2; ++i)
+                for (uint64_t off = 0; off < n_samples[i] && !bad2; off += kChunk)
+                {
+                    const uint64_t cnt = std::min<uint64_t>(kChunk, n_samples[i] - off);
+                    if (cudaMemcpyAsync(h_i16 + files[i].i16_off + off, d_i16 + files[i].i16_off + off, cnt * 2,
+                                        cudaMemcpyDeviceToHost, ds) != cudaSuccess)
+                        bad2 = true;
+                    pending += cnt;
+                    ops[i].push_back({off, cnt, (uint32_t)chunk_events.size()});
+                    const bool last = (i + 1 == n_files) && (off + cnt >= n_samples[i]);
+                    if (pending >= kChunk || last)
+                    {
+                        cudaEvent_t ev;
+                        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
+                            cudaEventRecord(ev, ds) != cudaSuccess)
+                            bad2 = true;
+                        chunk_events.push_back(ev);
+                        pending = 0;
+                    }
+                }
+            if (bad2)
+            {
+                st = set_error(GLC_ERR_CUDA, "D2H of converted samples failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            ctx_count_bytes(ctx, 0, tot_pcm * 2);
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const unsigned nthreads = std::min<unsigned>(hw, n_files);
+            const int device = ctx_device(ctx);
+            for (unsigned t = 0; t < nthreads; ++t)
+                workers.emplace_back([&, t, nthreads, device]() {
+                    cudaSetDevice(device);
+                    for (uint32_t i = t; i < n_files; i += nthreads)
+                    {
+                        Md5 m;
+                        for (const CopyOp &op : ops[i])
+                        {
+                            cudaEventSynchronize(chunk_events[op.event]);
+                            m.update(reinterpret_cast<const uint8_t *>(h_i16 + files[i].i16_off + op.off), op.cnt * 2);
+                        }
+                        m.finish(md5[i].data());
+                    }
+                });
+        }
 
         // frame sizes come back to the host: total size, largest frame, per-file extents
         h_fbytes = (uint32_t *)pinned_alloc(ctx, std::max<uint64_t>(tot_blocks, 1) * 4);
@@ -390,6 +462,10 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
     }
     if (h_fbytes)
         pinned_release(ctx, h_fbytes);
+    if (h_i16)
+        pinned_release(ctx, h_i16);
+    for (cudaEvent_t e : chunk_events)
+        cudaEventDestroy(e);
     dev_free(ctx, d_pcm, cs);
     dev_free(ctx, d_i16, cs);
     dev_free(ctx, d_files, cs);

@@ -178,6 +178,14 @@ __device__ __forceinline__ void load_block(const FlacLaunch &p, const FlacFileDe
             const uint32_t i = e / g.ch, c = e - i * g.ch;
             s_smp[c * g.bs + i] = (int16_t)q;
         }
+        // The MD5 covers every converted sample (src/flac.rs:1004), also a trailing partial sample
+        // frame that no block encodes (input length not a multiple of the channel count).
+        if (g.frame_no + 1 == fd.n_blocks)
+        {
+            const uint64_t done = g.smp_off + n;
+            for (uint64_t e = done + threadIdx.x; e < fd.n_samples; e += blockDim.x)
+                p.i16_arena[fd.i16_off + e] = (int16_t)f32_to_i16(__ldg(p.pcm_arena + fd.pcm_off + e));
+        }
     }
     else
     {
