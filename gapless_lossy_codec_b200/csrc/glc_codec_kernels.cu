@@ -363,17 +363,34 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         s_bits[tid] = 0;
     __syncthreads();
 
-    // pass 1: index union (any pair with idx < 1024 counts, also ones a later duplicate overwrites)
+    // pass 1: index union (any pair with idx < 1024 counts, also ones a later duplicate overwrites).
+    // Each lane walks a contiguous chunk of the row's pairs and merges bits of the same 32-bin word
+    // before touching shared memory: ascending indices would otherwise make all 32 lanes hit one word.
     for (uint32_t r = warp; r < rows_here; r += 8)
     {
         const uint64_t row = p.active_rows[tile * kBM + r];
-        const uint64_t b = p.pair_off[row], e = p.pair_off[row + 1];
-        for (uint64_t j = b + lane; j < e; j += 32)
+        const uint64_t b = p.pair_off[row];
+        const uint32_t n = (uint32_t)(p.pair_off[row + 1] - b);
+        const uint32_t chunk = (n + 31) / 32;
+        const uint32_t j0 = min(n, lane * chunk), j1 = min(n, j0 + chunk);
+        uint32_t cur = 0xffffffffu, mask = 0;
+        for (uint32_t j = j0; j < j1; ++j)
         {
-            const uint32_t idx = p.pairs[j].idx;
-            if (idx < kHop)
-                atomicOr(&s_bits[idx >> 5], 1u << (idx & 31));
+            const uint32_t idx = p.pairs[b + j].idx;
+            if (idx >= kHop)
+                continue;
+            const uint32_t w = idx >> 5;
+            if (w != cur)
+            {
+                if (mask)
+                    atomicOr(&s_bits[cur], mask);
+                cur = w;
+                mask = 0;
+            }
+            mask |= 1u << (idx & 31);
         }
+        if (mask)
+            atomicOr(&s_bits[cur], mask);
     }
     __syncthreads();
     if (warp == 0)
@@ -468,8 +485,19 @@ __device__ __forceinline__ float block_value(const OlaLaunch &p, const DecFileDe
 // overlap[ch][i] + block_h[ch][i] (src/codec.rs:695) with overlap = second half of block h-1; the hop after
 // the last frame is the final overlap pushed as is (:723-729).  Hops are numbered batch-wide:
 // hop id = frame index + file index (every file has n_frames + 1 hops).
+// Where each (channel, frame) half comes from is resolved once per CTA; the loop is 2 loads + 1 add.
+struct OlaSrc
+{
+    const float *blk;   // transformed block half (already offset), or null
+    const int16_t *raw; // raw frame body (frame base), or null; read interleaved (src/codec.rs:633-640)
+    uint32_t raw_len;   // i16 values in the raw frame
+};
+
+constexpr int kOlaMaxCh = 16;
+
 __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
 {
+    __shared__ OlaSrc s_prev[kOlaMaxCh], s_cur[kOlaMaxCh];
     const uint64_t hop_id = p.hop_begin + blockIdx.x;
     uint32_t lo = 0, hi = p.n_files - 1;
     while (lo < hi)
@@ -485,6 +513,58 @@ __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
     const uint32_t ch = fd.channels;
     float *out = p.out + fd.out_off + h * kHop * ch;
     const bool has_prev = h > 0, has_cur = h < fd.n_frames;
+    const bool fast_path = ch <= kOlaMaxCh;
+    if (fast_path && threadIdx.x < 2 * ch)
+    {
+        const uint32_t c = threadIdx.x % ch;
+        const bool is_cur = threadIdx.x >= ch;
+        OlaSrc d{nullptr, nullptr, 0};
+        if (is_cur ? has_cur : has_prev)
+        {
+            const uint64_t lf = is_cur ? h : h - 1;
+            const uint64_t frame = fd.first_frame + lf;
+            if (p.is_raw[frame])
+            {
+                d.raw = p.raw + p.raw_off[frame];
+                d.raw_len = (uint32_t)(p.raw_off[frame + 1] - p.raw_off[frame]);
+            }
+            else
+            {
+                const int32_t slot = p.row_slot[fd.first_row + lf * ch + c];
+                if (slot >= 0)
+                    d.blk = p.blocks + (size_t)slot * kFrame + (is_cur ? 0 : kHop);
+            }
+        }
+        (is_cur ? s_cur : s_prev)[c] = d;
+    }
+    __syncthreads();
+    if (fast_path)
+    {
+        auto fetch = [&](const OlaSrc &d, uint32_t c, uint32_t i) -> float {
+            if (d.blk)
+                return __ldg(d.blk + i);
+            if (d.raw)
+            {
+                const uint32_t si = i * ch + c;
+                return si < d.raw_len ? __fdiv_rn((float)d.raw[si], 32767.0f) : 0.0f;
+            }
+            return 0.0f; // no coefficients: (0 * norm) * window[i] = +0.0
+        };
+        for (uint32_t e = threadIdx.x; e < kHop * ch; e += blockDim.x)
+        {
+            const uint32_t i = e / ch, c = e - i * ch;
+            float v;
+            if (!has_cur)
+                v = has_prev ? fetch(s_prev[c], c, i + (s_prev[c].raw ? kHop : 0)) : 0.0f;
+            else
+            {
+                const float prev = has_prev ? fetch(s_prev[c], c, i + (s_prev[c].raw ? kHop : 0)) : 0.0f;
+                v = __fadd_rn(prev, fetch(s_cur[c], c, i));
+            }
+            out[e] = v;
+        }
+        return;
+    }
     for (uint32_t e = threadIdx.x; e < kHop * ch; e += blockDim.x)
     {
         const uint32_t i = e / ch, c = e - i * ch;

@@ -127,18 +127,6 @@ __device__ __forceinline__ uint32_t zigzag(int r) // src/flac.rs:560-567
     return r >= 0 ? ((uint32_t)r << 1) : ((((uint32_t)(-(r + 1))) << 1) | 1u);
 }
 
-// src/flac.rs:515-552: floor(log2(mean)) capped at 14 (the "adjust" branch can never fire)
-__device__ __forceinline__ uint32_t rice_param(unsigned long long sum_abs, uint32_t n)
-{
-    if (n == 0)
-        return 0;
-    const unsigned long long mean = sum_abs / n;
-    if (mean == 0)
-        return 0;
-    const int lg = 63 - __clzll((long long)mean);
-    return lg < 14 ? (uint32_t)lg : 14u;
-}
-
 __device__ __forceinline__ uint32_t header_bytes(uint32_t bs, uint32_t frame_no)
 {
     uint32_t n = 4;
@@ -161,41 +149,154 @@ __device__ __forceinline__ uint32_t header_bytes(uint32_t bs, uint32_t frame_no)
     return n + 1; // + CRC-8
 }
 
-// loads the block's samples as planar i16 into shared memory: s[c*bs + i]
+// loads the block's samples as planar i16 into shared memory: s[c*bs + i].  Four samples per load
+// (float4 from the PCM arena / 8-byte loads from the i16 arena), all of a thread's loads issued before
+// the first use so that several are in flight.  File starts are 4-sample aligned in both arenas and
+// every block before a file's last one holds a multiple of 4 samples, so the vector path applies
+// whenever (block offset) % 4 == 0.
+__device__ __forceinline__ void scatter_sample(int16_t *s_smp, const BlockGeom &g, uint32_t e, int q)
+{
+    uint32_t i, c;
+    if (g.ch == 1)
+    {
+        i = e;
+        c = 0;
+    }
+    else if (g.ch == 2)
+    {
+        i = e >> 1;
+        c = e & 1u;
+    }
+    else
+    {
+        i = e / g.ch;
+        c = e - i * g.ch;
+    }
+    s_smp[c * g.bs + i] = (int16_t)q;
+}
+
 template <bool FROM_F32>
 __device__ __forceinline__ void load_block(const FlacLaunch &p, const FlacFileDesc &fd, const BlockGeom &g,
                                            int16_t *s_smp)
 {
     const uint32_t n = g.bs * g.ch;
-    if (FROM_F32)
+    const float *src = p.pcm_arena + fd.pcm_off + g.smp_off;
+    int16_t *arena = p.i16_arena + fd.i16_off + g.smp_off;
+    const uint32_t n4 = (g.smp_off & 3ull) == 0 ? n / 4 : 0; // vectorisable quads
+    constexpr int kBatch = 4;
+    for (uint32_t q0 = threadIdx.x; q0 < n4; q0 += blockDim.x * kBatch)
     {
-        const float *src = p.pcm_arena + fd.pcm_off + g.smp_off;
-        int16_t *arena = p.i16_arena + fd.i16_off + g.smp_off;
-        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x)
+        if (FROM_F32)
         {
-            const int q = f32_to_i16(__ldg(src + e));
-            arena[e] = (int16_t)q;
-            const uint32_t i = e / g.ch, c = e - i * g.ch;
-            s_smp[c * g.bs + i] = (int16_t)q;
+            float4 v[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+            {
+                const uint32_t q = q0 + u * blockDim.x;
+                if (q < n4)
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(src) + q);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+            {
+                const uint32_t q = q0 + u * blockDim.x;
+                if (q < n4)
+                {
+                    const int a = f32_to_i16(v[u].x), b = f32_to_i16(v[u].y), c = f32_to_i16(v[u].z), d = f32_to_i16(v[u].w);
+                    short4 o;
+                    o.x = (short)a;
+                    o.y = (short)b;
+                    o.z = (short)c;
+                    o.w = (short)d;
+                    reinterpret_cast<short4 *>(arena)[q] = o;
+                    scatter_sample(s_smp, g, 4 * q, a);
+                    scatter_sample(s_smp, g, 4 * q + 1, b);
+                    scatter_sample(s_smp, g, 4 * q + 2, c);
+                    scatter_sample(s_smp, g, 4 * q + 3, d);
+                }
+            }
         }
+        else
+        {
+            short4 v[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+            {
+                const uint32_t q = q0 + u * blockDim.x;
+                if (q < n4)
+                    v[u] = reinterpret_cast<const short4 *>(arena)[q];
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+            {
+                const uint32_t q = q0 + u * blockDim.x;
+                if (q < n4)
+                {
+                    scatter_sample(s_smp, g, 4 * q, v[u].x);
+                    scatter_sample(s_smp, g, 4 * q + 1, v[u].y);
+                    scatter_sample(s_smp, g, 4 * q + 2, v[u].z);
+                    scatter_sample(s_smp, g, 4 * q + 3, v[u].w);
+                }
+            }
+        }
+    }
+    for (uint32_t e = 4 * n4 + threadIdx.x; e < n; e += blockDim.x)
+    {
+        int q;
+        if (FROM_F32)
+        {
+            q = f32_to_i16(__ldg(src + e));
+            arena[e] = (int16_t)q;
+        }
+        else
+            q = arena[e];
+        scatter_sample(s_smp, g, e, q);
+    }
+    if (FROM_F32 && g.frame_no + 1 == fd.n_blocks)
+    {
         // The MD5 covers every converted sample (src/flac.rs:1004), also a trailing partial sample
         // frame that no block encodes (input length not a multiple of the channel count).
-        if (g.frame_no + 1 == fd.n_blocks)
-        {
-            const uint64_t done = g.smp_off + n;
-            for (uint64_t e = done + threadIdx.x; e < fd.n_samples; e += blockDim.x)
-                p.i16_arena[fd.i16_off + e] = (int16_t)f32_to_i16(__ldg(p.pcm_arena + fd.pcm_off + e));
-        }
+        const uint64_t done = g.smp_off + n;
+        for (uint64_t e = done + threadIdx.x; e < fd.n_samples; e += blockDim.x)
+            p.i16_arena[fd.i16_off + e] = (int16_t)f32_to_i16(__ldg(p.pcm_arena + fd.pcm_off + e));
     }
-    else
-    {
-        const int16_t *src = p.i16_arena + fd.i16_off + g.smp_off;
-        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x)
-        {
-            const uint32_t i = e / g.ch, c = e - i * g.ch;
-            s_smp[c * g.bs + i] = src[e];
-        }
-    }
+}
+
+constexpr int kMaxRun = 16; // samples per thread and channel: block sizes never exceed 4096 (src/flac.rs:983-995)
+
+__device__ __forceinline__ uint32_t rice_param32(uint32_t sum_abs, uint32_t n) // src/flac.rs:515-552
+{
+    if (n == 0)
+        return 0;
+    const uint32_t mean = sum_abs / n;
+    if (mean == 0)
+        return 0;
+    const int lg = 31 - __clz((int)mean);
+    return lg < 14 ? (uint32_t)lg : 14u;
+}
+
+// Thread t owns samples i = t + 256 j (j < kMaxRun) of the channel: consecutive threads read
+// consecutive shared-memory words, and when the partition size is a multiple of 32 a whole warp
+// lies in one partition, so per-partition sums are one hardware warp reduction + one atomic.
+struct ChannelPlan
+{
+    int order, po;
+    uint32_t dps, nparts;
+    bool warp_uniform; // every warp's 32 samples share a partition
+    int dps_shift;     // log2(dps) when dps is a power of two, else -1
+    __device__ __forceinline__ uint32_t part_of(uint32_t i) const { return dps_shift >= 0 ? i >> dps_shift : i / dps; }
+};
+
+__device__ __forceinline__ ChannelPlan plan_channel(int level, uint32_t bs)
+{
+    ChannelPlan cp;
+    cp.order = predictor_order(level, bs);
+    cp.po = cp.order ? partition_order(level, bs, cp.order) : 0;
+    cp.dps = bs >> cp.po;
+    cp.nparts = 1u << cp.po;
+    cp.warp_uniform = (cp.dps & 31u) == 0;
+    cp.dps_shift = (cp.dps & (cp.dps - 1u)) == 0 ? (__ffs(cp.dps) - 1) : -1;
+    return cp;
 }
 
 // ------------------------------------------------------------------ pass A
@@ -205,7 +306,9 @@ __global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLa
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int16_t *s_smp = reinterpret_cast<int16_t *>(smem_raw);
-    __shared__ unsigned long long s_part_bits[kMaxParts];
+    __shared__ uint32_t s_psum[kMaxParts];
+    __shared__ uint32_t s_k[kMaxParts];
+    __shared__ uint32_t s_bits;
     __shared__ unsigned long long s_total_bits;
 
     const uint64_t b = blockIdx.x;
@@ -214,64 +317,83 @@ __global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLa
     const BlockGeom g = locate_block(p.files, p.n_files, b);
     const FlacFileDesc &fd = p.files[g.file];
     load_block<true>(p, fd, g, s_smp);
-    if (threadIdx.x == 0)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const ChannelPlan cp = plan_channel(p.level, g.bs);
+    if (tid == 0)
         s_total_bits = 0;
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int order = predictor_order(p.level, g.bs);
-    const int po = order ? partition_order(p.level, g.bs, order) : 0;
-    const uint32_t nparts = 1u << po, dps = g.bs >> po;
 
     for (uint32_t c = 0; c < g.ch; ++c)
     {
-        const int16_t *s = s_smp + c * g.bs;
-        uint8_t *kout = rice_k + (b * max_ch + c) * kMaxParts;
-        if (order == 0)
+        __syncthreads();
+        if (cp.order == 0)
         {
-            if (threadIdx.x == 0)
+            if (tid == 0)
                 s_total_bits += 8ull + 16ull * g.bs; // verbatim subframe, src/flac.rs:722-729
             continue;
         }
-        for (uint32_t part = warp; part < nparts; part += kFlacThreads / 32)
+        if (tid < kMaxParts)
+            s_psum[tid] = 0;
+        if (tid == 0)
+            s_bits = 0;
+        __syncthreads();
+        const int16_t *s = s_smp + c * g.bs;
+        uint32_t zz[kMaxRun];
+        // ---- residuals and per-partition sums of |r| ----
+#pragma unroll
+        for (int j = 0; j < kMaxRun; ++j)
         {
-            const uint32_t lo = part == 0 ? (uint32_t)order : part * dps;
-            const uint32_t hi = (part + 1) * dps;
-            unsigned long long sum = 0;
-            for (uint32_t i = lo + lane; i < hi; i += 32)
+            const uint32_t i = tid + kFlacThreads * j;
+            const bool valid = i < g.bs && i >= (uint32_t)cp.order;
+            int r = 0;
+            if (valid)
+                r = residual_at(s, i, cp.order);
+            zz[j] = valid ? zigzag(r) : 0xffffffffu;
+            const uint32_t a = (uint32_t)(r < 0 ? -r : r);
+            if (kFlacThreads * j >= g.bs)
+                continue; // uniform: nothing left in this block
+            if (cp.warp_uniform)
             {
-                const int r = residual_at(s, i, order);
-                sum += (unsigned long long)(r < 0 ? -r : r);
+                const uint32_t sum = __reduce_add_sync(0xffffffffu, a);
+                const uint32_t i0 = i - lane; // first sample of this warp
+                if (lane == 0 && i0 < g.bs)
+                    atomicAdd(&s_psum[cp.part_of(i0)], sum);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const uint32_t cnt = hi - lo;
-            const uint32_t k = rice_param(sum, cnt);
-            unsigned long long bits = 0;
-            for (uint32_t i = lo + lane; i < hi; i += 32)
-                bits += (zigzag(residual_at(s, i, order)) >> k) + 1u + k;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                bits += __shfl_xor_sync(0xffffffffu, bits, o);
-            if (lane == 0)
-            {
-                s_part_bits[part] = cnt ? bits + 4ull : 0ull; // empty first partition writes nothing (:632-635)
-                kout[part] = (uint8_t)k;
-            }
+            else if (valid)
+                atomicAdd(&s_psum[cp.part_of(i)], a);
         }
         __syncthreads();
-        if (threadIdx.x == 0)
+        uint8_t *kout = rice_k + (b * max_ch + c) * kMaxParts;
+        if ((uint32_t)tid < cp.nparts)
         {
-            unsigned long long t = 8ull + 16ull * order + 6ull;
-            for (uint32_t part = 0; part < nparts; ++part)
-                t += s_part_bits[part];
-            s_total_bits += t;
+            const uint32_t cnt = tid == 0 ? cp.dps - (uint32_t)cp.order : cp.dps;
+            const uint32_t k = rice_param32(s_psum[tid], cnt);
+            s_k[tid] = k;
+            kout[tid] = (uint8_t)k;
+            if (cnt)
+                atomicAdd(&s_bits, 4u); // an empty first partition writes nothing (:632-635)
         }
         __syncthreads();
+        // ---- code lengths ----
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxRun; ++j)
+        {
+            const uint32_t i = tid + kFlacThreads * j;
+            if (zz[j] != 0xffffffffu)
+            {
+                const uint32_t k = s_k[cp.part_of(i)];
+                mine += (zz[j] >> k) + 1u + k;
+            }
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0)
+            atomicAdd(&s_bits, mine);
+        __syncthreads();
+        if (tid == 0)
+            s_total_bits += 8ull + 16ull * cp.order + 6ull + s_bits;
     }
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (tid == 0)
     {
         const unsigned long long body = (s_total_bits + 7ull) >> 3;
         p.frame_bytes[b] = (uint32_t)(header_bytes(g.bs, g.frame_no) + body + 2ull);
@@ -280,56 +402,18 @@ __global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLa
 
 // ------------------------------------------------------------------ pass B
 
-struct BitWriter
+// OR the low `nbits` (<= 32) bits of v into the big-endian bit buffer at bit position `pos`
+__device__ __forceinline__ void put_bits(uint32_t *buf, unsigned long long pos, uint32_t v, int nbits)
 {
-    uint32_t *buf;
-    uint32_t wi;
-    unsigned long long acc;
-    int nacc;
-    __device__ __forceinline__ void init(uint32_t *b, unsigned long long bitpos)
-    {
-        buf = b;
-        wi = (uint32_t)(bitpos >> 5);
-        nacc = (int)(bitpos & 31);
-        acc = 0;
-    }
-    // append the low n bits of v (n <= 31), MSB first
-    __device__ __forceinline__ void put(uint32_t v, int n)
-    {
-        acc = (acc << n) | v;
-        nacc += n;
-        if (nacc >= 32)
-        {
-            atomicOr(buf + wi, (uint32_t)(acc >> (nacc - 32)));
-            ++wi;
-            nacc -= 32;
-            acc &= (1ull << nacc) - 1ull;
-        }
-    }
-    // append z zero bits (the buffer is pre-zeroed)
-    __device__ __forceinline__ void skip(uint32_t z)
-    {
-        const uint32_t total = (uint32_t)nacc + z;
-        if (total >= 32)
-        {
-            if (acc)
-                atomicOr(buf + wi, (uint32_t)(acc << (32 - nacc)));
-            wi += total >> 5;
-            nacc = (int)(total & 31);
-            acc = 0;
-        }
-        else
-        {
-            acc <<= z;
-            nacc = (int)total;
-        }
-    }
-    __device__ __forceinline__ void finish()
-    {
-        if (nacc && acc)
-            atomicOr(buf + wi, (uint32_t)(acc << (32 - nacc)));
-    }
-};
+    const uint32_t word = (uint32_t)(pos >> 5);
+    const int off = (int)(pos & 31);
+    const unsigned long long w = (unsigned long long)v << (64 - nbits - off);
+    const uint32_t hi = (uint32_t)(w >> 32), lo = (uint32_t)w;
+    if (hi)
+        atomicOr(buf + word, hi);
+    if (lo)
+        atomicOr(buf + word + 1, lo);
+}
 
 __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b) // mod x^16+x^15+x^2+1
 {
@@ -351,7 +435,118 @@ __device__ __forceinline__ uint32_t buf_byte(const volatile uint32_t *buf, uint3
     return (buf[j >> 2] >> (24 - 8 * (j & 3))) & 0xffu;
 }
 
-__global__ void __launch_bounds__(kFlacThreads) flac_emit_kernel(const FlacLaunch p, const uint8_t *rice_k, uint32_t max_ch,
+__device__ void write_frame_header(uint32_t *bitbuf, const BlockGeom &g)
+{
+    // frame header, src/flac.rs:759-871
+    uint8_t h[16];
+    uint32_t n = 0;
+    h[n++] = 0xFF;
+    h[n++] = 0xF8;
+    uint32_t bsb;
+    switch (g.bs)
+    {
+    case 192: bsb = 1; break;
+    case 576: bsb = 2; break;
+    case 1152: bsb = 3; break;
+    case 2304: bsb = 4; break;
+    case 4608: bsb = 5; break;
+    case 256: bsb = 8; break;
+    case 512: bsb = 9; break;
+    case 1024: bsb = 10; break;
+    case 2048: bsb = 11; break;
+    case 4096: bsb = 12; break;
+    case 8192: bsb = 13; break;
+    case 16384: bsb = 14; break;
+    case 32768: bsb = 15; break;
+    default: bsb = g.bs < 256 ? 6 : 7; break;
+    }
+    uint32_t srb;
+    switch (g.rate)
+    {
+    case 88200: srb = 1; break;
+    case 176400: srb = 2; break;
+    case 192000: srb = 3; break;
+    case 8000: srb = 4; break;
+    case 16000: srb = 5; break;
+    case 22050: srb = 6; break;
+    case 24000: srb = 7; break;
+    case 32000: srb = 8; break;
+    case 44100: srb = 9; break;
+    case 48000: srb = 10; break;
+    case 96000: srb = 11; break;
+    default: srb = 0; break;
+    }
+    h[n++] = (uint8_t)((bsb << 4) | srb);
+    const uint32_t chb = g.ch == 1 ? 0 : (g.ch == 2 ? 1 : ((g.ch - 1) & 0xF));
+    h[n++] = (uint8_t)((chb << 4) | (4u << 1)); // 16 bits per sample -> 0b100, reserved 0
+    const uint32_t v = g.frame_no; // UTF-8 style number, src/flac.rs:427-478
+    if (v < 0x80)
+        h[n++] = (uint8_t)v;
+    else if (v < 0x800)
+    {
+        h[n++] = (uint8_t)(0xC0 | ((v >> 6) & 0x1F));
+        h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+    }
+    else if (v < 0x10000)
+    {
+        h[n++] = (uint8_t)(0xE0 | ((v >> 12) & 0x0F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+    }
+    else if (v < 0x200000)
+    {
+        h[n++] = (uint8_t)(0xF0 | ((v >> 18) & 0x07));
+        h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+    }
+    else if (v < 0x4000000)
+    {
+        h[n++] = (uint8_t)(0xF8 | ((v >> 24) & 0x03));
+        h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+    }
+    else if (v < 0x80000000u)
+    {
+        h[n++] = (uint8_t)(0xFC | ((v >> 30) & 0x01));
+        h[n++] = (uint8_t)(0x80 | ((v >> 24) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+    }
+    else
+    {
+        h[n++] = 0xFE;
+        h[n++] = (uint8_t)(0x80 | ((v >> 30) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 24) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
+        h[n++] = (uint8_t)(0x80 | (v & 0x3F));
+    }
+    if (bsb == 6)
+        h[n++] = (uint8_t)((g.bs - 1) & 0xFF);
+    else if (bsb == 7)
+    {
+        h[n++] = (uint8_t)(((g.bs - 1) >> 8) & 0xFF);
+        h[n++] = (uint8_t)((g.bs - 1) & 0xFF);
+    }
+    uint32_t c8 = 0; // CRC-8 poly 0x07, src/flac.rs:19-51
+    for (uint32_t j = 0; j < n; ++j)
+    {
+        c8 ^= h[j];
+        for (int i = 0; i < 8; ++i)
+            c8 = (c8 & 0x80u) ? (((c8 << 1) ^ 0x07u) & 0xFFu) : ((c8 << 1) & 0xFFu);
+    }
+    h[n++] = (uint8_t)c8;
+    for (uint32_t j = 0; j < n; ++j)
+        put_bits(bitbuf, 8ull * j, h[j], 8);
+}
+
+__global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLaunch p, const uint8_t *rice_k, uint32_t max_ch,
                                                                  const uint64_t *frame_off, uint8_t *out_arena,
                                                                  uint32_t smp_bytes, uint32_t buf_words,
                                                                  uint32_t *g_scratch /* null = bit buffer in smem */)
@@ -360,10 +555,12 @@ __global__ void __launch_bounds__(kFlacThreads) flac_emit_kernel(const FlacLaunc
     int16_t *s_smp = reinterpret_cast<int16_t *>(smem_raw);
     uint32_t *bitbuf = g_scratch ? g_scratch + (size_t)blockIdx.x * buf_words
                                  : reinterpret_cast<uint32_t *>(smem_raw + smp_bytes);
-    __shared__ uint32_t s_scan[kFlacThreads / 32];
+    constexpr int kWarps = kFlacThreads / 32;
+    __shared__ uint32_t s_wtot[kMaxRun * kWarps]; // code bits per (run step j, warp), in sample order
+    __shared__ uint32_t s_chan_total;
     __shared__ uint16_t s_crc_tab[256];
     __shared__ uint16_t s_xpow[32];
-    __shared__ uint32_t s_crc_part[kFlacThreads / 32];
+    __shared__ uint32_t s_crc_part[kWarps];
     __shared__ unsigned long long s_bitpos;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -400,230 +597,176 @@ __global__ void __launch_bounds__(kFlacThreads) flac_emit_kernel(const FlacLaunc
         const uint32_t hbytes = header_bytes(g.bs, g.frame_no);
         if (tid == 0)
         {
-            // frame header, src/flac.rs:759-871
-            uint8_t h[16];
-            uint32_t n = 0;
-            h[n++] = 0xFF;
-            h[n++] = 0xF8;
-            uint32_t bsb;
-            switch (g.bs)
-            {
-            case 192: bsb = 1; break;
-            case 576: bsb = 2; break;
-            case 1152: bsb = 3; break;
-            case 2304: bsb = 4; break;
-            case 4608: bsb = 5; break;
-            case 256: bsb = 8; break;
-            case 512: bsb = 9; break;
-            case 1024: bsb = 10; break;
-            case 2048: bsb = 11; break;
-            case 4096: bsb = 12; break;
-            case 8192: bsb = 13; break;
-            case 16384: bsb = 14; break;
-            case 32768: bsb = 15; break;
-            default: bsb = g.bs < 256 ? 6 : 7; break;
-            }
-            uint32_t srb;
-            switch (g.rate)
-            {
-            case 88200: srb = 1; break;
-            case 176400: srb = 2; break;
-            case 192000: srb = 3; break;
-            case 8000: srb = 4; break;
-            case 16000: srb = 5; break;
-            case 22050: srb = 6; break;
-            case 24000: srb = 7; break;
-            case 32000: srb = 8; break;
-            case 44100: srb = 9; break;
-            case 48000: srb = 10; break;
-            case 96000: srb = 11; break;
-            default: srb = 0; break;
-            }
-            h[n++] = (uint8_t)((bsb << 4) | srb);
-            const uint32_t chb = g.ch == 1 ? 0 : (g.ch == 2 ? 1 : ((g.ch - 1) & 0xF));
-            h[n++] = (uint8_t)((chb << 4) | (4u << 1)); // 16 bits per sample -> 0b100, reserved 0
-            const uint32_t v = g.frame_no; // UTF-8 style number, src/flac.rs:427-478
-            if (v < 0x80)
-                h[n++] = (uint8_t)v;
-            else if (v < 0x800)
-            {
-                h[n++] = (uint8_t)(0xC0 | ((v >> 6) & 0x1F));
-                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
-            }
-            else if (v < 0x10000)
-            {
-                h[n++] = (uint8_t)(0xE0 | ((v >> 12) & 0x0F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
-            }
-            else if (v < 0x200000)
-            {
-                h[n++] = (uint8_t)(0xF0 | ((v >> 18) & 0x07));
-                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
-            }
-            else if (v < 0x4000000)
-            {
-                h[n++] = (uint8_t)(0xF8 | ((v >> 24) & 0x03));
-                h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
-            }
-            else if (v < 0x80000000u)
-            {
-                h[n++] = (uint8_t)(0xFC | ((v >> 30) & 0x01));
-                h[n++] = (uint8_t)(0x80 | ((v >> 24) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
-            }
-            else
-            {
-                h[n++] = 0xFE;
-                h[n++] = (uint8_t)(0x80 | ((v >> 30) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 24) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 18) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 12) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | ((v >> 6) & 0x3F));
-                h[n++] = (uint8_t)(0x80 | (v & 0x3F));
-            }
-            if (bsb == 6)
-                h[n++] = (uint8_t)((g.bs - 1) & 0xFF);
-            else if (bsb == 7)
-            {
-                h[n++] = (uint8_t)(((g.bs - 1) >> 8) & 0xFF);
-                h[n++] = (uint8_t)((g.bs - 1) & 0xFF);
-            }
-            uint32_t c8 = 0; // CRC-8 poly 0x07, src/flac.rs:19-51
-            for (uint32_t j = 0; j < n; ++j)
-            {
-                c8 ^= h[j];
-                for (int i = 0; i < 8; ++i)
-                    c8 = (c8 & 0x80u) ? (((c8 << 1) ^ 0x07u) & 0xFFu) : ((c8 << 1) & 0xFFu);
-            }
-            h[n++] = (uint8_t)c8;
-            BitWriter w;
-            w.init(bitbuf, 0);
-            for (uint32_t j = 0; j < n; ++j)
-                w.put(h[j], 8);
-            w.finish();
+            write_frame_header(bitbuf, g);
             s_bitpos = (unsigned long long)hbytes * 8ull;
         }
         __syncthreads();
 
-        const int order = predictor_order(p.level, g.bs);
-        const int po = order ? partition_order(p.level, g.bs, order) : 0;
-        const uint32_t dps = g.bs >> po;
-        const uint32_t per_thread = (g.bs + kFlacThreads - 1) / kFlacThreads;
+        const ChannelPlan cp = plan_channel(p.level, g.bs);
+        const int order = cp.order;
+        const uint32_t n_steps = (g.bs + kFlacThreads - 1) / kFlacThreads;
 
         for (uint32_t c = 0; c < g.ch; ++c)
         {
             const int16_t *s = s_smp + c * g.bs;
             const uint8_t *kin = rice_k + (b * max_ch + c) * kMaxParts;
             const unsigned long long sub0 = s_bitpos; // first bit of this subframe
-            const uint32_t lo = min(g.bs, (uint32_t)tid * per_thread);
-            const uint32_t hi = min(g.bs, lo + per_thread);
-            const uint32_t first = max(lo, (uint32_t)order);
-
-            // bits this thread will emit for the residual section (or the verbatim samples)
-            uint32_t mine = 0;
             if (order == 0)
-                mine = (hi - lo) * 16u;
-            else
-                for (uint32_t i = first; i < hi; ++i)
+            {
+                // verbatim subframe: 0 | 000001 | 0, then the samples (src/flac.rs:704-729)
+                if (tid == 0)
+                    put_bits(bitbuf, sub0, 0x02u, 8);
+                for (uint32_t i = tid; i < g.bs; i += kFlacThreads)
+                    put_bits(bitbuf, sub0 + 8ull + 16ull * i, (uint32_t)(uint16_t)s[i], 16);
+                __syncthreads();
+                if (tid == 0)
+                    s_bitpos = sub0 + 8ull + 16ull * g.bs;
+                __syncthreads();
+                continue;
+            }
+            // ---- code lengths in sample order: (step j, warp, lane) ----
+            uint32_t zz[kMaxRun], len[kMaxRun];
+#pragma unroll
+            for (int j = 0; j < kMaxRun; ++j)
+            {
+                const uint32_t i = tid + kFlacThreads * j;
+                zz[j] = 0;
+                len[j] = 0;
+                if ((uint32_t)j >= n_steps)
+                    continue;
+                if (i < g.bs && i >= (uint32_t)order)
                 {
-                    const uint32_t part = i / dps;
+                    const uint32_t part = cp.part_of(i);
                     const uint32_t k = kin[part];
-                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * dps;
-                    mine += (zigzag(residual_at(s, i, order)) >> k) + 1u + k + (i == pstart ? 4u : 0u);
+                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * cp.dps;
+                    zz[j] = zigzag(residual_at(s, i, order));
+                    len[j] = (zz[j] >> k) + 1u + k + (i == pstart ? 4u : 0u);
                 }
-            uint32_t incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o)
-                    incl += t;
+                const uint32_t wsum = __reduce_add_sync(0xffffffffu, len[j]);
+                if (lane == 0)
+                    s_wtot[j * kWarps + warp] = wsum;
             }
-            if (lane == 31)
-                s_scan[warp] = incl;
             __syncthreads();
-            uint32_t woff = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kFlacThreads / 32; ++w)
+            if (warp == 0)
             {
-                if (w < warp)
-                    woff += s_scan[w];
-                total += s_scan[w];
+                // exclusive scan of the n_steps * 8 warp totals (<= 128 values, 4 per lane)
+                uint32_t v[4], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    const uint32_t idx = lane * 4 + q;
+                    v[q] = idx < n_steps * kWarps ? s_wtot[idx] : 0u;
+                    sum += v[q];
+                }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o)
+                        incl += t;
+                }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    const uint32_t idx = lane * 4 + q;
+                    if (idx < n_steps * kWarps)
+                        s_wtot[idx] = run;
+                    run += v[q];
+                }
+                if (lane == 31)
+                    s_chan_total = incl;
             }
-            const unsigned long long fixed = 8ull + (order ? 16ull * order + 6ull : 0ull);
-            BitWriter w;
+            __syncthreads();
+            const unsigned long long fixed = 8ull + 16ull * order + 6ull;
             if (tid == 0)
             {
                 // subframe header + warm-up + residual header, src/flac.rs:704-720, 733-736, 611-614
-                w.init(bitbuf, sub0);
-                w.put(order == 0 ? 0x02u : ((0x08u | (uint32_t)order) << 1), 8); // 0 | type(6) | 0
+                put_bits(bitbuf, sub0, (0x08u | (uint32_t)order) << 1, 8); // 0 | 001ooo | 0
                 for (int i = 0; i < order; ++i)
-                    w.put((uint32_t)(uint16_t)s[i], 16);
-                if (order)
-                    w.put((uint32_t)po, 6); // method 00 + partition order
-                w.finish();
+                    put_bits(bitbuf, sub0 + 8ull + 16ull * i, (uint32_t)(uint16_t)s[i], 16);
+                put_bits(bitbuf, sub0 + 8ull + 16ull * order, (uint32_t)cp.po, 6); // method 00 + partition order
             }
-            w.init(bitbuf, sub0 + fixed + woff + (incl - mine));
-            if (order == 0)
-                for (uint32_t i = lo; i < hi; ++i)
-                    w.put((uint32_t)(uint16_t)s[i], 16);
-            else
-                for (uint32_t i = first; i < hi; ++i)
+#pragma unroll
+            for (int j = 0; j < kMaxRun; ++j)
+            {
+                if ((uint32_t)j >= n_steps)
+                    continue;
+                uint32_t incl = len[j];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
                 {
-                    const uint32_t part = i / dps;
-                    const uint32_t k = kin[part];
-                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * dps;
-                    if (i == pstart)
-                        w.put(k, 4);
-                    const uint32_t u = zigzag(residual_at(s, i, order));
-                    w.skip(u >> k);                                // unary zeros
-                    w.put((1u << k) | (u & ((1u << k) - 1u)), (int)k + 1); // stop bit + k low bits
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o)
+                        incl += t;
                 }
-            w.finish();
+                if (len[j])
+                {
+                    const uint32_t i = tid + kFlacThreads * j;
+                    const uint32_t part = cp.part_of(i);
+                    const uint32_t k = kin[part];
+                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * cp.dps;
+                    unsigned long long pos = sub0 + fixed + s_wtot[j * kWarps + warp] + (incl - len[j]);
+                    if (i == pstart)
+                    {
+                        put_bits(bitbuf, pos, k, 4);
+                        pos += 4;
+                    }
+                    // unary zeros (the buffer is zeroed), then the stop bit and the k low bits
+                    put_bits(bitbuf, pos + (zz[j] >> k), (1u << k) | (zz[j] & ((1u << k) - 1u)), (int)k + 1);
+                }
+            }
             __syncthreads();
             if (tid == 0)
-                s_bitpos = sub0 + fixed + total;
+                s_bitpos = sub0 + fixed + s_chan_total;
             __syncthreads();
         }
 
-        // ---- CRC-16 over bytes [0, nb) ----
+        // ---- CRC-16 over bytes [0, nb): the frame is right-aligned in a virtual buffer of 256 chunks of
+        //      2^m bytes (leading zero bytes do not change a CRC with init 0), every thread hashes its
+        //      chunk with the table, then chunks are merged pairwise: crc(A|B) = crc(A) x^(8|B|) + crc(B),
+        //      with x^(8 * 2^j) mod P tabulated ----
         const uint32_t nb = fbytes - 2;
         {
-            const uint32_t cb = (nb + kFlacThreads - 1) / kFlacThreads;
-            const uint32_t b0 = min(nb, (uint32_t)tid * cb), b1 = min(nb, b0 + cb);
+            uint32_t m = 0;
+            while (((uint32_t)kFlacThreads << m) < nb)
+                ++m;
+            const uint32_t chunk = 1u << m;
+            const uint32_t pad = kFlacThreads * chunk - nb;
+            const uint32_t v0 = (uint32_t)tid * chunk, v1 = v0 + chunk;
+            const uint32_t b0 = v0 > pad ? v0 - pad : 0u, b1 = v1 > pad ? v1 - pad : 0u;
             uint32_t crc = 0;
-            for (uint32_t j = b0; j < b1; ++j)
-                crc = ((crc << 8) & 0xffffu) ^ s_crc_tab[((crc >> 8) ^ buf_byte(bitbuf, j)) & 0xffu];
-            // append (nb - b1) zero bytes: multiply by x^(8*(nb-b1)) mod P
-            uint32_t e = nb - b1;
-            for (int j = 0; e; ++j, e >>= 1)
-                if (e & 1u)
-                    crc = gf16_mul(crc, s_xpow[j]);
+            uint32_t j = b0;
+            auto step = [&](uint32_t byte) { crc = ((crc << 8) & 0xffffu) ^ s_crc_tab[((crc >> 8) ^ byte) & 0xffu]; };
+            for (; j < b1 && (j & 3u); ++j)
+                step(buf_byte(bitbuf, j));
+            for (; j + 4 <= b1; j += 4)
+            {
+                const uint32_t w = bitbuf[j >> 2];
+                step(w >> 24);
+                step((w >> 16) & 0xffu);
+                step((w >> 8) & 0xffu);
+                step(w & 0xffu);
+            }
+            for (; j < b1; ++j)
+                step(buf_byte(bitbuf, j));
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+            for (int l = 0; l < 5; ++l)
+            {
+                const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << l);
+                crc = gf16_mul(crc, s_xpow[m + l]) ^ other;
+            }
             if (lane == 0)
                 s_crc_part[warp] = crc;
-        }
-        __syncthreads();
-        if (tid == 0)
-        {
-            uint32_t crc = 0;
-            for (int w = 0; w < kFlacThreads / 32; ++w)
-                crc ^= s_crc_part[w];
-            BitWriter w;
-            w.init(bitbuf, (unsigned long long)nb * 8ull);
-            w.put(crc & 0xffffu, 16);
-            w.finish();
+            __syncthreads();
+            if (tid == 0)
+            {
+                uint32_t acc = 0;
+                for (int w = 0; w < kWarps; ++w)
+                    acc = gf16_mul(acc, s_xpow[m + 5]) ^ s_crc_part[w];
+                put_bits(bitbuf, (unsigned long long)nb * 8ull, acc & 0xffffu, 16);
+            }
         }
         __syncthreads();
         uint8_t *dst = out_arena + frame_off[b];
