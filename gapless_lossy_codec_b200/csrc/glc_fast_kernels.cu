@@ -23,6 +23,8 @@
 // Compiled with FMA contraction ON (this file only).
 #include <math.h>
 
+#include <algorithm>
+
 #include "glc_fft_gen.cuh"
 #include "glc_internal.cuh"
 
@@ -35,20 +37,27 @@ namespace
 constexpr int kFastThreads = 128;            // 4 warps
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastFcs = 8;                  // frame-channels per CTA (4 pairs)
-constexpr int kXchStride = 33;               // float2 per (fc,k2) row of the exchange buffer (bank skew)
-constexpr int kXchFloat2 = 2 * 16 * kXchStride; // per warp: 2 frame-channels x 16 rows
-constexpr int kCoefStride = 1025;            // floats per frame-channel in the coefficient buffer (bank skew)
+constexpr int kCoefStride = kHop;            // floats per frame-channel in the coefficient buffer
 
 struct FastSmem
 {
-    float2 u[kFastFcs][kHop / 2];        // folded + windowed input as (u[2n], u[N-1-2n]) pairs, 32 KiB
-    float2 xch[kFastWarps][kXchFloat2];  // per-warp exchange buffer, reused as coefficient buffer (8448 B each)
+    // folded + windowed input as (u[2n], u[N-1-2n]) pairs, 4 KiB per frame-channel.  The two rows of
+    // a pair are reused in place, first as the FFT exchange buffer ([fc][k2][n1 ^ k2], XOR-swizzled
+    // instead of padded so that it fits exactly), then as the coefficient buffer ([fc][1024] floats).
+    float2 u[kFastFcs][kHop / 2];
     float inv_w[kHop];
     float band_base[kFastWarps][kMaxBands];
+    float band_fac[kMaxBands];  // 0.01 * compression_factor * perceptual_factor        src/codec.rs:221-223
+    float band_rcnt[kMaxBands]; // 1 / bins in the band
+    int16_t band_lo[kMaxBands], band_hi[kMaxBands];
     uint8_t band_of[kHop];
     uint32_t frame_nnz[kFastFcs];
+    int n_bands;
+    // staging descriptors of the group's frame-channels
+    const float *st_ptr[kFastFcs];
+    long long st_base[kFastFcs];
+    int st_interior[kFastFcs];
 };
-static_assert(sizeof(float2) * kXchFloat2 >= sizeof(float) * 2 * kCoefStride, "coefficient buffer must fit the exchange buffer");
 
 // per-lane twiddle constants, computed once per thread
 struct LaneTw
@@ -67,17 +76,17 @@ __device__ __forceinline__ void load_lane_tw(LaneTw &tw, const float2 *table, in
     tw.qb = __ldg(table + 32 * 16 + (lane & 15));
 }
 
-// DCT-IV of two frame-channels whose (u[2n], u[N-1-2n]) pairs are in u_a / u_b (shared memory).
-// Results (times `norm`) land in coef[0..1023] (first) and coef[kCoefStride..] (second), which
-// alias the warp's exchange buffer.  All 32 lanes must call.
-__device__ __forceinline__ void dct4_pair(const float2 *u_a, const float2 *u_b, const LaneTw &tw, float2 *xch, int lane)
+// DCT-IV of two frame-channels whose (u[2n], u[N-1-2n]) pairs are the two consecutive rows at `pair`
+// (shared memory, 2 x 512 float2).  Results (times `norm`) replace them in place: coefficients of the
+// first at ((float*)pair)[0..1023], of the second at [1024..2047].  All 32 lanes must call.
+__device__ __forceinline__ void dct4_pair(float2 *pair, const LaneTw &tw, int lane)
 {
     using namespace fastfft;
     // ---- pass 1: lane = n1, 16-point FFT over n2 for each of the two inputs ----
 #pragma unroll
     for (int f = 0; f < 2; ++f)
     {
-        const float2 *u = f ? u_b : u_a;
+        float2 *u = pair + f * (kHop / 2);
         float re[16], im[16];
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2)
@@ -87,11 +96,12 @@ __device__ __forceinline__ void dct4_pair(const float2 *u_a, const float2 *u_b, 
             im[n2] = v.x * kPreStepIm[n2] + v.y * kPreStepRe[n2];
         }
         fft16(re, im);
+        __syncwarp(); // every lane holds its column: the row can be overwritten
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2)
         {
             const int s = kBitrev16[k2];
-            xch[(f * 16 + k2) * kXchStride + lane] =
+            u[k2 * 32 + (lane ^ k2)] =
                 make_float2(re[s] * tw.t[k2].x - im[s] * tw.t[k2].y, re[s] * tw.t[k2].y + im[s] * tw.t[k2].x);
         }
     }
@@ -99,16 +109,19 @@ __device__ __forceinline__ void dct4_pair(const float2 *u_a, const float2 *u_b, 
     // ---- pass 2: lane = (f, k2), 32-point FFT over n1 ----
     const int f = lane >> 4, k2 = lane & 15;
     float re[32], im[32];
-#pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1)
     {
-        const float2 v = xch[(f * 16 + k2) * kXchStride + n1];
-        re[n1] = v.x;
-        im[n1] = v.y;
+        const float2 *x = pair + f * (kHop / 2) + k2 * 32;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1)
+        {
+            const float2 v = x[n1 ^ k2];
+            re[n1] = v.x;
+            im[n1] = v.y;
+        }
     }
     fft32(re, im);
     __syncwarp(); // every lane has its column: the buffer can be overwritten with coefficients
-    float *coef = reinterpret_cast<float *>(xch) + f * kCoefStride;
+    float *coef = reinterpret_cast<float *>(pair) + f * kCoefStride;
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1)
     {
@@ -171,44 +184,67 @@ __device__ __forceinline__ GroupGeom locate_group(const uint64_t *first_group, c
 
 // ------------------------------------------------------------------ encode
 
-__global__ void __launch_bounds__(kFastThreads, 3) fast_encode_kernel(const FastEncodeLaunch p)
+// Persistent CTAs: the perceptual tables and the lane twiddles are loaded once, then the CTA walks
+// frame groups with a grid stride.
+__global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const FastEncodeLaunch p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DevPerceptual &pm = *p.perc;
-
-    const GroupGeom gg = locate_group(p.first_group, p.files, p.n_files, p.group_begin + blockIdx.x);
-    const FileDesc fd = p.files[gg.file];
-    const uint32_t ch = fd.channels;
-    const uint32_t n_fc = gg.n_frames * ch; // may exceed kFastFcs only when ch > 8 (then processed in rounds)
-
-    for (int k = tid; k < kHop; k += kFastThreads)
     {
-        sm.inv_w[k] = pm.inv_w[k];
-        sm.band_of[k] = pm.band_of[k];
+        const DevPerceptual &pm = *p.perc;
+        for (int k = tid; k < kHop; k += kFastThreads)
+        {
+            sm.inv_w[k] = pm.inv_w[k];
+            sm.band_of[k] = pm.band_of[k];
+        }
+        const int nb = pm.n_edges - 1;
+        if (tid < nb)
+        {
+            sm.band_lo[tid] = (int16_t)pm.band_edges[tid];
+            sm.band_hi[tid] = (int16_t)pm.band_edges[tid + 1];
+            sm.band_fac[tid] = 0.01f * pm.cf * pm.band_pf[tid];
+            sm.band_rcnt[tid] = 1.0f / pm.band_cnt[tid];
+        }
+        if (tid == 0)
+            sm.n_bands = nb;
     }
-    if (tid < kFastFcs)
-        sm.frame_nnz[tid] = 0;
+    const float noise_floor_factor = p.perc->noise_floor_factor;
     LaneTw tw;
     load_lane_tw(tw, p.twiddles, lane);
-    const float *src = p.pcm_arena + fd.pcm_off;
-    const long long len = (long long)fd.len;
 
-    for (uint32_t fc0 = 0; fc0 < n_fc; fc0 += kFastFcs)
+    for (uint64_t g = p.group_begin + blockIdx.x; g < p.group_end; g += gridDim.x)
     {
-        const uint32_t fcs_here = min((uint32_t)kFastFcs, n_fc - fc0);
-        __syncthreads();
-        // ---- stage: fold + window, (u[2n], u[N-1-2n]) per n, over the reference's padded signal
-        //      (512 zeros + data + zero tail, src/codec.rs:433-447) ----
-        for (uint32_t fc = 0; fc < fcs_here; ++fc)
+        __syncthreads(); // tables ready / previous group done with shared memory
+        const GroupGeom gg = locate_group(p.first_group, p.files, p.n_files, g);
+        const FileDesc fd = p.files[gg.file];
+        const uint32_t ch = fd.channels;
+        const uint32_t n_fc = gg.n_frames * ch; // may exceed kFastFcs only when ch > 8 (then processed in rounds)
+        if (tid < kFastFcs)
+            sm.frame_nnz[tid] = 0;
+        const float *src = p.pcm_arena + fd.pcm_off;
+        const long long len = (long long)fd.len;
+        const int n_bands = sm.n_bands;
+
+        for (uint32_t fc0 = 0; fc0 < n_fc; fc0 += kFastFcs)
         {
-            const uint32_t lf = (fc0 + fc) / ch, c = (fc0 + fc) - lf * ch;
-            const long long base = (long long)((gg.frame0 + lf) * kHop) - kHop / 2; // sample index of i = 0
-            const bool interior = base >= 0 && base + kFrame <= len;               // no padding inside this frame
-            const float *fb = src + base * (long long)ch + c;                        // only dereferenced in range
+            const uint32_t fcs_here = min((uint32_t)kFastFcs, n_fc - fc0);
+            __syncthreads();
+            // ---- stage: fold + window, (u[2n], u[N-1-2n]) per n, over the reference's padded signal
+            //      (512 zeros + data + zero tail, src/codec.rs:433-447).  A thread takes the same n of
+            //      every frame-channel of the group: the two window values are loaded once and up to
+            //      32 PCM loads are in flight before the first use. ----
+            if (tid < (int)fcs_here)
+            {
+                const uint32_t lf = (fc0 + tid) / ch, c = (fc0 + tid) - lf * ch;
+                const long long base = (long long)((gg.frame0 + lf) * kHop) - kHop / 2; // sample index of i = 0
+                sm.st_base[tid] = base;
+                sm.st_ptr[tid] = src + base * (long long)ch + c; // only dereferenced in range
+                sm.st_interior[tid] = base >= 0 && base + kFrame <= len; // no padding inside this frame
+            }
+            __syncthreads();
             const int ich = (int)ch;
-#pragma unroll
+#pragma unroll 1
             for (int it = 0; it < (kHop / 2) / kFastThreads; ++it)
             {
                 const int n = tid + it * kFastThreads;
@@ -230,163 +266,206 @@ __global__ void __launch_bounds__(kFastThreads, 3) fast_encode_kernel(const Fast
                     i2 = 512 + 2 * n;
                     i3 = 2559 - 2 * n;
                 }
-                float x0, x1, x2, x3;
-                if (interior)
+                float x[kFastFcs][4];
+#pragma unroll
+                for (int fc = 0; fc < kFastFcs; ++fc)
                 {
-                    x0 = __ldg(fb + i0 * ich);
-                    x1 = __ldg(fb + i1 * ich);
-                    x2 = __ldg(fb + i2 * ich);
-                    x3 = __ldg(fb + i3 * ich);
+                    x[fc][0] = x[fc][1] = x[fc][2] = x[fc][3] = 0.0f;
+                    if ((uint32_t)fc < fcs_here)
+                    {
+                        const float *fb = sm.st_ptr[fc];
+                        if (sm.st_interior[fc])
+                        {
+                            x[fc][0] = __ldg(fb + i0 * ich);
+                            x[fc][1] = __ldg(fb + i1 * ich);
+                            x[fc][2] = __ldg(fb + i2 * ich);
+                            x[fc][3] = __ldg(fb + i3 * ich);
+                        }
+                        else
+                        {
+                            const long long base = sm.st_base[fc];
+                            auto smp = [&](int i) -> float {
+                                const long long pos = base + i;
+                                return (pos >= 0 && pos < len) ? __ldg(fb + (long long)i * ich) : 0.0f;
+                            };
+                            x[fc][0] = smp(i0);
+                            x[fc][1] = smp(i1);
+                            x[fc][2] = smp(i2);
+                            x[fc][3] = smp(i3);
+                        }
+                    }
                 }
-                else
+#pragma unroll
+                for (int fc = 0; fc < kFastFcs; ++fc)
+                    if ((uint32_t)fc < fcs_here)
+                    {
+                        float u0, u1;
+                        if (n < 256)
+                        {
+                            u0 = -x[fc][0] * wa - x[fc][1] * wo; // windows: w[i0] = wa, w[i1] = wo, w[i2] = wo, w[i3] = wa
+                            u1 = x[fc][2] * wo - x[fc][3] * wa;
+                        }
+                        else
+                        {
+                            u0 = x[fc][0] * wo - x[fc][1] * wa;  // windows: w[i0] = wo, w[i1] = wa, w[i2] = wa, w[i3] = wo
+                            u1 = -x[fc][2] * wa - x[fc][3] * wo;
+                        }
+                        sm.u[fc][n] = make_float2(u0, u1);
+                    }
+            }
+            if (fcs_here & 1u) // the transform works on pairs: an odd group gets a silent partner
+                for (uint32_t n = tid; n < kHop / 2; n += kFastThreads)
+                    sm.u[fcs_here][n] = make_float2(0.f, 0.f);
+            __syncthreads();
+
+            for (uint32_t pr = warp; pr * 2 < fcs_here; pr += kFastWarps)
+            {
+                const uint32_t fa = pr * 2;
+                dct4_pair(sm.u[fa], tw, lane);
+                const uint32_t n_here = (pr * 2 + 1 < fcs_here) ? 2u : 1u;
+                for (uint32_t h = 0; h < n_here; ++h)
                 {
-                    auto smp = [&](int i) -> float {
-                        const long long pos = base + i;
-                        return (pos >= 0 && pos < len) ? __ldg(fb + (long long)i * ich) : 0.0f;
-                    };
-                    x0 = smp(i0);
-                    x1 = smp(i1);
-                    x2 = smp(i2);
-                    x3 = smp(i3);
+                    const float *coef = reinterpret_cast<const float *>(sm.u[fa]) + h * kCoefStride;
+                    const uint32_t fc = fc0 + fa + h;
+                    const uint32_t lf = fc / ch;
+                    const uint64_t row = fd.first_row + (gg.frame0 + lf) * ch + (fc - lf * ch);
+                    // lane l holds bins 128 j + 4 l + {0..3}, j = 0..7
+                    float cf[8][4];
+                    float m = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                    {
+                        const float4 v = *reinterpret_cast<const float4 *>(coef + j * 128 + lane * 4);
+                        cf[j][0] = v.x;
+                        cf[j][1] = v.y;
+                        cf[j][2] = v.z;
+                        cf[j][3] = v.w;
+                        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                    }
+                    // scale = max|c| .max(1e-10)                                  src/codec.rs:488-489
+                    const float gmax = fmaxf(warp_max_f(m), 1e-10f);
+                    const float scale = gmax;
+                    // band energies -> per-band base threshold (already times scale, :288)   :205-224
+                    for (int b0 = 0; b0 < n_bands; b0 += 32)
+                    {
+                        const int b = b0 + lane;
+                        int lo = 0, hi = 0;
+                        if (b < n_bands)
+                        {
+                            lo = sm.band_lo[b];
+                            hi = sm.band_hi[b];
+                        }
+                        const bool wide = (hi - lo) > 32;
+                        float acc = 0.0f;
+                        if (!wide)
+                            for (int k = lo; k < hi; ++k)
+                                acc = fmaf(coef[k], coef[k], acc);
+                        unsigned wide_mask = __ballot_sync(0xffffffffu, wide);
+                        while (wide_mask)
+                        {
+                            const int src_lane = __ffs(wide_mask) - 1;
+                            wide_mask &= wide_mask - 1;
+                            const int wlo = __shfl_sync(0xffffffffu, lo, src_lane), whi = __shfl_sync(0xffffffffu, hi, src_lane);
+                            float part = 0.0f;
+                            for (int k = wlo + lane; k < whi; k += 32)
+                                part = fmaf(coef[k], coef[k], part);
+                            part = warp_sum_f(part);
+                            if (lane == src_lane)
+                                acc = part;
+                        }
+                        if (b < n_bands)
+                            sm.band_base[warp][b] = sqrtf(acc * sm.band_rcnt[b]) * sm.band_fac[b] * scale;
+                    }
+                    __syncwarp();
+                    // thresholds + quantiser + ordered compaction               src/codec.rs:226-235, 277-307
+                    const float nf = noise_floor_factor * scale;
+                    const float peak_gate = 0.3f * gmax;
+                    const float peak_cap = 0.05f * gmax * scale;
+                    const float qmul = 32768.0f / scale;
+                    glc_pair *dst = p.slots + row * kHop;
+                    uint32_t total = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                    {
+                        const float4 iw4 = *reinterpret_cast<const float4 *>(sm.inv_w + j * 128 + lane * 4);
+                        const uchar4 bo4 = *reinterpret_cast<const uchar4 *>(sm.band_of + j * 128 + lane * 4);
+                        const float iw[4] = {iw4.x, iw4.y, iw4.z, iw4.w};
+                        const unsigned bo[4] = {bo4.x, bo4.y, bo4.z, bo4.w};
+                        int qv[4];
+                        uint32_t cnt = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                        {
+                            const float v = cf[j][e];
+                            const float a = fabsf(v);
+                            float th = sm.band_base[warp][bo[e]] * iw[e];
+                            if (a > peak_gate)
+                                th = fminf(th, peak_cap);
+                            int q = 0;
+                            if (a > fmaxf(nf, th))
+                            {
+                                // round half away from zero (f32::round) as trunc(x + copysign(0.5, x))
+                                const float x = v * qmul;
+                                q = __float2int_rz(fminf(fmaxf(x + copysignf(0.5f, x), -32768.0f), 32767.0f));
+                            }
+                            qv[e] = q;
+                            cnt += q != 0;
+                        }
+                        uint32_t incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1)
+                        {
+                            const uint32_t nn = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o)
+                                incl += nn;
+                        }
+                        uint32_t pos = total + (incl - cnt);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (qv[e] != 0)
+                            {
+                                glc_pair pr2;
+                                pr2.idx = (uint16_t)(j * 128 + lane * 4 + e);
+                                pr2.q = (int16_t)qv[e];
+                                dst[pos++] = pr2;
+                            }
+                        total += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                    if (lane == 0)
+                    {
+                        p.nnz[row] = total;
+                        p.scales[row] = scale;
+                        atomicAdd(&sm.frame_nnz[lf], total); // lf < frames per group <= kFastFcs
+                    }
+                    __syncwarp();
                 }
-                float u0, u1;
-                if (n < 256)
-                {
-                    u0 = -x0 * wa - x1 * wo; // windows: w[i0] = wa, w[i1] = wo, w[i2] = wo, w[i3] = wa
-                    u1 = x2 * wo - x3 * wa;
-                }
-                else
-                {
-                    u0 = x0 * wo - x1 * wa;  // windows: w[i0] = wo, w[i1] = wa, w[i2] = wa, w[i3] = wo
-                    u1 = -x2 * wa - x3 * wo;
-                }
-                sm.u[fc][n] = make_float2(u0, u1);
             }
         }
         __syncthreads();
-
-        for (uint32_t pr = warp; pr * 2 < fcs_here; pr += kFastWarps)
+        // raw-PCM / sparse decision per frame                                 src/codec.rs:505-540
+        if (tid < gg.n_frames)
         {
-            const uint32_t fa = pr * 2, fb = min(pr * 2 + 1, fcs_here - 1);
-            dct4_pair(sm.u[fa], sm.u[fb], tw, sm.xch[warp], lane);
-            const uint32_t n_here = (pr * 2 + 1 < fcs_here) ? 2u : 1u;
-            for (uint32_t h = 0; h < n_here; ++h)
-            {
-                const float *coef = reinterpret_cast<const float *>(sm.xch[warp]) + h * kCoefStride;
-                const uint32_t fc = fc0 + fa + h;
-                const uint32_t lf = fc / ch;
-                const uint64_t row = fd.first_row + (gg.frame0 + lf) * ch + (fc - lf * ch);
-                // scale = max|c| .max(1e-10)                                  src/codec.rs:488-489
-                float m = 0.0f;
-#pragma unroll 8
-                for (int t = 0; t < kHop / 32; ++t)
-                    m = fmaxf(m, fabsf(coef[lane + 32 * t]));
-                const float gmax = fmaxf(warp_max_f(m), 1e-10f);
-                const float scale = gmax;
-                // band energies -> per-band base threshold                  src/codec.rs:205-224
-                const int n_bands = pm.n_edges - 1;
-                for (int b0 = 0; b0 < n_bands; b0 += 32)
+            const uint64_t frame = fd.first_frame + gg.frame0 + tid;
+            const uint64_t row_f = fd.first_row + (gg.frame0 + tid) * ch;
+            const uint64_t compressed = (uint64_t)ch * 8 + (uint64_t)sm.frame_nnz[tid] * 4 + 8 + (uint64_t)ch * 4 + 64;
+            const float rhs = (float)((uint64_t)kFrame * ch * 2) * 0.85f;
+            const bool raw = (float)compressed >= rhs;
+            p.is_raw[frame] = raw ? 1 : 0;
+            p.raw_len[frame] = raw ? (uint32_t)(kFrame * ch) : 0u;
+            if (raw)
+                for (uint32_t c = 0; c < ch; ++c)
                 {
-                    const int b = b0 + lane;
-                    int lo = 0, hi = 0;
-                    if (b < n_bands)
-                    {
-                        lo = pm.band_edges[b];
-                        hi = pm.band_edges[b + 1];
-                    }
-                    const bool wide = (hi - lo) > 32;
-                    float acc = 0.0f;
-                    if (!wide)
-                        for (int k = lo; k < hi; ++k)
-                            acc = fmaf(coef[k], coef[k], acc);
-                    unsigned wide_mask = __ballot_sync(0xffffffffu, wide);
-                    while (wide_mask)
-                    {
-                        const int src_lane = __ffs(wide_mask) - 1;
-                        wide_mask &= wide_mask - 1;
-                        const int wlo = __shfl_sync(0xffffffffu, lo, src_lane), whi = __shfl_sync(0xffffffffu, hi, src_lane);
-                        float part = 0.0f;
-                        for (int k = wlo + lane; k < whi; k += 32)
-                            part = fmaf(coef[k], coef[k], part);
-                        part = warp_sum_f(part);
-                        if (lane == src_lane)
-                            acc = part;
-                    }
-                    if (b < n_bands)
-                    {
-                        const float energy = sqrtf(acc / pm.band_cnt[b]);
-                        // thresholds are later multiplied by scale (src/codec.rs:288): fold it in here
-                        sm.band_base[warp][b] = energy * 0.01f * pm.cf * pm.band_pf[b] * scale;
-                    }
+                    p.nnz[row_f + c] = 0;
+                    p.scales[row_f + c] = 0.0f;
                 }
-                __syncwarp();
-                // thresholds + quantiser + ordered compaction               src/codec.rs:226-235, 277-307
-                const float nf = pm.noise_floor_factor * scale;
-                const float peak_gate = 0.3f * gmax;
-                const float peak_cap = 0.05f * gmax * scale;
-                const float qmul = 32768.0f / scale;
-                glc_pair *dst = p.slots + row * kHop;
-                uint32_t count = 0;
-#pragma unroll 4
-                for (int t = 0; t < kHop / 32; ++t)
-                {
-                    const int k = lane + 32 * t;
-                    const float v = coef[k];
-                    const float a = fabsf(v);
-                    float th = sm.band_base[warp][sm.band_of[k]] * sm.inv_w[k];
-                    if (a > peak_gate)
-                        th = fminf(th, peak_cap);
-                    int q = 0;
-                    if (a > fmaxf(nf, th))
-                    {
-                        // round half away from zero (f32::round) as trunc(x + copysign(0.5, x))
-                        const float x = v * qmul;
-                        q = __float2int_rz(fminf(fmaxf(x + copysignf(0.5f, x), -32768.0f), 32767.0f));
-                    }
-                    const unsigned keep = __ballot_sync(0xffffffffu, q != 0);
-                    if (q != 0)
-                    {
-                        glc_pair pr2;
-                        pr2.idx = (uint16_t)k;
-                        pr2.q = (int16_t)q;
-                        dst[count + __popc(keep & ((1u << lane) - 1u))] = pr2;
-                    }
-                    count += __popc(keep);
-                }
-                if (lane == 0)
-                {
-                    p.nnz[row] = count;
-                    p.scales[row] = scale;
-                    atomicAdd(&sm.frame_nnz[lf], count); // lf < frames per group <= kFastFcs
-                }
-                __syncwarp();
-            }
         }
-    }
-    __syncthreads();
-    // raw-PCM / sparse decision per frame                                 src/codec.rs:505-540
-    if (tid < gg.n_frames)
-    {
-        const uint64_t frame = fd.first_frame + gg.frame0 + tid;
-        const uint64_t row_f = fd.first_row + (gg.frame0 + tid) * ch;
-        const uint64_t compressed = (uint64_t)ch * 8 + (uint64_t)sm.frame_nnz[tid] * 4 + 8 + (uint64_t)ch * 4 + 64;
-        const float rhs = (float)((uint64_t)kFrame * ch * 2) * 0.85f;
-        const bool raw = (float)compressed >= rhs;
-        p.is_raw[frame] = raw ? 1 : 0;
-        p.raw_len[frame] = raw ? (uint32_t)(kFrame * ch) : 0u;
-        if (raw)
-            for (uint32_t c = 0; c < ch; ++c)
-            {
-                p.nnz[row_f + c] = 0;
-                p.scales[row_f + c] = 0.0f;
-            }
     }
 }
 
 // ------------------------------------------------------------------ decode
 
 // One CTA per 8 rows: dequantise into the (c[2n], c[N-1-2n]) layout, DCT-IV, unfold, synthesis window.
-__global__ void __launch_bounds__(kFastThreads, 3) fast_decode_kernel(const FastDecodeLaunch p)
+__global__ void __launch_bounds__(kFastThreads, 4) fast_decode_kernel(const FastDecodeLaunch p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
@@ -420,7 +499,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fast_decode_kernel(const Fast
         }
         s_live[tid] = live;
     }
-    for (uint32_t e = tid; e < rows_here * (kHop / 2); e += kFastThreads)
+    for (uint32_t e = tid; e < ((rows_here + 1u) & ~1u) * (kHop / 2); e += kFastThreads)
         sm.u[e >> 9][e & 511] = make_float2(0.f, 0.f);
     __syncthreads();
     // dequantise (src/codec.rs:651-665).  "Later duplicates overwrite": lane-ordered replay when the
@@ -464,13 +543,13 @@ __global__ void __launch_bounds__(kFastThreads, 3) fast_decode_kernel(const Fast
         const uint32_t fa = prn * 2, fb = min(prn * 2 + 1, rows_here - 1);
         if (!s_live[fa] && !s_live[fb])
             continue;
-        dct4_pair(sm.u[fa], sm.u[fb], tw, sm.xch[warp], lane);
+        dct4_pair(sm.u[fa], tw, lane);
         const uint32_t n_here = (prn * 2 + 1 < rows_here) ? 2u : 1u;
         for (uint32_t h = 0; h < n_here; ++h)
         {
             if (!s_live[fa + h])
                 continue;
-            const float *v = reinterpret_cast<const float *>(sm.xch[warp]) + h * kCoefStride;
+            const float *v = reinterpret_cast<const float *>(sm.u[fa]) + h * kCoefStride;
             float *out = p.blocks + (row0 + fa + h) * kFrame;
             // unfold (transpose of the fold) + synthesis window           src/codec.rs:672-675
 #pragma unroll 4
@@ -532,7 +611,12 @@ cudaError_t launch_fast_encode(const FastEncodeLaunch &p, cudaStream_t s)
             return e;
         configured = true;
     }
-    fast_encode_kernel<<<(unsigned)(p.group_end - p.group_begin), kFastThreads, sizeof(FastSmem), s>>>(p);
+    // persistent CTAs: 4 resident per SM, grid-stride over the frame groups
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t grid = std::min<uint64_t>(p.group_end - p.group_begin, (uint64_t)sms * 4);
+    fast_encode_kernel<<<(unsigned)grid, kFastThreads, sizeof(FastSmem), s>>>(p);
     return cudaGetLastError();
 }
 
