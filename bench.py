@@ -335,6 +335,38 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     e2e_ms = max_over_ranks(e2e_s / args.steps * 1e3)
     launches += sum(st2["launches"].values())
 
+    # ---- timed region 3: the same round trip with 16-bit integer ingest (glc_encode_i16: the WAV
+    #      loader's division runs on the device, half the H2D bytes) ----
+    x16 = ctx.pinned_array(xp.size, np.int16)
+    np.multiply(xp, 32767.0, out=xp)  # in place: the f32 copy is not needed any more
+    x16[:] = xp.astype(np.int16)
+
+    def host_step_i16():
+        out = C.POINTER(_ffi.Encoded)()
+        chk(L.glc_encode_i16(enc_h, x16.ctypes.data, x16.size, CH, C.byref(out)))
+        p, n = C.POINTER(C.c_float)(), C.c_uint64()
+        chk(L.glc_decode(dec_h, out, C.byref(p), C.byref(n)))
+        got = n.value
+        L.glc_free(ctx.handle, p)
+        L.glc_encoded_free(ctx.handle, out)
+        return got
+
+    for _ in range(2):
+        host_step_i16()
+    ctx.stats_reset()
+    barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        assert host_step_i16() == x16.size
+    ctx.sync()
+    e2e16_s = time.perf_counter() - t0
+    barrier()
+    t_region1 = time.perf_counter()
+    st3 = ctx.stats()
+    e2e16_ms = max_over_ranks(e2e16_s / args.steps * 1e3)
+    launches += sum(st3["launches"].values())
+
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
 
     # ---- roofline of the dominant kernel (rank 0's own launches) ----
@@ -397,6 +429,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "e2e": {"value": total_secs / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps,
                 "ms_per_step": e2e_ms, "api": "glc_encode + glc_decode (C ABI, pinned host buffers)"},
+        "e2e_int16_ingest": {"value": total_secs / (e2e16_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e16_ms,
+                             "h2d_bytes_per_step": st3["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st3["d2h_bytes"] // args.steps,
+                             "api": "glc_encode_i16 + glc_decode (16-bit PCM in, f32 PCM out)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks,

@@ -70,9 +70,10 @@ EXPORTS = [
     "glc_abi_version", "glc_last_error", "glc_device_count", "glc_ctx_create", "glc_ctx_destroy",
     "glc_ctx_set_tuning", "glc_host_alloc", "glc_host_free", "glc_free",
     "glc_encoder_new", "glc_encoder_free", "glc_encode", "glc_encode_batch", "glc_encoded_free",
+    "glc_encode_i16", "glc_encode_batch_i16", "glc_encode_i32",
     "glc_decoder_new", "glc_decoder_free", "glc_decode", "glc_decode_untrimmed", "glc_decode_batch",
     "glc_decode_stream_open", "glc_decode_stream_next", "glc_decode_stream_close",
-    "glc_flac_encode", "glc_flac_encode_batch",
+    "glc_flac_encode", "glc_flac_encode_batch", "glc_decode_to_flac", "glc_decode_to_flac_batch",
     "glc_encoded_to_bincode", "glc_encoded_from_bincode",
     "glc_stats_reset", "glc_stats_get", "glc_stats_enable_kernel_timing",
     "glc_dev_upload", "glc_dev_pcm_free", "glc_dev_encode", "glc_dev_decode",
@@ -110,6 +111,9 @@ def load() -> C.CDLL:
         "glc_encode": (C.c_int, [vp, vp, u64, u16, pp(pp(Encoded))]),
         "glc_encode_batch": (C.c_int, [vp, u32, pp(vp), pp(u64), pp(u16), pp(pp(Encoded))]),
         "glc_encoded_free": (None, [vp, pp(Encoded)]),
+        "glc_encode_i16": (C.c_int, [vp, vp, u64, u16, pp(pp(Encoded))]),
+        "glc_encode_batch_i16": (C.c_int, [vp, u32, pp(vp), pp(u64), pp(u16), pp(pp(Encoded))]),
+        "glc_encode_i32": (C.c_int, [vp, vp, u64, u16, u32, pp(pp(Encoded))]),
         "glc_decoder_new": (C.c_int, [vp, u32, u32, pp(vp)]),
         "glc_decoder_free": (None, [vp]),
         "glc_decode": (C.c_int, [vp, pp(Encoded), pp(fp), pp(u64)]),
@@ -121,6 +125,8 @@ def load() -> C.CDLL:
         "glc_flac_encode": (C.c_int, [vp, vp, u64, u32, u16, u8, pp(pp(u8)), pp(u64)]),
         "glc_flac_encode_batch": (C.c_int, [vp, u32, pp(vp), pp(u64), pp(u32), pp(u16), u8,
                                             pp(pp(u8)), pp(u64)]),
+        "glc_decode_to_flac": (C.c_int, [vp, pp(Encoded), u8, pp(pp(u8)), pp(u64)]),
+        "glc_decode_to_flac_batch": (C.c_int, [vp, u32, pp(pp(Encoded)), u8, pp(pp(u8)), pp(u64)]),
         "glc_encoded_to_bincode": (C.c_int, [vp, pp(Encoded), pp(pp(u8)), pp(u64)]),
         "glc_encoded_from_bincode": (C.c_int, [vp, vp, u64, pp(pp(Encoded))]),
         "glc_stats_reset": (None, [vp]),

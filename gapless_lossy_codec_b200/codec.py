@@ -258,6 +258,24 @@ class Encoder:
         finally:
             self._lib.glc_encoded_free(self.ctx.handle, out)
 
+    def encode_pcm_int(self, samples, channels: int, bits_per_sample: int = 16) -> EncodedAudio:
+        """Encoder::encode over integer PCM as audio::load_wav / load_flac would convert it
+        (`s as f32 / 2^(bits-1)`, src/audio.rs:51-59): int16 arrays take the 16-bit path (half the
+        PCIe bytes), anything else goes through an int32 container.  Bit-identical to
+        `encode(samples / 2**(bits-1))`."""
+        a = np.ascontiguousarray(samples).reshape(-1)
+        out = C.POINTER(_ffi.Encoded)()
+        if a.dtype == np.int16 and bits_per_sample == 16:
+            check(self._lib.glc_encode_i16(self.handle, a.ctypes.data, a.size, int(channels), C.byref(out)))
+        else:
+            a = np.ascontiguousarray(a, np.int32)
+            check(self._lib.glc_encode_i32(self.handle, a.ctypes.data, a.size, int(channels), int(bits_per_sample),
+                                           C.byref(out)))
+        try:
+            return EncodedAudio._from_struct(out.contents)
+        finally:
+            self._lib.glc_encoded_free(self.ctx.handle, out)
+
     def encode_batch(self, files: Sequence, channels: Sequence[int]) -> List[EncodedAudio]:
         """Many `encode` calls fused into one device pass (sharding unit: file)."""
         n = len(files)
@@ -317,6 +335,18 @@ class Decoder:
         if progress:
             progress(Progress("Complete", f"Decoded {encoded.n_frames} frames"))
         return self._take(p, n.value)
+
+    def decode_to_flac(self, encoded: EncodedAudio, compression_level: int = 5) -> bytes:
+        """`glc -d file.glc --flac-level N` (src/main.rs:55-113): decode, then FLAC-encode the decoded
+        samples, with the PCM kept on the device in between."""
+        st = encoded._as_struct()
+        b = C.POINTER(C.c_uint8)()
+        n = C.c_uint64()
+        check(self._lib.glc_decode_to_flac(self.handle, C.byref(st), int(compression_level), C.byref(b), C.byref(n)))
+        try:
+            return C.string_at(b, n.value)
+        finally:
+            self._lib.glc_free(self.ctx.handle, b)
 
     def decode_untrimmed(self, encoded: EncodedAudio) -> np.ndarray:
         st = encoded._as_struct()

@@ -998,10 +998,22 @@ static glc_status build_file_table(uint32_t n_files, const uint64_t *n_samples, 
     return GLC_OK;
 }
 
+// Host PCM of a batched encode: f32 as the reference's Encoder::encode takes it, or the integer
+// samples a WAV/FLAC loader would have divided by 2^(bits-1) (src/audio.rs:39-83) -- then the
+// integers cross PCIe (half the bytes for 16-bit sources) and the division runs on the device.
+struct HostPcm
+{
+    const void *const *ptr; // [n_files]
+    int elem_bytes;         // 4 = f32 or i32 container, 2 = i16 container
+    bool is_int;
+    float inv_max;          // 1 / 2^(bits-1)
+    void *d_stage;          // device staging arena for integer input (same offsets as the f32 arena)
+};
+
 // Core: everything after "PCM is (being put) in the arena".  host_pcm == nullptr means the arena
 // is already fully resident; otherwise the H2D copies are issued here, wave by wave.
 static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &files, uint64_t tot_rows,
-                              uint64_t tot_frames, float *d_arena, const float *const *host_pcm,
+                              uint64_t tot_frames, float *d_arena, const HostPcm *host_pcm,
                               const uint64_t *n_samples, EncodeHostOut *ho, glc_dev_encoded **out)
 {
     glc_ctx *c = enc->ctx;
@@ -1139,6 +1151,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         c->stats.d2h_bytes += (p1 - p0) * sizeof(glc_pair) + (q1 - q0) * sizeof(int16_t);
         return GLC_OK;
     };
+    std::vector<std::pair<uint64_t, uint64_t>> pending_convert; // (arena offset, count) of integer samples to convert
     uint32_t copy_file = 0;      // next file with bytes left to copy
     uint64_t copy_done = 0;      // interleaved samples of copy_file already enqueued
     for (size_t wi = 0; wi < waves.size(); ++wi)
@@ -1160,9 +1173,14 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
                 need = smp * fd.channels;
                 if (need > copy_done)
                 {
-                    CUDA_TRY(cudaMemcpyAsync(d_arena + fd.pcm_off + copy_done, host_pcm[copy_file] + copy_done,
-                                             (need - copy_done) * sizeof(float), cudaMemcpyHostToDevice, c->copy));
-                    c->stats.h2d_bytes += (need - copy_done) * sizeof(float);
+                    const size_t eb = (size_t)host_pcm->elem_bytes;
+                    char *dst_h2d = host_pcm->is_int ? (char *)host_pcm->d_stage : (char *)d_arena;
+                    CUDA_TRY(cudaMemcpyAsync(dst_h2d + (fd.pcm_off + copy_done) * eb,
+                                             (const char *)host_pcm->ptr[copy_file] + copy_done * eb,
+                                             (need - copy_done) * eb, cudaMemcpyHostToDevice, c->copy));
+                    c->stats.h2d_bytes += (need - copy_done) * eb;
+                    if (host_pcm->is_int)
+                        pending_convert.push_back({fd.pcm_off + copy_done, need - copy_done});
                     copy_done = need;
                     issued = true;
                 }
@@ -1179,6 +1197,14 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
                 CUDA_TRY(cudaEventRecord(ev_copy, c->copy));
                 CUDA_TRY(cudaStreamWaitEvent(cs, ev_copy, 0));
             }
+            // integer input: sample as f32 / 2^(bits-1) (src/audio.rs:51-59) for what just arrived
+            for (const auto &seg : pending_convert)
+            {
+                LaunchScope ls(c, GLC_K_MISC, cs);
+                CUDA_TRY(launch_pcm_convert(host_pcm->d_stage, host_pcm->elem_bytes, seg.first, seg.second,
+                                            host_pcm->inv_max, d_arena, cs));
+            }
+            pending_convert.clear();
         }
         if (fast)
         {
@@ -1448,11 +1474,14 @@ static glc_status download_encoded(glc_dev_encoded *de, EncodeHostOut *ho, glc_e
     return GLC_OK;
 }
 
-extern "C" glc_status glc_encode_batch(glc_encoder *enc, uint32_t n_files, const float *const *pcm,
-                                       const uint64_t *n_samples, const uint16_t *channels, glc_encoded **out)
+static glc_status encode_batch_impl(glc_encoder *enc, uint32_t n_files, const void *const *pcm, int elem_bytes,
+                                    bool is_int, uint32_t bits, const uint64_t *n_samples, const uint16_t *channels,
+                                    glc_encoded **out)
 {
     if (!enc || !pcm || !n_samples || !channels || !out || n_files == 0)
         return fail(GLC_ERR_INVALID_ARG, "null/empty argument");
+    if (is_int && (bits < 1 || bits > (uint32_t)elem_bytes * 8))
+        return fail(GLC_ERR_INVALID_ARG, "bits_per_sample %u does not fit a %d-byte container", bits, elem_bytes);
     glc_ctx *c = enc->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     std::vector<FileDesc> files;
@@ -1463,9 +1492,18 @@ extern "C" glc_status glc_encode_batch(glc_encoder *enc, uint32_t n_files, const
             return fail(GLC_ERR_INVALID_ARG, "file %u: pcm is null", i);
     float *d_arena = nullptr;
     CUDA_TRY(dmalloc(&d_arena, tot_pcm, c->copy));
+    HostPcm hp{};
+    hp.ptr = pcm;
+    hp.elem_bytes = elem_bytes;
+    hp.is_int = is_int;
+    hp.inv_max = is_int ? 1.0f / (float)(1ull << (bits - 1)) : 1.0f;
+    char *d_stage = nullptr;
+    if (is_int)
+        CUDA_TRY(dmalloc(&d_stage, tot_pcm * (size_t)elem_bytes, c->copy));
+    hp.d_stage = d_stage;
     glc_dev_encoded *de = nullptr;
     EncodeHostOut ho;
-    glc_status st = encode_core(enc, files, rows, frames, d_arena, pcm, n_samples, &ho, &de);
+    glc_status st = encode_core(enc, files, rows, frames, d_arena, &hp, n_samples, &ho, &de);
     if (st == GLC_OK)
         st = download_encoded(de, &ho, out);
     cudaStreamSynchronize(c->d2h);
@@ -1477,7 +1515,38 @@ extern "C" glc_status glc_encode_batch(glc_encoder *enc, uint32_t n_files, const
         glc_dev_encoded_free(de);
     cudaStreamSynchronize(c->compute);
     dfree(d_arena, c->copy);
+    dfree(d_stage, c->copy);
     return st;
+}
+
+extern "C" glc_status glc_encode_batch(glc_encoder *enc, uint32_t n_files, const float *const *pcm,
+                                       const uint64_t *n_samples, const uint16_t *channels, glc_encoded **out)
+{
+    return encode_batch_impl(enc, n_files, (const void *const *)pcm, 4, false, 0, n_samples, channels, out);
+}
+
+extern "C" glc_status glc_encode_batch_i16(glc_encoder *enc, uint32_t n_files, const int16_t *const *pcm,
+                                           const uint64_t *n_samples, const uint16_t *channels, glc_encoded **out)
+{
+    return encode_batch_impl(enc, n_files, (const void *const *)pcm, 2, true, 16, n_samples, channels, out);
+}
+
+extern "C" glc_status glc_encode_i16(glc_encoder *enc, const int16_t *pcm, uint64_t n_samples, uint16_t channels,
+                                     glc_encoded **out)
+{
+    if (!out)
+        return fail(GLC_ERR_INVALID_ARG, "out is null");
+    const void *files[1] = {pcm};
+    return encode_batch_impl(enc, 1, files, 2, true, 16, &n_samples, &channels, out);
+}
+
+extern "C" glc_status glc_encode_i32(glc_encoder *enc, const int32_t *pcm, uint64_t n_samples, uint16_t channels,
+                                     uint32_t bits_per_sample, glc_encoded **out)
+{
+    if (!out)
+        return fail(GLC_ERR_INVALID_ARG, "out is null");
+    const void *files[1] = {pcm};
+    return encode_batch_impl(enc, 1, files, 4, true, bits_per_sample, &n_samples, &channels, out);
 }
 
 extern "C" glc_status glc_encode(glc_encoder *enc, const float *pcm, uint64_t n_samples, uint16_t channels,
@@ -1771,7 +1840,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             o.out = d_out;
             CUDA_TRY(launch_ola(o, cs));
         }
-        if (io)
+        if (io && io->h_out)
         {
             // D2H of the finished range, clipped to every file's gapless window
             cudaEvent_t ev = get_event(c);
@@ -1829,10 +1898,17 @@ static void trim_window(uint64_t untrimmed, uint32_t delay, uint64_t original_le
     *len = n;
 }
 
-static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc, bool trim,
-                                    float **pcm, uint64_t *n_out)
+// Where a decode leaves its PCM when the caller wants it to stay in HBM (fused decode -> FLAC).
+struct DeviceSink
 {
-    if (!dec || !enc || !pcm || !n_out || n_files == 0)
+    float *d_out = nullptr;          // untrimmed streams of all files, caller frees with dfree(.., compute)
+    std::vector<uint64_t> off, len;  // per file: first kept value (absolute in d_out) and kept count
+};
+
+static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc, bool trim,
+                                    float **pcm, uint64_t *n_out, DeviceSink *sink = nullptr)
+{
+    if (!dec || !enc || (!sink && (!pcm || !n_out)) || n_files == 0)
         return fail(GLC_ERR_INVALID_ARG, "null/empty argument");
     glc_ctx *c = dec->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1972,6 +2048,7 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
         if (trim)
             trim_window(untrimmed, e->encoder_delay, e->original_length, &win_off[i], &win_len[i]);
     }
+    if (!sink)
     {
         std::vector<uint64_t> bytes(n_files);
         for (uint32_t i = 0; i < n_files; ++i)
@@ -1986,7 +2063,7 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
     io.enc = enc;
     io.h_pair_off = h_pair_off;
     io.h_raw_off = h_raw_off;
-    io.h_out = h_out.data();
+    io.h_out = sink ? nullptr : h_out.data();
     io.win_off = win_off.data();
     io.win_len = win_len.data();
     io.d_pairs = d_pairs;
@@ -2001,10 +2078,22 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
         se = cudaStreamSynchronize(c->copy);
     if (st == GLC_OK && se != cudaSuccess)
         st = fail(GLC_ERR_CUDA, "decode failed: %s", cudaGetErrorString(se));
+    if (sink && st == GLC_OK)
+    {
+        sink->d_out = d_out;
+        sink->off.resize(n_files);
+        sink->len.resize(n_files);
+        for (uint32_t i = 0; i < n_files; ++i)
+        {
+            sink->off[i] = files[i].out_off + win_off[i];
+            sink->len[i] = win_len[i];
+        }
+        d_out = nullptr;
+    }
     if (d_out)
         dfree(d_out, cs);
     cleanup(st == GLC_OK);
-    if (st == GLC_OK)
+    if (st == GLC_OK && !sink)
         for (uint32_t i = 0; i < n_files; ++i)
         {
             pcm[i] = h_out[i];
@@ -2012,6 +2101,36 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
         }
     return st;
 #undef DEC_TRY
+}
+
+// The CLI's `glc -d file.glc --flac-level N` path (src/main.rs:55-113): Decoder::decode, then
+// flac::export_to_flac_with_level on the decoded samples -- here the PCM never leaves HBM.
+extern "C" glc_status glc_decode_to_flac_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
+                                               uint8_t level, uint8_t **bytes, uint64_t *len)
+{
+    if (!dec || !enc || !bytes || !len || n_files == 0)
+        return fail(GLC_ERR_INVALID_ARG, "null/empty argument");
+    glc_ctx *c = dec->ctx;
+    DeviceSink sink;
+    GLC_TRY(decode_batch_impl(dec, n_files, enc, true, nullptr, nullptr, &sink));
+    std::vector<uint32_t> rates(n_files);
+    std::vector<uint16_t> chs(n_files);
+    for (uint32_t i = 0; i < n_files; ++i)
+    {
+        rates[i] = enc[i]->sample_rate; // the stream header wins (src/codec.rs:598; main.rs:62-66)
+        chs[i] = enc[i]->channels;
+    }
+    glc_status st = flac_encode_impl(c, n_files, nullptr, sink.d_out, sink.off.data(), sink.len.data(), rates.data(),
+                                     chs.data(), level, bytes, len);
+    cudaStreamSynchronize(c->compute);
+    dfree(sink.d_out, c->compute);
+    return st;
+}
+
+extern "C" glc_status glc_decode_to_flac(glc_decoder *dec, const glc_encoded *enc, uint8_t level, uint8_t **bytes,
+                                         uint64_t *len)
+{
+    return glc_decode_to_flac_batch(dec, 1, &enc, level, bytes, len);
 }
 
 extern "C" glc_status glc_decode_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,

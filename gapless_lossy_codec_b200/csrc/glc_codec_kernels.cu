@@ -9,6 +9,8 @@
 //
 // All of these are HBM-bound streaming kernels: coalesced 16-byte loads, one pass over their input.
 // Compiled with -fmad=false: every f32 operation below is a single IEEE operation, as in Rust.
+#include <algorithm>
+
 #include "glc_internal.cuh"
 
 namespace glc
@@ -580,6 +582,19 @@ __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
     }
 }
 
+// Integer PCM -> f32 exactly as the reference's loaders do it: `s as f32 / 2^(bits-1)`
+// (src/audio.rs:51-59, 76-80): one i32 -> f32 conversion (round to nearest) and an exact scaling.
+__global__ void pcm_convert_kernel(const void *stage, int elem_bytes, uint64_t off, uint64_t n, float inv_max, float *arena)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const int v = elem_bytes == 2 ? (int)reinterpret_cast<const int16_t *>(stage)[off + i]
+                                      : reinterpret_cast<const int32_t *>(stage)[off + i];
+        arena[off + i] = __fmul_rn(__int2float_rn(v), inv_max);
+    }
+}
+
 __global__ void fill_kernel(float *p, uint64_t n, float v)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -693,6 +708,16 @@ cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s)
     if (p.hop_end <= p.hop_begin)
         return cudaSuccess;
     ola_kernel<<<(unsigned)(p.hop_end - p.hop_begin), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pcm_convert(const void *stage, int elem_bytes, uint64_t off, uint64_t n, float inv_max, float *arena,
+                               cudaStream_t s)
+{
+    if (n == 0)
+        return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 16);
+    pcm_convert_kernel<<<grid, 256, 0, s>>>(stage, elem_bytes, off, n, inv_max, arena);
     return cudaGetLastError();
 }
 

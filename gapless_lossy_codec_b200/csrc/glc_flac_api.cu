@@ -183,16 +183,17 @@ struct BitOut
 
 } // namespace
 
-extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, const float *const *pcm,
-                                            const uint64_t *n_samples, const uint32_t *sample_rate,
-                                            const uint16_t *channels, uint8_t level, uint8_t **bytes, uint64_t *len)
+// pcm == nullptr: the samples are already on the device, file i at d_base + d_off[i] (16-byte aligned).
+glc_status glc::flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *const *pcm, const float *d_base,
+                                 const uint64_t *d_off, const uint64_t *n_samples, const uint32_t *sample_rate,
+                                 const uint16_t *channels, uint8_t level, uint8_t **bytes, uint64_t *len)
 {
-    if (!ctx || !pcm || !n_samples || !sample_rate || !channels || !bytes || !len || n_files == 0)
+    if (!ctx || (!pcm && !(d_base && d_off)) || !n_samples || !sample_rate || !channels || !bytes || !len || n_files == 0)
         return set_error(GLC_ERR_INVALID_ARG, "null/empty argument");
     // ---- checks, in the reference's order: length first (:963), then level (:972) ----
     for (uint32_t i = 0; i < n_files; ++i)
     {
-        if (!pcm[i] && n_samples[i])
+        if (pcm && !pcm[i] && n_samples[i])
             return set_error(GLC_ERR_INVALID_ARG, "file %u: pcm is null", i);
         if (channels[i] == 0)
             return set_error(GLC_ERR_INVALID_ARG, "file %u: channels is 0", i);
@@ -220,7 +221,7 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
         const uint64_t total = n_samples[i] / channels[i];
         uint64_t bs = level <= 2 ? 1152 : 4096; // src/flac.rs:983-995
         bs = std::max<uint64_t>(std::min<uint64_t>(bs, total), 16);
-        f.pcm_off = tot_pcm;
+        f.pcm_off = pcm ? tot_pcm : d_off[i];
         f.i16_off = tot_pcm;
         f.n_samples = n_samples[i];
         f.first_block = tot_blocks;
@@ -274,7 +275,8 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
             break;                                                                                \
         }                                                                                         \
     }
-        FL_STEP(dev_alloc(ctx, (void **)&d_pcm, std::max<uint64_t>(tot_pcm, 1) * 4, cs));
+        if (pcm)
+            FL_STEP(dev_alloc(ctx, (void **)&d_pcm, std::max<uint64_t>(tot_pcm, 1) * 4, cs));
         FL_STEP(dev_alloc(ctx, (void **)&d_i16, std::max<uint64_t>(tot_pcm, 1) * 2, cs));
         FL_STEP(dev_alloc(ctx, (void **)&d_files, sizeof(FlacFileDesc) * n_files, cs));
         FL_STEP(dev_alloc(ctx, (void **)&d_k, std::max<uint64_t>(tot_blocks, 1) * max_ch * 64, cs));
@@ -282,7 +284,7 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
         FL_STEP(dev_alloc(ctx, (void **)&d_foff, (tot_blocks + 1) * 8, cs));
         FL_STEP(cudaMemcpyAsync(d_files, files.data(), sizeof(FlacFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
         bool bad = false;
-        for (uint32_t i = 0; i < n_files && !bad; ++i)
+        for (uint32_t i = 0; pcm && i < n_files && !bad; ++i)
             if (cudaMemcpyAsync(d_pcm + files[i].pcm_off, pcm[i], n_samples[i] * 4, cudaMemcpyHostToDevice, cs) !=
                 cudaSuccess)
                 bad = true;
@@ -291,10 +293,11 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
             st = set_error(GLC_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        ctx_count_bytes(ctx, tot_pcm * 4, 0);
+        if (pcm)
+            ctx_count_bytes(ctx, tot_pcm * 4, 0);
 
         FlacLaunch fl{};
-        fl.pcm_arena = d_pcm;
+        fl.pcm_arena = pcm ? d_pcm : d_base;
         fl.files = d_files;
         fl.n_files = n_files;
         fl.n_blocks_total = tot_blocks;
@@ -475,6 +478,15 @@ extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, cons
     dev_free(ctx, d_out, cs);
     dev_free(ctx, d_scratch, cs);
     return st;
+}
+
+extern "C" glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, const float *const *pcm,
+                                            const uint64_t *n_samples, const uint32_t *sample_rate,
+                                            const uint16_t *channels, uint8_t level, uint8_t **bytes, uint64_t *len)
+{
+    if (!pcm)
+        return set_error(GLC_ERR_INVALID_ARG, "null/empty argument");
+    return flac_encode_impl(ctx, n_files, pcm, nullptr, nullptr, n_samples, sample_rate, channels, level, bytes, len);
 }
 
 extern "C" glc_status glc_flac_encode(glc_ctx *ctx, const float *pcm, uint64_t n_samples, uint32_t sample_rate,

@@ -182,7 +182,10 @@ __device__ __forceinline__ void load_block(const FlacLaunch &p, const FlacFileDe
     const uint32_t n = g.bs * g.ch;
     const float *src = p.pcm_arena + fd.pcm_off + g.smp_off;
     int16_t *arena = p.i16_arena + fd.i16_off + g.smp_off;
-    const uint32_t n4 = (g.smp_off & 3ull) == 0 ? n / 4 : 0; // vectorisable quads
+    // vectorisable quads: the block must start on a 4-sample boundary of the arena it is read from
+    const uint64_t start = (FROM_F32 ? fd.pcm_off : fd.i16_off) + g.smp_off;
+    const bool arena_ok = FROM_F32 ? ((fd.i16_off + g.smp_off) & 3ull) == 0 : true; // short4 stores into the i16 arena
+    const uint32_t n4 = ((start & 3ull) == 0 && arena_ok) ? n / 4 : 0;
     constexpr int kBatch = 4;
     for (uint32_t q0 = threadIdx.x; q0 < n4; q0 += blockDim.x * kBatch)
     {

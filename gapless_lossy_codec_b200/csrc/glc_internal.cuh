@@ -234,6 +234,8 @@ struct FastDecodeLaunch
 };
 cudaError_t launch_fast_decode(const FastDecodeLaunch &p, cudaStream_t s);
 
+cudaError_t launch_pcm_convert(const void *stage, int elem_bytes, uint64_t off, uint64_t n, float inv_max, float *arena,
+                               cudaStream_t s);
 cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s);
 cudaError_t launch_fp32_issue_bench(int packed, int iters, float *sink, int blocks, cudaStream_t s);
 
@@ -268,6 +270,10 @@ cudaError_t launch_flac_emit(const FlacLaunch &p, const uint8_t *rice_k, uint32_
                              uint32_t max_frame_bytes, const uint64_t *frame_off, uint8_t *out_arena,
                              uint32_t *scratch, int sm_count, cudaStream_t s);
 uint32_t flac_slot_bytes(uint32_t block_size, uint32_t channels);
+// flac::encode_flac_with_level over host PCM (pcm != nullptr) or device-resident PCM (file i at d_base + d_off[i])
+glc_status flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *const *pcm, const float *d_base,
+                            const uint64_t *d_off, const uint64_t *n_samples, const uint32_t *sample_rate,
+                            const uint16_t *channels, uint8_t level, uint8_t **bytes, uint64_t *len);
 
 // ---- host-side plumbing shared by the API translation units ----
 glc_status set_error(glc_status st, const char *fmt, ...);

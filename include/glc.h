@@ -32,7 +32,7 @@ extern "C" {
 #define GLC_FRAME_SIZE 2048u      /* src/codec.rs:15 */
 #define GLC_HOP_SIZE 1024u        /* src/codec.rs:16 */
 #define GLC_FRAMES_PER_CHUNK 500u /* src/codec.rs:18 */
-#define GLC_ABI_VERSION 3u
+#define GLC_ABI_VERSION 4u
 
 typedef enum glc_status
 {
@@ -130,6 +130,18 @@ glc_status glc_encode(glc_encoder *enc, const float *pcm, uint64_t n_samples, ui
 glc_status glc_encode_batch(glc_encoder *enc, uint32_t n_files, const float *const *pcm,
                             const uint64_t *n_samples, const uint16_t *channels,
                             glc_encoded **out /* [n_files] */);
+/* Integer-PCM ingest ("next" row of SURVEY.md 8f): Encoder::encode over the samples that
+ * audio::load_wav / load_flac would have produced from integer sources, `s as f32 / 2^(bits-1)`
+ * (src/audio.rs:51-59, 76-80).  The integers cross PCIe (half the bytes for 16-bit sources) and the
+ * conversion runs on the device; the result is bit-identical to glc_encode over the converted f32. */
+glc_status glc_encode_i16(glc_encoder *enc, const int16_t *pcm, uint64_t n_samples, uint16_t channels,
+                          glc_encoded **out);
+glc_status glc_encode_batch_i16(glc_encoder *enc, uint32_t n_files, const int16_t *const *pcm,
+                                const uint64_t *n_samples, const uint16_t *channels,
+                                glc_encoded **out /* [n_files] */);
+/* 8..32-bit samples in an int32 container (24-bit WAV/FLAC as hound/claxon deliver them). */
+glc_status glc_encode_i32(glc_encoder *enc, const int32_t *pcm, uint64_t n_samples, uint16_t channels,
+                          uint32_t bits_per_sample, glc_encoded **out);
 void glc_encoded_free(glc_ctx *ctx, glc_encoded *e);
 
 /* Decoder::new(channels, sample_rate)                              src/codec.rs:581-592
@@ -167,6 +179,14 @@ glc_status glc_flac_encode_batch(glc_ctx *ctx, uint32_t n_files, const float *co
                                  const uint64_t *n_samples, const uint32_t *sample_rate,
                                  const uint16_t *channels, uint8_t level, uint8_t **bytes,
                                  uint64_t *len);
+
+/* Fused decode -> FLAC ("next" row of SURVEY.md 8f): what `glc -d file.glc --flac-level N` does
+ * (src/main.rs:55-113: Decoder::decode, then flac::export_to_flac_with_level) with the decoded PCM
+ * kept in HBM between the two steps.  Bytes are identical to glc_flac_encode over glc_decode's output. */
+glc_status glc_decode_to_flac(glc_decoder *dec, const glc_encoded *enc, uint8_t level, uint8_t **bytes,
+                              uint64_t *len);
+glc_status glc_decode_to_flac_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
+                                    uint8_t level, uint8_t **bytes /* [n_files] */, uint64_t *len /* [n_files] */);
 
 /* ---------------------------------------------------------------- container */
 

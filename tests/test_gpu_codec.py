@@ -199,3 +199,39 @@ def test_large_property_roundtrip(gpu_ctx):
     # only), so the bar is the reference's own -10 dB (tests/test_codec.rs:104-106).
     snr = signals.snr_db(x[:-512], pcm[512:])
     assert snr > -10.0, snr
+
+
+def test_integer_pcm_ingest_matches_converted_f32(gpu_ctx):
+    """"next" row 3 of SURVEY 8(f): integer samples cross PCIe, the loaders' division (src/audio.rs:51-59)
+    runs on the device; the stream must equal the encode of the converted f32 bit for bit."""
+    from gapless_lossy_codec_b200 import Encoder
+
+    rng = np.random.default_rng(3)
+    x = signals.music_like(44100, 2, 1.2)
+    x16 = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    enc = Encoder(44100, gpu_ctx)
+    got = enc.encode_pcm_int(x16, 2, 16)
+    assert_encoded_equal(got, oracle.encode(x16.astype(np.float32) / np.float32(32768.0), 2, 44100), "i16 ingest")
+    x24 = rng.integers(-(1 << 23), 1 << 23, 48000 * 3, dtype=np.int64).astype(np.int32)
+    x24[::5] = (np.sin(np.arange(len(x24[::5])) * 0.05) * 4e6).astype(np.int32)
+    got = Encoder(48000, gpu_ctx).encode_pcm_int(x24, 3, 24)
+    assert_encoded_equal(got, oracle.encode(x24.astype(np.float32) / np.float32(8388608.0), 3, 48000), "24-bit ingest")
+    x32 = rng.integers(-(1 << 31), 1 << 31, 30000, dtype=np.int64).astype(np.int32)  # i32 -> f32 rounds to nearest
+    got = Encoder(44100, gpu_ctx).encode_pcm_int(x32, 1, 32)
+    assert_encoded_equal(got, oracle.encode(x32.astype(np.float32) / np.float32(2147483648.0), 1, 44100), "32-bit ingest")
+
+
+def test_decode_to_flac_equals_two_step_path(gpu_ctx):
+    """"next" row 2 of SURVEY 8(f): `glc -d x.glc --flac-level N` = decode, then FLAC-encode the decoded
+    samples (src/main.rs:55-113).  The fused call keeps the PCM in HBM; bytes must equal the oracle chain."""
+    from gapless_lossy_codec_b200 import Decoder
+
+    for x, ch, sr, level in [(signals.music_like(44100, 2, 1.0), 2, 44100, 5),
+                             (signals.sine(440, 48000, 1, 0.7), 1, 48000, 8),
+                             (signals.sweep(100, 8000, 48000, 6, 0.3), 6, 48000, 0)]:
+        ref = oracle.encode(x, ch, sr)
+        want = oracle.flac_encode(oracle.decode(ref), sr, ch, level)
+        got = Decoder(ch, sr, gpu_ctx).decode_to_flac(to_product(ref), level)
+        assert got == want, (ch, sr, level, len(got), len(want))
+        info = oracle.flac_decode(got)
+        assert info["md5_ok"] and info["total_samples"] == len(x) // ch  # gapless count survives the whole chain
