@@ -2198,31 +2198,31 @@ extern "C" glc_status glc_dev_pcm_download(const glc_dev_pcm *p, float **pcm, ui
 }
 
 // ------------------------------------------------------- streaming decode
+//
+// Decoder::decode_streaming (src/codec.rs:595-741) hands out chunks of exactly 500 frames while a
+// background thread keeps decoding; here every _next decodes just the frames of its chunk on the
+// device (plus the one frame before it, whose second half is the chunk's first overlap), so the
+// first audio is available after one chunk's worth of work and the host holds one chunk at a time.
 
 struct glc_stream
 {
-    glc_ctx *ctx;
-    float *all;       // untrimmed decode, pinned
-    uint64_t n_all;
-    uint64_t n_frames;
-    uint32_t channels;
-    uint64_t next_frame; // frames already handed out
+    glc_decoder *dec;
+    const glc_encoded *enc; // borrowed: must stay alive until _close (the reference shares an Arc)
+    float *chunk;           // pinned memory of the current chunk (from glc_decode_untrimmed)
+    uint64_t next_frame;    // frames already handed out
     bool finished;
+    std::vector<uint64_t> pair_off, raw_off; // rebased offsets of the sub-range being decoded
 };
 
 extern "C" glc_status glc_decode_stream_open(glc_decoder *dec, const glc_encoded *enc, glc_stream **out)
 {
     if (!dec || !enc || !out)
         return fail(GLC_ERR_INVALID_ARG, "null argument");
-    float *all = nullptr;
-    uint64_t n = 0;
-    GLC_TRY(glc_decode_untrimmed(dec, enc, &all, &n));
+    GLC_TRY(validate_encoded(enc, 0));
     glc_stream *s = new glc_stream();
-    s->ctx = dec->ctx;
-    s->all = all;
-    s->n_all = n;
-    s->n_frames = enc->n_frames;
-    s->channels = enc->channels;
+    s->dec = dec;
+    s->enc = enc;
+    s->chunk = nullptr;
     s->next_frame = 0;
     s->finished = false;
     *out = s;
@@ -2236,19 +2236,56 @@ extern "C" glc_status glc_decode_stream_next(glc_stream *s, const float **sample
         return fail(GLC_ERR_INVALID_ARG, "null argument");
     if (s->finished)
         return fail(GLC_ERR_INVALID_ARG, "stream already delivered its last chunk");
-    const uint64_t per_frame = (uint64_t)kHop * s->channels;
-    const uint64_t remaining = s->n_frames - s->next_frame;
-    *samples = s->all + s->next_frame * per_frame;
-    if (remaining >= GLC_FRAMES_PER_CHUNK)
+    const glc_encoded *e = s->enc;
+    const uint64_t ch = e->channels, per_frame = (uint64_t)kHop * ch;
+    const uint64_t remaining = e->n_frames - s->next_frame;
+    const bool last = remaining < GLC_FRAMES_PER_CHUNK;
+    const uint64_t a = s->next_frame, b = last ? e->n_frames : a + GLC_FRAMES_PER_CHUNK;
+    const uint64_t a0 = a ? a - 1 : 0; // one frame of history for the first overlap
+    if (s->chunk)
+    {
+        glc_free(s->dec->ctx, s->chunk);
+        s->chunk = nullptr;
+    }
+    // view of frames [a0, b) as a stream of its own
+    glc_encoded sub = *e;
+    sub.n_frames = b - a0;
+    sub.frame_is_raw = e->frame_is_raw + a0;
+    sub.nnz = e->nnz + a0 * ch;
+    sub.scales = e->scales + a0 * ch;
+    const uint64_t rows = (b - a0) * ch;
+    uint64_t pbase = 0, rbase = 0;
+    if (e->n_frames)
+    {
+        pbase = e->pair_offset[a0 * ch];
+        rbase = e->raw_offset[a0];
+    }
+    s->pair_off.resize(rows + 1);
+    s->raw_off.resize(b - a0 + 1);
+    for (uint64_t r = 0; r <= rows; ++r)
+        s->pair_off[r] = e->n_frames ? e->pair_offset[a0 * ch + r] - pbase : 0;
+    for (uint64_t f = 0; f <= b - a0; ++f)
+        s->raw_off[f] = e->n_frames ? e->raw_offset[a0 + f] - rbase : 0;
+    sub.pair_offset = s->pair_off.data();
+    sub.raw_offset = s->raw_off.data();
+    sub.pairs = e->pairs + pbase;
+    sub.raw = e->raw + rbase;
+    float *pcm = nullptr;
+    uint64_t n = 0;
+    GLC_TRY(glc_decode_untrimmed(s->dec, &sub, &pcm, &n)); // hops of frames a0..b-1, then the final overlap
+    s->chunk = pcm;
+    const uint64_t skip = (a - a0) * per_frame; // the history frame's own hop was delivered with the previous chunk
+    *samples = pcm + skip;
+    if (!last)
     {
         // a full chunk is flushed as soon as 500 frames are buffered (src/codec.rs:708-717);
         // `idx` there is the index of the frame that completed the chunk
         *n_samples = GLC_FRAMES_PER_CHUNK * per_frame;
         *is_last = 0;
-        const uint64_t idx = s->next_frame + GLC_FRAMES_PER_CHUNK - 1;
+        const uint64_t idx = a + GLC_FRAMES_PER_CHUNK - 1;
         if (progress_percent)
-            *progress_percent = (float)idx / (float)s->n_frames * 100.0f;
-        s->next_frame += GLC_FRAMES_PER_CHUNK;
+            *progress_percent = (float)idx / (float)e->n_frames * 100.0f;
+        s->next_frame = b;
     }
     else
     {
@@ -2256,7 +2293,7 @@ extern "C" glc_status glc_decode_stream_next(glc_stream *s, const float **sample
         *is_last = 1;
         if (progress_percent)
             *progress_percent = -1.0f;
-        s->next_frame = s->n_frames;
+        s->next_frame = e->n_frames;
         s->finished = true;
     }
     return GLC_OK;
@@ -2266,6 +2303,7 @@ extern "C" void glc_decode_stream_close(glc_stream *s)
 {
     if (!s)
         return;
-    glc_free(s->ctx, s->all);
+    if (s->chunk)
+        glc_free(s->dec->ctx, s->chunk);
     delete s;
 }

@@ -162,7 +162,8 @@ glc_status glc_decode_batch(glc_decoder *dec, uint32_t n_files, const glc_encode
  * FRAMES_PER_CHUNK*HOP_SIZE*channels values while more frames remain, then the tail with
  * is_last = 1 (src/codec.rs:708-717, :723-732).  `progress_percent` is the value the reference
  * sends as Progress::Decoding before that chunk (:712), or -1 for the last chunk.  The chunk
- * memory belongs to the stream and is valid until the next _next/_close. */
+ * memory belongs to the stream and is valid until the next _next/_close.  Each _next decodes only
+ * its own frames on the device (incremental); `enc` is borrowed and must outlive the stream. */
 glc_status glc_decode_stream_open(glc_decoder *dec, const glc_encoded *enc, glc_stream **out);
 glc_status glc_decode_stream_next(glc_stream *s, const float **samples, uint64_t *n_samples,
                                   int *is_last, float *progress_percent);

@@ -148,6 +148,27 @@ def test_streaming_chunks_match_reference_shape(gpu_ctx):
     assert pct[0] == pytest.approx(499 / enc.n_frames * 100, rel=1e-6)
 
 
+def test_streaming_is_incremental_and_exact_across_chunk_boundaries(gpu_ctx):
+    """stereo content with raw and sparse frames on both sides of the 500-frame boundaries: every chunk is
+    decoded on its own (plus one frame of history) and must still concatenate to the reference stream."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    x = np.tile(signals.music_like(44100, 2, 6.0), 4)  # 24 s stereo -> 1035 frames -> 500 + 500 + 36
+    enc = Encoder(44100, gpu_ctx).encode(x, 2)
+    dec = Decoder(2, 44100, gpu_ctx)
+    gpu_ctx.stats_reset()
+    it = dec.decode_streaming(enc)
+    first = next(it)
+    launched_for_first = gpu_ctx.stats()["launches"]["imdct_exact"]
+    rest = list(it)
+    total = gpu_ctx.stats()["launches"]["imdct_exact"]
+    assert launched_for_first >= 1 and total > launched_for_first  # work happens per chunk, not at open
+    chunks = [first] + rest
+    assert [len(c.samples) for c in chunks] == [500 * 1024 * 2, 500 * 1024 * 2, (enc.n_frames - 1000 + 1) * 1024 * 2]
+    cat = np.concatenate([c.samples for c in chunks])
+    assert_pcm_bits_equal(cat, oracle.decode(to_oracle(enc), trimmed=False), "incremental streaming concat")
+
+
 def test_decoder_accepts_unsorted_and_duplicate_pairs(gpu_ctx):
     """'later duplicates overwrite' + idx >= 1024 ignored (src/codec.rs:659-665)."""
     from gapless_lossy_codec_b200 import Decoder
