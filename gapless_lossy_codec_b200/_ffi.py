@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libglc_b200.so")
+# GLC_B200_LIB overrides the library path (used to A/B kernel variants; still no fallback of any kind)
+LIB_PATH = os.environ.get("GLC_B200_LIB") or os.path.join(_PKG, "libglc_b200.so")
 
 GLC_OK = 0
 STATUS_NAMES = {
