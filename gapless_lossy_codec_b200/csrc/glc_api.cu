@@ -1060,8 +1060,8 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     uint64_t target_rows = kRowQuantum * (host_pcm ? 4 : 32);
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1); // explicit tuning: rows per wave
-    if (fast)
-        target_rows = UINT64_MAX; // the fused FFT kernel takes the whole batch in one launch
+    if (fast && !host_pcm)
+        target_rows = UINT64_MAX; // device-resident: the fused FFT kernel takes the whole batch in one launch
     uint64_t max_wave_rows = 0;
     const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, true);
     float *d_atiles = nullptr;
@@ -1214,8 +1214,8 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             fe.files = d_files;
             fe.n_files = n_files;
             fe.first_group = d_first_group;
-            fe.group_begin = 0;
-            fe.group_end = n_groups;
+            fe.group_begin = group_of_frame(w.f0);
+            fe.group_end = group_of_frame(w.f1);
             fe.window = c->d_window;
             fe.twiddles = reinterpret_cast<const float2 *>(c->d_fast_tw);
             fe.norm = c->host.norm;

@@ -43,6 +43,9 @@ CASES = [
     ("rate_8k_mono", lambda: signals.sine(300, 8000, 1, 1.0), 1, 8000),
     ("silence", lambda: np.zeros(30000, np.float32), 1, 44100),
     ("full_scale_clip", lambda: np.clip(signals.sine(997, 44100, 1, 0.5, amp=1.5), -1, 1), 1, 44100),
+    # more channels than a frame group / than the OLA fast path holds
+    ("ten_channels", lambda: signals.music_like(44100, 10, 0.4, seed=77), 10, 44100),
+    ("seventeen_channels", lambda: signals.sweep(200, 6000, 32000, 17, 0.25), 17, 32000),
 ]
 
 

@@ -45,6 +45,7 @@ CASES = [
     ("square_mono", lambda: signals.square(440, 44100, 1, 0.7), 1, 44100),
     ("ragged_len", lambda: signals.sine(300, 44100, 1, 0.3)[:4097], 1, 44100),
     ("three_channels", lambda: signals.music_like(44100, 3, 0.5), 3, 44100),
+    ("ten_channels", lambda: signals.music_like(44100, 10, 0.4, seed=77), 10, 44100),
 ]
 
 
