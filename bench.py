@@ -409,7 +409,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "frac": achieved_tops / fp32_roof if fp32_roof else None,
         "peak_source": "FMUL+FADD issue micro-benchmark on this GPU in this run (glc_measure_fp32_issue); "
                        "non-FMA FP32 lane-ops: tensor cores / FMA / reordering break bit-exact parity",
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
+        # profiles/r1_ncu_exact_gemm_tma_full_summary.csv: 620 965 888 B for a launch of 51 712 rows
+        # (12 008 B/row = the 8 KiB A tile it reads + the 4 KiB coefficient row it writes; the table stays
+        # in L2), scaled to the rows of one launch of this run
+        "traffic": 12008.0 * rows / max(k_n["mdct_exact"] / args.steps, 1),
+        "traffic_source": "ncu capture of a 51 712-row launch (12 008 B per row), scaled to this run's rows per launch",
         "launches_per_step": k_n["mdct_exact"] / args.steps,
         "ms_per_launch": k_ms["mdct_exact"] / max(k_n["mdct_exact"], 1),
         "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
