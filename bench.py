@@ -515,8 +515,12 @@ def cpu_baseline(args) -> dict:
     x = synth(secs)
     cpu_codec_pass(x[: 5 * SR * CH], cores)
     te, td = cpu_codec_pass(x, cores)
+    one = x[: 6 * SR * CH]  # single-core figure on a 6 s prefix (SURVEY.md 8d asks for both)
+    te1, td1 = cpu_codec_pass(one, 1)
     return {"value": secs / (te + td), "unit": UNIT, "cores": cores, "kind": "port",
             "encode_value": secs / te, "decode_value": secs / td,
+            "one_core": {"value": 6.0 / (te1 + td1), "encode_value": 6.0 / te1, "decode_value": 6.0 / td1,
+                         "sample": "first 6 s, 1 thread"},
             "sample": f"first {secs:.0f} s of the same workload, one pass; C restatement of the reference "
                       f"(the Rust crate cannot be built here), {cores} pthreads over frames, dense reference-order IMDCT"}
 

@@ -82,8 +82,9 @@ __device__ __forceinline__ void load_lane_tw(LaneTw &tw, const float2 *table, in
 __device__ __forceinline__ void dct4_pair(float2 *pair, const LaneTw &tw, int lane)
 {
     using namespace fastfft;
-    // ---- pass 1: lane = n1, 16-point FFT over n2 for each of the two inputs ----
-#pragma unroll
+    // ---- pass 1: lane = n1, 16-point FFT over n2 for each of the two inputs (rolled: the kernel is
+    //      instruction-cache bound, one copy of the butterfly code is enough) ----
+#pragma unroll 1
     for (int f = 0; f < 2; ++f)
     {
         float2 *u = pair + f * (kHop / 2);
@@ -271,28 +272,13 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                 for (int fc = 0; fc < kFastFcs; ++fc)
                 {
                     x[fc][0] = x[fc][1] = x[fc][2] = x[fc][3] = 0.0f;
-                    if ((uint32_t)fc < fcs_here)
+                    if ((uint32_t)fc < fcs_here && sm.st_interior[fc])
                     {
                         const float *fb = sm.st_ptr[fc];
-                        if (sm.st_interior[fc])
-                        {
-                            x[fc][0] = __ldg(fb + i0 * ich);
-                            x[fc][1] = __ldg(fb + i1 * ich);
-                            x[fc][2] = __ldg(fb + i2 * ich);
-                            x[fc][3] = __ldg(fb + i3 * ich);
-                        }
-                        else
-                        {
-                            const long long base = sm.st_base[fc];
-                            auto smp = [&](int i) -> float {
-                                const long long pos = base + i;
-                                return (pos >= 0 && pos < len) ? __ldg(fb + (long long)i * ich) : 0.0f;
-                            };
-                            x[fc][0] = smp(i0);
-                            x[fc][1] = smp(i1);
-                            x[fc][2] = smp(i2);
-                            x[fc][3] = smp(i3);
-                        }
+                        x[fc][0] = __ldg(fb + i0 * ich);
+                        x[fc][1] = __ldg(fb + i1 * ich);
+                        x[fc][2] = __ldg(fb + i2 * ich);
+                        x[fc][3] = __ldg(fb + i3 * ich);
                     }
                 }
 #pragma unroll
@@ -312,6 +298,32 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                         }
                         sm.u[fc][n] = make_float2(u0, u1);
                     }
+                // frames that touch the 512-zero lead-in or the zero tail (first / last frames of a file)
+#pragma unroll 1
+                for (uint32_t fc = 0; fc < fcs_here; ++fc)
+                {
+                    if (sm.st_interior[fc])
+                        continue;
+                    const float *fb = sm.st_ptr[fc];
+                    const long long base = sm.st_base[fc];
+                    auto smp = [&](int i) -> float {
+                        const long long pos = base + i;
+                        return (pos >= 0 && pos < len) ? __ldg(fb + (long long)i * ich) : 0.0f;
+                    };
+                    const float y0 = smp(i0), y1 = smp(i1), y2 = smp(i2), y3 = smp(i3);
+                    float u0, u1;
+                    if (n < 256)
+                    {
+                        u0 = -y0 * wa - y1 * wo;
+                        u1 = y2 * wo - y3 * wa;
+                    }
+                    else
+                    {
+                        u0 = y0 * wo - y1 * wa;
+                        u1 = -y2 * wa - y3 * wo;
+                    }
+                    sm.u[fc][n] = make_float2(u0, u1);
+                }
             }
             if (fcs_here & 1u) // the transform works on pairs: an odd group gets a silent partner
                 for (uint32_t n = tid; n < kHop / 2; n += kFastThreads)
@@ -329,17 +341,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                     const uint32_t fc = fc0 + fa + h;
                     const uint32_t lf = fc / ch;
                     const uint64_t row = fd.first_row + (gg.frame0 + lf) * ch + (fc - lf * ch);
-                    // lane l holds bins 128 j + 4 l + {0..3}, j = 0..7
-                    float cf[8][4];
+                    // lane l handles bins 128 j + 4 l + {0..3}, j = 0..7
                     float m = 0.0f;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                     {
                         const float4 v = *reinterpret_cast<const float4 *>(coef + j * 128 + lane * 4);
-                        cf[j][0] = v.x;
-                        cf[j][1] = v.y;
-                        cf[j][2] = v.z;
-                        cf[j][3] = v.w;
                         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
                     }
                     // scale = max|c| .max(1e-10)                                  src/codec.rs:488-489
@@ -384,9 +391,11 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                     const float qmul = 32768.0f / scale;
                     glc_pair *dst = p.slots + row * kHop;
                     uint32_t total = 0;
-#pragma unroll
+#pragma unroll 1
                     for (int j = 0; j < 8; ++j)
                     {
+                        const float4 c4 = *reinterpret_cast<const float4 *>(coef + j * 128 + lane * 4);
+                        const float cfj[4] = {c4.x, c4.y, c4.z, c4.w};
                         const float4 iw4 = *reinterpret_cast<const float4 *>(sm.inv_w + j * 128 + lane * 4);
                         const uchar4 bo4 = *reinterpret_cast<const uchar4 *>(sm.band_of + j * 128 + lane * 4);
                         const float iw[4] = {iw4.x, iw4.y, iw4.z, iw4.w};
@@ -396,7 +405,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                         {
-                            const float v = cf[j][e];
+                            const float v = cfj[e];
                             const float a = fabsf(v);
                             float th = sm.band_base[warp][bo[e]] * iw[e];
                             if (a > peak_gate)
