@@ -56,7 +56,14 @@ struct FastSmem
     // staging descriptors of the group's frame-channels
     const float *st_ptr[kFastFcs];
     long long st_base[kFastFcs];
+    unsigned long long st_row[kFastFcs]; // output row (frame-channel index in the batch)
     int st_interior[kFastFcs];
+    int st_lf[kFastFcs];                 // frame of the group the frame-channel belongs to
+    // the group being processed (filled by thread 0)
+    const float *g_src;
+    long long g_len;
+    unsigned long long g_first_row, g_first_frame, g_frame0;
+    uint32_t g_ch, g_n_frames;
 };
 
 // per-lane twiddle constants, computed once per thread
@@ -217,14 +224,34 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
     for (uint64_t g = p.group_begin + blockIdx.x; g < p.group_end; g += gridDim.x)
     {
         __syncthreads(); // tables ready / previous group done with shared memory
-        const GroupGeom gg = locate_group(p.first_group, p.files, p.n_files, g);
-        const FileDesc fd = p.files[gg.file];
-        const uint32_t ch = fd.channels;
-        const uint32_t n_fc = gg.n_frames * ch; // may exceed kFastFcs only when ch > 8 (then processed in rounds)
+        if (tid == 0)
+        {
+            const GroupGeom gg0 = locate_group(p.first_group, p.files, p.n_files, g);
+            const FileDesc &fd0 = p.files[gg0.file];
+            sm.g_src = p.pcm_arena + fd0.pcm_off;
+            sm.g_len = (long long)fd0.len;
+            sm.g_first_row = fd0.first_row;
+            sm.g_first_frame = fd0.first_frame;
+            sm.g_frame0 = gg0.frame0;
+            sm.g_ch = fd0.channels;
+            sm.g_n_frames = gg0.n_frames;
+        }
         if (tid < kFastFcs)
             sm.frame_nnz[tid] = 0;
-        const float *src = p.pcm_arena + fd.pcm_off;
-        const long long len = (long long)fd.len;
+        __syncthreads();
+        struct
+        {
+            uint64_t frame0;
+            uint32_t n_frames;
+        } gg{sm.g_frame0, sm.g_n_frames};
+        struct
+        {
+            uint64_t first_row, first_frame;
+        } fd{sm.g_first_row, sm.g_first_frame};
+        const uint32_t ch = sm.g_ch;
+        const uint32_t n_fc = gg.n_frames * ch; // may exceed kFastFcs only when ch > 8 (then processed in rounds)
+        const float *src = sm.g_src;
+        const long long len = sm.g_len;
         const int n_bands = sm.n_bands;
 
         for (uint32_t fc0 = 0; fc0 < n_fc; fc0 += kFastFcs)
@@ -242,6 +269,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                 sm.st_base[tid] = base;
                 sm.st_ptr[tid] = src + base * (long long)ch + c; // only dereferenced in range
                 sm.st_interior[tid] = base >= 0 && base + kFrame <= len; // no padding inside this frame
+                sm.st_row[tid] = fd.first_row + (gg.frame0 + lf) * ch + c;
+                sm.st_lf[tid] = (int)lf;
             }
             __syncthreads();
             const int ich = (int)ch;
@@ -338,9 +367,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                 for (uint32_t h = 0; h < n_here; ++h)
                 {
                     const float *coef = reinterpret_cast<const float *>(sm.u[fa]) + h * kCoefStride;
-                    const uint32_t fc = fc0 + fa + h;
-                    const uint32_t lf = fc / ch;
-                    const uint64_t row = fd.first_row + (gg.frame0 + lf) * ch + (fc - lf * ch);
+                    const uint32_t lf = (uint32_t)sm.st_lf[fa + h];
+                    const uint64_t row = sm.st_row[fa + h];
                     // lane l handles bins 128 j + 4 l + {0..3}, j = 0..7
                     float m = 0.0f;
 #pragma unroll
