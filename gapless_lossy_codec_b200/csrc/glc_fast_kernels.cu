@@ -47,6 +47,7 @@ struct FastSmem
     float2 u[kFastFcs][kHop / 2];
     float inv_w[kHop];
     float band_base[kFastWarps][kMaxBands];
+    float band_base2[kFastWarps][kMaxBands]; // second frame-channel of the warp's pair
     float band_fac[kMaxBands];  // 0.01 * compression_factor * perceptual_factor        src/codec.rs:221-223
     float band_rcnt[kMaxBands]; // 1 / bins in the band
     int16_t band_lo[kMaxBands], band_hi[kMaxBands];
@@ -59,6 +60,7 @@ struct FastSmem
     unsigned long long st_row[kFastFcs]; // output row (frame-channel index in the batch)
     int st_interior[kFastFcs];
     int st_lf[kFastFcs];                 // frame of the group the frame-channel belongs to
+    int st_off[kFastFcs];                // element offset of the frame-channel's window from st_ptr[0]
     // the group being processed (filled by thread 0)
     const float *g_src;
     long long g_len;
@@ -271,9 +273,22 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                 sm.st_interior[tid] = base >= 0 && base + kFrame <= len; // no padding inside this frame
                 sm.st_row[tid] = fd.first_row + (gg.frame0 + lf) * ch + c;
                 sm.st_lf[tid] = (int)lf;
+                const uint32_t lf0 = fc0 / ch, c0 = fc0 - lf0 * ch; // frame-channel 0 of this round
+                sm.st_off[tid] = (int)(lf - lf0) * (int)(kHop * ch) + ((int)c - (int)c0);
             }
             __syncthreads();
             const int ich = (int)ch;
+            // per-thread copies of the round's descriptors: one base pointer, 32-bit offsets, a validity mask
+            const float *gb = sm.st_ptr[0];
+            int foff[kFastFcs];
+            unsigned interior_mask = 0;
+#pragma unroll
+            for (int fc = 0; fc < kFastFcs; ++fc)
+            {
+                foff[fc] = sm.st_off[fc];
+                if ((uint32_t)fc < fcs_here && sm.st_interior[fc])
+                    interior_mask |= 1u << fc;
+            }
 #pragma unroll 1
             for (int it = 0; it < (kHop / 2) / kFastThreads; ++it)
             {
@@ -296,18 +311,18 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                     i2 = 512 + 2 * n;
                     i3 = 2559 - 2 * n;
                 }
+                const int o0 = i0 * ich, o1 = i1 * ich, o2 = i2 * ich, o3 = i3 * ich;
                 float x[kFastFcs][4];
 #pragma unroll
                 for (int fc = 0; fc < kFastFcs; ++fc)
                 {
                     x[fc][0] = x[fc][1] = x[fc][2] = x[fc][3] = 0.0f;
-                    if ((uint32_t)fc < fcs_here && sm.st_interior[fc])
+                    if ((interior_mask >> fc) & 1u)
                     {
-                        const float *fb = sm.st_ptr[fc];
-                        x[fc][0] = __ldg(fb + i0 * ich);
-                        x[fc][1] = __ldg(fb + i1 * ich);
-                        x[fc][2] = __ldg(fb + i2 * ich);
-                        x[fc][3] = __ldg(fb + i3 * ich);
+                        x[fc][0] = __ldg(gb + (foff[fc] + o0));
+                        x[fc][1] = __ldg(gb + (foff[fc] + o1));
+                        x[fc][2] = __ldg(gb + (foff[fc] + o2));
+                        x[fc][3] = __ldg(gb + (foff[fc] + o3));
                     }
                 }
 #pragma unroll
@@ -363,119 +378,162 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
             {
                 const uint32_t fa = pr * 2;
                 dct4_pair(sm.u[fa], tw, lane);
-                const uint32_t n_here = (pr * 2 + 1 < fcs_here) ? 2u : 1u;
-                for (uint32_t h = 0; h < n_here; ++h)
+                // Both frame-channels of the pair are quantised in lock step: the two instruction streams
+                // are independent, which doubles the work in flight of this latency-bound phase.  (For an
+                // odd group the partner is silence; its results are not stored.)
+                const bool two = pr * 2 + 1 < fcs_here;
+                const float *coef0 = reinterpret_cast<const float *>(sm.u[fa]);
+                const float *coef1 = coef0 + kCoefStride;
+                float m0 = 0.0f, m1 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
                 {
-                    const float *coef = reinterpret_cast<const float *>(sm.u[fa]) + h * kCoefStride;
-                    const uint32_t lf = (uint32_t)sm.st_lf[fa + h];
-                    const uint64_t row = sm.st_row[fa + h];
-                    // lane l handles bins 128 j + 4 l + {0..3}, j = 0..7
-                    float m = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                    {
-                        const float4 v = *reinterpret_cast<const float4 *>(coef + j * 128 + lane * 4);
-                        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-                    }
-                    // scale = max|c| .max(1e-10)                                  src/codec.rs:488-489
-                    const float gmax = fmaxf(warp_max_f(m), 1e-10f);
-                    const float scale = gmax;
-                    // band energies -> per-band base threshold (already times scale, :288)   :205-224
-                    for (int b0 = 0; b0 < n_bands; b0 += 32)
-                    {
-                        const int b = b0 + lane;
-                        int lo = 0, hi = 0;
-                        if (b < n_bands)
-                        {
-                            lo = sm.band_lo[b];
-                            hi = sm.band_hi[b];
-                        }
-                        const bool wide = (hi - lo) > 32;
-                        float acc = 0.0f;
-                        if (!wide)
-                            for (int k = lo; k < hi; ++k)
-                                acc = fmaf(coef[k], coef[k], acc);
-                        unsigned wide_mask = __ballot_sync(0xffffffffu, wide);
-                        while (wide_mask)
-                        {
-                            const int src_lane = __ffs(wide_mask) - 1;
-                            wide_mask &= wide_mask - 1;
-                            const int wlo = __shfl_sync(0xffffffffu, lo, src_lane), whi = __shfl_sync(0xffffffffu, hi, src_lane);
-                            float part = 0.0f;
-                            for (int k = wlo + lane; k < whi; k += 32)
-                                part = fmaf(coef[k], coef[k], part);
-                            part = warp_sum_f(part);
-                            if (lane == src_lane)
-                                acc = part;
-                        }
-                        if (b < n_bands)
-                            sm.band_base[warp][b] = sqrtf(acc * sm.band_rcnt[b]) * sm.band_fac[b] * scale;
-                    }
-                    __syncwarp();
-                    // thresholds + quantiser + ordered compaction               src/codec.rs:226-235, 277-307
-                    const float nf = noise_floor_factor * scale;
-                    const float peak_gate = 0.3f * gmax;
-                    const float peak_cap = 0.05f * gmax * scale;
-                    const float qmul = 32768.0f / scale;
-                    glc_pair *dst = p.slots + row * kHop;
-                    uint32_t total = 0;
-#pragma unroll 1
-                    for (int j = 0; j < 8; ++j)
-                    {
-                        const float4 c4 = *reinterpret_cast<const float4 *>(coef + j * 128 + lane * 4);
-                        const float cfj[4] = {c4.x, c4.y, c4.z, c4.w};
-                        const float4 iw4 = *reinterpret_cast<const float4 *>(sm.inv_w + j * 128 + lane * 4);
-                        const uchar4 bo4 = *reinterpret_cast<const uchar4 *>(sm.band_of + j * 128 + lane * 4);
-                        const float iw[4] = {iw4.x, iw4.y, iw4.z, iw4.w};
-                        const unsigned bo[4] = {bo4.x, bo4.y, bo4.z, bo4.w};
-                        int qv[4];
-                        uint32_t cnt = 0;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                        {
-                            const float v = cfj[e];
-                            const float a = fabsf(v);
-                            float th = sm.band_base[warp][bo[e]] * iw[e];
-                            if (a > peak_gate)
-                                th = fminf(th, peak_cap);
-                            int q = 0;
-                            if (a > fmaxf(nf, th))
-                            {
-                                // round half away from zero (f32::round) as trunc(x + copysign(0.5, x))
-                                const float x = v * qmul;
-                                q = __float2int_rz(fminf(fmaxf(x + copysignf(0.5f, x), -32768.0f), 32767.0f));
-                            }
-                            qv[e] = q;
-                            cnt += q != 0;
-                        }
-                        uint32_t incl = cnt;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1)
-                        {
-                            const uint32_t nn = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o)
-                                incl += nn;
-                        }
-                        uint32_t pos = total + (incl - cnt);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (qv[e] != 0)
-                            {
-                                glc_pair pr2;
-                                pr2.idx = (uint16_t)(j * 128 + lane * 4 + e);
-                                pr2.q = (int16_t)qv[e];
-                                dst[pos++] = pr2;
-                            }
-                        total += __shfl_sync(0xffffffffu, incl, 31);
-                    }
-                    if (lane == 0)
-                    {
-                        p.nnz[row] = total;
-                        p.scales[row] = scale;
-                        atomicAdd(&sm.frame_nnz[lf], total); // lf < frames per group <= kFastFcs
-                    }
-                    __syncwarp();
+                    const float4 v0 = *reinterpret_cast<const float4 *>(coef0 + j * 128 + lane * 4);
+                    const float4 v1 = *reinterpret_cast<const float4 *>(coef1 + j * 128 + lane * 4);
+                    m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+                    m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
                 }
+                // scale = max|c| .max(1e-10)                                  src/codec.rs:488-489
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+                }
+                const float gmax0 = fmaxf(m0, 1e-10f), gmax1 = fmaxf(m1, 1e-10f);
+                const float scale0 = gmax0, scale1 = gmax1;
+                // band energies -> per-band base threshold (already times scale, :288)   :205-224
+                float *base0 = sm.band_base[warp], *base1 = sm.band_base2[warp];
+                for (int b0 = 0; b0 < n_bands; b0 += 32)
+                {
+                    const int b = b0 + lane;
+                    int lo = 0, hi = 0;
+                    if (b < n_bands)
+                    {
+                        lo = sm.band_lo[b];
+                        hi = sm.band_hi[b];
+                    }
+                    const bool wide = (hi - lo) > 32;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+                    if (!wide)
+                        for (int k = lo; k < hi; ++k)
+                        {
+                            acc0 = fmaf(coef0[k], coef0[k], acc0);
+                            acc1 = fmaf(coef1[k], coef1[k], acc1);
+                        }
+                    unsigned wide_mask = __ballot_sync(0xffffffffu, wide);
+                    while (wide_mask)
+                    {
+                        const int src_lane = __ffs(wide_mask) - 1;
+                        wide_mask &= wide_mask - 1;
+                        const int wlo = __shfl_sync(0xffffffffu, lo, src_lane), whi = __shfl_sync(0xffffffffu, hi, src_lane);
+                        float p0 = 0.0f, p1 = 0.0f;
+                        for (int k = wlo + lane; k < whi; k += 32)
+                        {
+                            p0 = fmaf(coef0[k], coef0[k], p0);
+                            p1 = fmaf(coef1[k], coef1[k], p1);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                        {
+                            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                        }
+                        if (lane == src_lane)
+                        {
+                            acc0 = p0;
+                            acc1 = p1;
+                        }
+                    }
+                    if (b < n_bands)
+                    {
+                        const float f = sm.band_fac[b], rc = sm.band_rcnt[b];
+                        base0[b] = sqrtf(acc0 * rc) * f * scale0;
+                        base1[b] = sqrtf(acc1 * rc) * f * scale1;
+                    }
+                }
+                __syncwarp();
+                // thresholds + quantiser + ordered compaction               src/codec.rs:226-235, 277-307
+                const float nf0 = noise_floor_factor * scale0, nf1 = noise_floor_factor * scale1;
+                const float gate0 = 0.3f * gmax0, gate1 = 0.3f * gmax1;
+                const float cap0 = 0.05f * gmax0 * scale0, cap1 = 0.05f * gmax1 * scale1;
+                const float qmul0 = 32768.0f / scale0, qmul1 = 32768.0f / scale1;
+                const uint64_t row0 = sm.st_row[fa], row1 = sm.st_row[two ? fa + 1 : fa];
+                glc_pair *dst0 = p.slots + row0 * kHop, *dst1 = p.slots + row1 * kHop;
+                uint32_t total0 = 0, total1 = 0;
+                auto quant1 = [&](float v, float bs, float iw, float nf, float gate, float cap, float qmul) -> int {
+                    const float a = fabsf(v);
+                    float th = bs * iw;
+                    th = fminf(th, a > gate ? cap : th);
+                    const float x = v * qmul;
+                    // round half away from zero (f32::round) as trunc(x + copysign(0.5, x))
+                    const int q = __float2int_rz(fminf(fmaxf(x + copysignf(0.5f, x), -32768.0f), 32767.0f));
+                    return a > fmaxf(nf, th) ? q : 0;
+                };
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j)
+                {
+                    const float4 c40 = *reinterpret_cast<const float4 *>(coef0 + j * 128 + lane * 4);
+                    const float4 c41 = *reinterpret_cast<const float4 *>(coef1 + j * 128 + lane * 4);
+                    const float4 iw4 = *reinterpret_cast<const float4 *>(sm.inv_w + j * 128 + lane * 4);
+                    const uchar4 bo4 = *reinterpret_cast<const uchar4 *>(sm.band_of + j * 128 + lane * 4);
+                    int q0[4], q1[4];
+                    q0[0] = quant1(c40.x, base0[bo4.x], iw4.x, nf0, gate0, cap0, qmul0);
+                    q1[0] = quant1(c41.x, base1[bo4.x], iw4.x, nf1, gate1, cap1, qmul1);
+                    q0[1] = quant1(c40.y, base0[bo4.y], iw4.y, nf0, gate0, cap0, qmul0);
+                    q1[1] = quant1(c41.y, base1[bo4.y], iw4.y, nf1, gate1, cap1, qmul1);
+                    q0[2] = quant1(c40.z, base0[bo4.z], iw4.z, nf0, gate0, cap0, qmul0);
+                    q1[2] = quant1(c41.z, base1[bo4.z], iw4.z, nf1, gate1, cap1, qmul1);
+                    q0[3] = quant1(c40.w, base0[bo4.w], iw4.w, nf0, gate0, cap0, qmul0);
+                    q1[3] = quant1(c41.w, base1[bo4.w], iw4.w, nf1, gate1, cap1, qmul1);
+                    const uint32_t cnt0 = (q0[0] != 0) + (q0[1] != 0) + (q0[2] != 0) + (q0[3] != 0);
+                    const uint32_t cnt1 = (q1[0] != 0) + (q1[1] != 0) + (q1[2] != 0) + (q1[3] != 0);
+                    // one scan for both: the two counts (<= 4 per lane, <= 128 per warp) share a register
+                    uint32_t incl = cnt0 | (cnt1 << 16);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        const uint32_t nn = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o)
+                            incl += nn;
+                    }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t pos0 = total0 + (incl & 0xffffu) - cnt0, pos1 = total1 + (incl >> 16) - cnt1;
+                    const uint32_t kbase = (uint32_t)(j * 128 + lane * 4);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                    {
+                        if (q0[e] != 0)
+                        {
+                            glc_pair pr2;
+                            pr2.idx = (uint16_t)(kbase + e);
+                            pr2.q = (int16_t)q0[e];
+                            dst0[pos0++] = pr2;
+                        }
+                        if (two && q1[e] != 0)
+                        {
+                            glc_pair pr2;
+                            pr2.idx = (uint16_t)(kbase + e);
+                            pr2.q = (int16_t)q1[e];
+                            dst1[pos1++] = pr2;
+                        }
+                    }
+                    total0 += tot & 0xffffu;
+                    total1 += tot >> 16;
+                }
+                if (lane == 0)
+                {
+                    p.nnz[row0] = total0;
+                    p.scales[row0] = scale0;
+                    atomicAdd(&sm.frame_nnz[sm.st_lf[fa]], total0); // frame index < frames per group <= kFastFcs
+                    if (two)
+                    {
+                        p.nnz[row1] = total1;
+                        p.scales[row1] = scale1;
+                        atomicAdd(&sm.frame_nnz[sm.st_lf[fa + 1]], total1);
+                    }
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
