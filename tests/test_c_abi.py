@@ -31,3 +31,28 @@ def test_c_client_on_gpu():
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert r.stdout.startswith("OK frames=86")
+
+
+SUITE = os.path.join(HERE, "cpp", "reference_suite")
+
+
+def test_cpp_mirror_suite_links_and_refuses_to_run_without_a_gpu():
+    """include/glc.hpp (the C++ mirror of the reference's codec/flac API) compiles, links against the C
+    ABI and, with no device, stops at the context with GLC_ERR_NO_DEVICE."""
+    _build()
+    r = subprocess.run([SUITE], capture_output=True, text=True, timeout=120)
+    if r.returncode == 0:
+        pytest.skip("a CUDA device is present: covered by the gpu test")
+    assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)
+    assert "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_test_suite_over_cpp_mirror_on_gpu():
+    """Every test of the reference's tests/*.rs, restated over include/glc.hpp (tests/cpp/reference_suite.cpp),
+    plus the mirror's output compared bit for bit with the CPU oracle."""
+    _build()
+    r = subprocess.run([SUITE], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-4000:], r.stderr[-2000:])
+    assert "test result: ok." in r.stdout
+    assert r.stdout.count("... ok") >= 50
