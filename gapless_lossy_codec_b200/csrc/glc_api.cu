@@ -1673,7 +1673,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     // Worst-case sizes (every row transformed, every k present); the live counts stay on the device,
     // so the decode needs no host round trip.  `blocks` holds every row of the batch (+1 tile of
     // slack for the clipped last tile of a wave) because hop h needs frames h-1 and h.
-    CUDA_TRY(dmalloc(&d_atiles, wave_tiles * kHop * kBM, cs));
+    CUDA_TRY(dmalloc(&d_atiles, wave_tiles * kImdctATileFloats, cs));
     CUDA_TRY(dmalloc(&d_blocks, (tot_rows + kBM) * kFrame, cs));
     CUDA_TRY(dmalloc(&d_flags, max_wave_rows, cs));
     CUDA_TRY(dmalloc(&d_slot_off, max_wave_rows + 1, cs));

@@ -349,10 +349,12 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const DequantLaunch p)
 
 // One CTA per tile of kBM compacted rows: union of the coefficient indices present in the tile
 // (ascending), then the dequantised values (src/codec.rs:651-665) laid out as the A operand of the
-// IMDCT, [stage][kKC][kBM], over that union only.
+// IMDCT over that union only: per stage [kKC][kBM] values followed by one step mask per warp of the
+// IMDCT kernel (bit b of mask g = "one of rows 8g..8g+7 has a coefficient at step b of this stage").
 __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p)
 {
     __shared__ uint32_t s_bits[kHop / 32];
+    __shared__ uint32_t s_gbits[kImdctWarps][kHop / 32]; // per 8-row group
     __shared__ uint32_t s_prefix[kHop / 32];
     __shared__ uint32_t s_nk;
     const uint64_t n_active = p.slot_off[p.row_end - p.row_begin];
@@ -363,6 +365,8 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
     const uint32_t rows_here = (uint32_t)min((uint64_t)kBM, n_active - tile * kBM);
     if (tid < kHop / 32)
         s_bits[tid] = 0;
+    for (int e = tid; e < kImdctWarps * (kHop / 32); e += 256)
+        (&s_gbits[0][0])[e] = 0;
     __syncthreads();
 
     // pass 1: index union (any pair with idx < 1024 counts, also ones a later duplicate overwrites).
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         const uint32_t n = (uint32_t)(p.pair_off[row + 1] - b);
         const uint32_t chunk = (n + 31) / 32;
         const uint32_t j0 = min(n, lane * chunk), j1 = min(n, j0 + chunk);
+        uint32_t *gb = s_gbits[r / kImdctRowsPerWarp];
         uint32_t cur = 0xffffffffu, mask = 0;
         for (uint32_t j = j0; j < j1; ++j)
         {
@@ -385,14 +390,20 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
             if (w != cur)
             {
                 if (mask)
+                {
                     atomicOr(&s_bits[cur], mask);
+                    atomicOr(&gb[cur], mask);
+                }
                 cur = w;
                 mask = 0;
             }
             mask |= 1u << (idx & 31);
         }
         if (mask)
+        {
             atomicOr(&s_bits[cur], mask);
+            atomicOr(&gb[cur], mask);
+        }
     }
     __syncthreads();
     if (warp == 0)
@@ -413,6 +424,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
     __syncthreads();
     const uint32_t nk = s_nk;
     const uint32_t nk_pad = (nk + kKC - 1) / kKC * kKC;
+    const uint32_t n_stages = nk_pad / kKC;
     uint16_t *kl = p.klist + tile * kHop;
     for (uint32_t k = tid; k < kHop; k += 256)
     {
@@ -421,16 +433,16 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
             kl[s_prefix[k >> 5] + __popc(w & ((1u << (k & 31)) - 1u))] = (uint16_t)k;
     }
     for (uint32_t j = nk + tid; j < nk_pad; j += 256)
-        kl[j] = 0; // padding steps multiply an all-zero A column: exact no-ops
+        kl[j] = 0; // padding steps: no warp's mask selects them (and their A column is all zero)
     if (tid == 0)
         p.n_k[tile] = nk_pad;
 
-    // pass 2: zero the tile's A region, then scatter the values
-    float *a = p.a_tiles + tile * ((size_t)kHop * kBM);
+    // pass 2: zero the tile's A region (values and masks), then scatter the values
+    float *a = p.a_tiles + tile * kImdctATileFloats;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t e = tid; e < nk_pad * (kBM / 4); e += 256)
+    for (uint32_t e = tid; e < n_stages * (kImdctAStageFloats / 4); e += 256)
         reinterpret_cast<float4 *>(a)[e] = z;
-    __syncthreads();
+    __syncthreads(); // also makes kl[] visible to the mask pass below
     for (uint32_t r = warp; r < rows_here; r += 8)
     {
         const uint64_t row = p.active_rows[tile * kBM + r];
@@ -450,7 +462,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
             {
                 const uint32_t w = s_bits[q.idx >> 5];
                 const uint32_t pos = s_prefix[q.idx >> 5] + __popc(w & ((1u << (q.idx & 31)) - 1u));
-                a[(size_t)(pos / kKC) * (kKC * kBM) + (pos % kKC) * kBM + r] =
+                a[(size_t)(pos / kKC) * kImdctAStageFloats + (pos % kKC) * kBM + r] =
                     __fmul_rn(__fdiv_rn((float)q.q, 32768.0f), scale);
             }
         };
@@ -460,6 +472,23 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         else if (lane == 0)
             for (uint32_t j = 0; j < n; ++j)
                 put(j);
+    }
+    // step masks: presence of the index in the group's rows (a present pair whose value happens to be
+    // zero is simply not skipped, which is exact as well)
+    for (uint32_t e = tid; e < n_stages * kImdctWarps; e += 256)
+    {
+        const uint32_t st = e / kImdctWarps, g = e % kImdctWarps;
+        uint32_t m = 0;
+        for (uint32_t bpos = 0; bpos < (uint32_t)kKC; ++bpos)
+        {
+            const uint32_t pos = st * kKC + bpos;
+            if (pos < nk)
+            {
+                const uint32_t k = kl[pos];
+                m |= ((s_gbits[g][k >> 5] >> (k & 31)) & 1u) << bpos;
+            }
+        }
+        reinterpret_cast<uint32_t *>(a + (size_t)st * kImdctAStageFloats + kKC * kBM)[g] = m;
     }
 }
 

@@ -20,12 +20,14 @@
 //       - MDCT: A tiles are written by window_tile_kernel (padding rules of src/codec.rs:433-447 +
 //         window multiply, i.e. block[i]), one contiguous 16 KiB block per (row tile, stage); T comes
 //         from a host re-tiled copy of the table, also one contiguous block per (output block, stage).
-//       - IMDCT: the reduction runs over the UNION of the coefficient indices present in the 128
-//         rows of the tile, in ascending k (dequant_tile_kernel builds the list and the compacted A
-//         tiles).  Skipping a k whose coefficient is zero in a row is exact: the product is +-0 and
-//         the running sum (which starts at +0.0 and can never become -0) is unchanged.  T rows are
-//         gathered from the natural-layout table: 32 bulk copies of 512 B per stage, one per lane of
-//         warp 0.
+//   * IMDCT (imdct_sparse_kernel below) keeps the ring and the TMA feed but is SPARSE at warp
+//     granularity: the reduction runs over the ascending UNION of the coefficient indices present in
+//     the 128 rows of the tile (dequant_tile_kernel builds the list and the compacted A tiles), and
+//     every warp owns 8 rows and executes only the steps at which one of ITS rows has a coefficient
+//     (a 32-bit mask per warp and stage, delivered with the A stage).  Skipping a k whose coefficient
+//     is zero in a row is exact: the product is +-0 and the running sum (which starts at +0.0 and can
+//     never become -0) is unchanged.  T rows are gathered from the natural-layout table: 32 bulk
+//     copies of 1 KiB per stage, one per lane of warp 0.
 //   * Epilogue: * norm (and * window for IMDCT), two float4 stores per row.
 #include "glc_internal.cuh"
 
@@ -109,14 +111,13 @@ struct Smem
     uint64_t empty[kRing];
 };
 
-// MODE 0 = MDCT (reduce over i, 64 stages), MODE 1 = IMDCT (reduce over the tile's k-union)
-template <int MODE>
+// MDCT: reduce over i (64 stages of 32 steps)
 __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __grid_constant__ GemmParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    constexpr int kNOut = (MODE == 0 ? kHop : kFrame);
-    constexpr int kNBlocks = kNOut / kBN;
+    constexpr int kNBlocks = kHop / kBN;
+    constexpr int n_stages = kFrame / kKC;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -126,16 +127,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
     // linear grid, output block fastest: the CTAs that run together share A tiles in L2
     const int n_block = (int)(blockIdx.x % kNBlocks);
     const uint64_t m_tile = p.tile_begin + blockIdx.x / kNBlocks;
-
-    int n_stages;
-    if (MODE == 0)
-        n_stages = kFrame / kKC;
-    else
-    {
-        if (m_tile >= (uint64_t)__ldg(p.n_tiles))
-            return;
-        n_stages = (int)(__ldg(p.n_k + m_tile) / kKC);
-    }
 
     if (tid == 0)
     {
@@ -149,49 +140,28 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
     }
     __syncthreads();
 
-    const float *a_src = p.a_tiles + (size_t)m_tile * ((MODE == 0 ? kFrame : kHop) * kBM);
-    const float *t_src = (MODE == 0) ? p.tab + (size_t)n_block * (kFrame / kKC) * kStageFloats
-                                     : p.tab + (size_t)n_block * kBN;
-    const uint16_t *kl = (MODE == 1) ? p.klist + (size_t)m_tile * kHop : nullptr;
+    const float *a_src = p.a_tiles + (size_t)m_tile * (kFrame * kBM);
+    const float *t_src = p.tab + (size_t)n_block * (kFrame / kKC) * kStageFloats;
 
-    // producer step, executed by warp 0 only: fill ring slot `s % kRing` with stage s
+    // producer step, executed by lane 0 of warp 0: fill ring slot `s % kRing` with stage s
     auto issue = [&](int s) {
         const int slot = s % kRing;
-        if (s >= kRing)
+        if (lane == 0)
         {
             // the (s/kRing)-th refill waits for the (s/kRing - 1)-th release of this slot
-            if (lane == 0)
+            if (s >= kRing)
                 mbar_wait(&sm.empty[slot], (uint32_t)((s / kRing) - 1) & 1u);
-            __syncwarp();
+            mbar_expect_tx(&sm.full[slot], 2 * kStageBytes);
+            bulk_g2s(sm.a[slot], a_src + (size_t)s * kStageFloats, kStageBytes, &sm.full[slot]);
+            bulk_g2s(sm.t[slot], t_src + (size_t)s * kStageFloats, kStageBytes, &sm.full[slot]);
         }
-        if (MODE == 0)
-        {
-            if (lane == 0)
-            {
-                mbar_expect_tx(&sm.full[slot], 2 * kStageBytes);
-                bulk_g2s(sm.a[slot], a_src + (size_t)s * kStageFloats, kStageBytes, &sm.full[slot]);
-                bulk_g2s(sm.t[slot], t_src + (size_t)s * kStageFloats, kStageBytes, &sm.full[slot]);
-            }
-        }
-        else
-        {
-            const uint32_t k = __ldg(kl + s * kKC + lane);
-            if (lane == 0)
-            {
-                mbar_expect_tx(&sm.full[slot], 2 * kStageBytes);
-                bulk_g2s(sm.a[slot], a_src + (size_t)s * kStageFloats, kStageBytes, &sm.full[slot]);
-            }
-            __syncwarp();
-            bulk_g2s(sm.t[slot] + lane * kBN, t_src + (size_t)k * kFrame, kBN * 4, &sm.full[slot]);
-        }
+        __syncwarp();
     };
 
     if (warp == 0)
     {
-        if (n_stages > 0)
-            issue(0);
-        if (n_stages > 1)
-            issue(1);
+        issue(0);
+        issue(1);
     }
 
     float acc[8][8];
@@ -230,15 +200,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
             mbar_arrive(&sm.empty[slot]);
     }
 
-    // ---- epilogue: * norm (and * window for IMDCT), 2 x float4 per row ----
+    // ---- epilogue: * norm, two float4 stores per row ----
     const int n_lo = n_block * kBN + tx * 4;
     const int n_hi = n_lo + 64;
-    float4 w_lo = make_float4(1.f, 1.f, 1.f, 1.f), w_hi = w_lo;
-    if (MODE == 1)
-    {
-        w_lo = __ldg(reinterpret_cast<const float4 *>(p.window + n_lo));
-        w_hi = __ldg(reinterpret_cast<const float4 *>(p.window + n_hi));
-    }
     const uint64_t row0 = m_tile * kBM + ty * 8;
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -250,44 +214,211 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             v[c] = __fmul_rn(acc[r][c], p.norm);
-        if (MODE == 1)
-        {
-            v[0] = __fmul_rn(v[0], w_lo.x);
-            v[1] = __fmul_rn(v[1], w_lo.y);
-            v[2] = __fmul_rn(v[2], w_lo.z);
-            v[3] = __fmul_rn(v[3], w_lo.w);
-            v[4] = __fmul_rn(v[4], w_hi.x);
-            v[5] = __fmul_rn(v[5], w_hi.y);
-            v[6] = __fmul_rn(v[6], w_hi.z);
-            v[7] = __fmul_rn(v[7], w_hi.w);
-        }
-        float *orow = p.out + row * kNOut;
+        float *orow = p.out + row * kHop;
         *reinterpret_cast<float4 *>(orow + n_lo) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4 *>(orow + n_hi) = make_float4(v[4], v[5], v[6], v[7]);
     }
 }
 
-template <int MODE>
 cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
 {
     static bool configured = false;
     const size_t smem = sizeof(Smem);
     if (!configured)
     {
-        cudaError_t e =
-            cudaFuncSetAttribute(exact_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(exact_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
         configured = true;
     }
     if (m_tiles == 0)
         return cudaSuccess;
-    constexpr int kNBlocks = (MODE == 0 ? kHop : kFrame) / kBN;
-    const uint64_t n_ctas = m_tiles * kNBlocks;
+    const uint64_t n_ctas = m_tiles * (kHop / kBN);
     if (n_ctas > 0x7fffffffull)
         return cudaErrorInvalidValue;
-    exact_gemm_kernel<MODE><<<(unsigned)n_ctas, kGemmThreads, smem, s>>>(p);
+    exact_gemm_kernel<<<(unsigned)n_ctas, kGemmThreads, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// imdct_sparse_kernel: direct IMDCT (src/codec.rs:377-390) + synthesis window (:672-675) over the
+// compacted rows of a decode wave.
+//   CTA  = 128 rows x 256 outputs, 16 warps, one CTA per SM (128 registers);
+//   warp = 8 rows x 256 outputs (thread: 8 rows x 2 float4 of outputs), so a reduction step is needed
+//          by the whole warp or by none of it: the warp walks the set bits of its step mask and the
+//          branch is uniform.  On the bench workload the union of 128 rows holds ~945 of the 1024
+//          indices while a row holds ~258; 8 rows hold ~560, which is the work that is left.
+//   ring = 4 slots of {A stage 16 448 B (values + masks), T stage 32 KiB}, full/empty mbarriers, both
+//          operands by cp.async.bulk; a warp that has nothing to do in a stage releases it at once, the
+//          warps may drift up to 4 stages apart, and a slot is refilled by the last warp that leaves it.
+constexpr int kImdctRing = 4;
+struct ImdctSmem
+{
+    float a[kImdctRing][kImdctAStageFloats];
+    float t[kImdctRing][kKC * kImdctBN];
+    uint64_t full[kImdctRing];
+    uint64_t empty[kImdctRing];
+    uint32_t released[kImdctRing]; // consumer warps that have left the slot (running count)
+    uint16_t klist[kHop];          // the tile's reduction list
+};
+static_assert((kImdctAStageFloats * 4) % 16 == 0, "bulk copies need 16-byte granularity");
+
+__global__ void __launch_bounds__(kImdctThreads, 1) imdct_sparse_kernel(const __grid_constant__ GemmParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ImdctSmem &sm = *reinterpret_cast<ImdctSmem *>(smem_raw);
+    constexpr int kNBlocks = kFrame / kImdctBN;
+    constexpr uint32_t kTxBytes = kImdctAStageFloats * 4 + kKC * kImdctBN * 4;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    // linear grid, output block fastest: the CTAs that run together share A tiles in L2
+    const int n_block = (int)(blockIdx.x % kNBlocks);
+    const uint64_t m_tile = p.tile_begin + blockIdx.x / kNBlocks;
+    if (m_tile >= (uint64_t)__ldg(p.n_tiles))
+        return;
+    const int n_stages = (int)(__ldg(p.n_k + m_tile) / kKC);
+
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < kImdctRing; ++s)
+        {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kImdctWarps);
+            sm.released[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.klist + (size_t)m_tile * kHop);
+        for (int e = tid; e < n_stages * (kKC / 2); e += kImdctThreads)
+            reinterpret_cast<uint32_t *>(sm.klist)[e] = __ldg(src + e);
+    }
+    __syncthreads();
+
+    const float *a_src = p.a_tiles + (size_t)m_tile * kImdctATileFloats;
+    const float *t_src = p.tab + (size_t)n_block * kImdctBN;
+
+    // Fill ring slot `s % ring` with stage s; executed by one whole warp.  There is no producer warp:
+    // the first `ring` stages are issued by warp 0, and stage s + ring is issued by whichever warp is the
+    // LAST to leave stage s, i.e. at the moment the slot becomes free, by the only warp that nobody is
+    // waiting for any more.
+    auto issue = [&](int s) {
+        const int slot = s % kImdctRing;
+        const uint32_t k = sm.klist[s * kKC + lane];
+        if (lane == 0)
+        {
+            mbar_expect_tx(&sm.full[slot], kTxBytes);
+            bulk_g2s(sm.a[slot], a_src + (size_t)s * kImdctAStageFloats, kImdctAStageFloats * 4, &sm.full[slot]);
+        }
+        __syncwarp();
+        bulk_g2s(sm.t[slot] + lane * kImdctBN, t_src + (size_t)k * kFrame, kImdctBN * 4, &sm.full[slot]);
+    };
+
+    if (warp == 0)
+        for (int s = 0; s < kImdctRing && s < n_stages; ++s)
+            issue(s);
+
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            acc[r][c] = 0.0f;
+
+    for (int s = 0; s < n_stages; ++s)
+    {
+        const int slot = s % kImdctRing;
+        mbar_wait(&sm.full[slot], (uint32_t)(s / kImdctRing) & 1u);
+
+        // bit-reversed step mask: the next step in ascending order is clz(rm)
+        uint32_t rm = __brev(reinterpret_cast<const uint32_t *>(sm.a[slot] + kKC * kBM)[warp]);
+        const float *As = sm.a[slot] + warp * kImdctRowsPerWarp;
+        const float *Ts = sm.t[slot] + lane * 4;
+        // Software pipeline: the operands of the next selected step are loaded BEFORE the 128 FMUL/FADD of
+        // the current one are issued (the empty asm statements pin that order), so that the find-bit ->
+        // address -> LDS latency chain is covered by the warp's own arithmetic and a warp that runs alone
+        // on its scheduler (the slowest of a stage, which the others are waiting for) runs at full rate.
+        // When no step is left the loads fetch step 0 again, which is harmless and keeps the loop free of
+        // divergence bookkeeping.
+        float4 na_lo, na_hi, nt_lo, nt_hi;
+        bool have = rm != 0;
+        {
+            const int ii = have ? __clz((int)rm) : 0;
+            rm &= ~(0x80000000u >> ii);
+            na_lo = *reinterpret_cast<const float4 *>(As + ii * kBM);
+            na_hi = *reinterpret_cast<const float4 *>(As + ii * kBM + 4);
+            nt_lo = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN);
+            nt_hi = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN + 128);
+        }
+        while (have)
+        {
+            const float a[8] = {na_lo.x, na_lo.y, na_lo.z, na_lo.w, na_hi.x, na_hi.y, na_hi.z, na_hi.w};
+            const float t[8] = {nt_lo.x, nt_lo.y, nt_lo.z, nt_lo.w, nt_hi.x, nt_hi.y, nt_hi.z, nt_hi.w};
+            have = rm != 0;
+            {
+                const int ii = have ? __clz((int)rm) : 0;
+                rm &= ~(0x80000000u >> ii);
+                asm volatile("" ::: "memory");
+                na_lo = *reinterpret_cast<const float4 *>(As + ii * kBM);
+                na_hi = *reinterpret_cast<const float4 *>(As + ii * kBM + 4);
+                nt_lo = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN);
+                nt_hi = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN + 128);
+                asm volatile("" ::: "memory");
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
+        }
+        __syncwarp();
+        uint32_t nth = 0;
+        if (lane == 0)
+        {
+            mbar_arrive(&sm.empty[slot]);
+            nth = atomicAdd(&sm.released[slot], 1u);
+        }
+        nth = __shfl_sync(0xffffffffu, nth, 0);
+        if (nth % kImdctWarps == kImdctWarps - 1 && s + kImdctRing < n_stages)
+        {
+            // last warp out: every arrival on `empty` precedes its own count, so this wait returns at once
+            // and orders the other warps' reads of the slot before the refill
+            mbar_wait(&sm.empty[slot], (uint32_t)(s / kImdctRing) & 1u);
+            issue(s + kImdctRing);
+        }
+    }
+
+    // ---- epilogue: * norm, * window, 2 x float4 per row (a warp writes 2 x 512 contiguous bytes) ----
+    const int n_lo = n_block * kImdctBN + lane * 4;
+    const int n_hi = n_lo + 128;
+    const float4 w_lo = __ldg(reinterpret_cast<const float4 *>(p.window + n_lo));
+    const float4 w_hi = __ldg(reinterpret_cast<const float4 *>(p.window + n_hi));
+    const uint64_t row0 = m_tile * kBM + warp * kImdctRowsPerWarp;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+    {
+        const uint64_t row = row0 + r;
+        if (row >= p.n_rows)
+            continue;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            v[c] = __fmul_rn(acc[r][c], p.norm);
+        v[0] = __fmul_rn(v[0], w_lo.x);
+        v[1] = __fmul_rn(v[1], w_lo.y);
+        v[2] = __fmul_rn(v[2], w_lo.z);
+        v[3] = __fmul_rn(v[3], w_lo.w);
+        v[4] = __fmul_rn(v[4], w_hi.x);
+        v[5] = __fmul_rn(v[5], w_hi.y);
+        v[6] = __fmul_rn(v[6], w_hi.z);
+        v[7] = __fmul_rn(v[7], w_hi.w);
+        float *orow = p.out + row * kFrame;
+        *reinterpret_cast<float4 *>(orow + n_lo) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(orow + n_hi) = make_float4(v[4], v[5], v[6], v[7]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -401,7 +532,7 @@ cudaError_t launch_mdct_exact(const MdctLaunch &l, cudaStream_t s)
     p.n_rows = l.row_end - l.row_begin;
     p.norm = l.norm;
     p.out = l.coefs + l.row_begin * kHop; // rows of this launch are numbered from 0 inside the kernel
-    return launch_gemm<0>(p, m_tiles, s);
+    return launch_gemm(p, m_tiles, s);
 }
 
 cudaError_t launch_imdct_exact(const ImdctLaunch &l, cudaStream_t s)
@@ -417,7 +548,23 @@ cudaError_t launch_imdct_exact(const ImdctLaunch &l, cudaStream_t s)
     p.n_rows = l.max_slots;
     p.norm = l.norm;
     p.out = l.blocks;
-    return launch_gemm<1>(p, (l.max_slots + kBM - 1) / kBM, s);
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaError_t e = cudaFuncSetAttribute(imdct_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(ImdctSmem));
+        if (e != cudaSuccess)
+            return e;
+        configured = true;
+    }
+    const uint64_t m_tiles = (l.max_slots + kBM - 1) / kBM;
+    if (m_tiles == 0)
+        return cudaSuccess;
+    const uint64_t n_ctas = m_tiles * (kFrame / kImdctBN);
+    if (n_ctas > 0x7fffffffull)
+        return cudaErrorInvalidValue;
+    imdct_sparse_kernel<<<(unsigned)n_ctas, kImdctThreads, sizeof(ImdctSmem), s>>>(p);
+    return cudaGetLastError();
 }
 
 } // namespace glc

@@ -21,6 +21,14 @@ constexpr int kBM = 128;     // frame-channels (rows) per CTA tile
 constexpr int kBN = 128;     // outputs per CTA tile (coefficients for MDCT, samples for IMDCT)
 constexpr int kKC = 32;      // reduction steps per pipeline stage
 constexpr int kGemmThreads = 256;
+// IMDCT (warp-sparse variant): a warp owns kImdctRowsPerWarp rows of the tile and all kImdctBN outputs
+// of the CTA; one A stage carries, after its [kKC][kBM] values, one 32-bit step mask per warp.
+constexpr int kImdctBN = 256;
+constexpr int kImdctRowsPerWarp = 8;
+constexpr int kImdctWarps = kBM / kImdctRowsPerWarp;        // 16
+constexpr int kImdctThreads = kImdctWarps * 32;             // 512
+constexpr int kImdctAStageFloats = kKC * kBM + kImdctWarps; // 4096 values + 16 masks = 16 448 B
+constexpr size_t kImdctATileFloats = (size_t)(kHop / kKC) * kImdctAStageFloats;
 
 // One input file inside a batched encode (device copy lives in FileTable::d_files).
 struct FileDesc
@@ -92,7 +100,7 @@ cudaError_t launch_mdct_exact(const MdctLaunch &p, cudaStream_t s);   // a_tiles
 
 struct ImdctLaunch
 {
-    const float *a_tiles;    // [tile][stage][kKC][kBM] compacted dequantised coefficients (dequant_tile_kernel)
+    const float *a_tiles;    // [tile][stage]{[kKC][kBM] compacted dequantised coefficients, [kImdctWarps] step masks}
     const uint16_t *klist;   // [tile][1024]
     const uint32_t *n_k;     // [tile] reduction length (multiple of kKC)
     const uint32_t *n_tiles; // device-side number of live tiles
@@ -165,7 +173,7 @@ struct DequantLaunch
     uint32_t *n_tiles;        // [1]
     uint16_t *klist;          // [max_tiles][1024]
     uint32_t *n_k;            // [max_tiles]
-    float *a_tiles;           // [max_tiles][1024][kBM]
+    float *a_tiles;           // [max_tiles][kImdctATileFloats]
 };
 cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s); // flags -> scan -> scatter -> tiles
 
