@@ -396,9 +396,9 @@ extern "C" glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out)
     CUDA_TRY(cudaMalloc(&c->d_window, sizeof(float) * kFrame));
     tile_table_for_mdct(c->host.cos_tab, tiled);
     CUDA_TRY(cudaMemcpy(c->d_tab_mdct, tiled, tab_bytes, cudaMemcpyHostToDevice));
+    tile_table_for_imdct(c->host.cos_tab, tiled);
+    CUDA_TRY(cudaMemcpy(c->d_tab_imdct, tiled, tab_bytes, cudaMemcpyHostToDevice));
     free(tiled);
-    // the IMDCT gathers rows k of the reference layout tab[k][i] directly
-    CUDA_TRY(cudaMemcpy(c->d_tab_imdct, c->host.cos_tab, tab_bytes, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->d_window, c->host.window, sizeof(float) * kFrame, cudaMemcpyHostToDevice));
     {
         float tw[kFastTwiddleFloats];
@@ -1657,7 +1657,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     uint32_t *d_flags = nullptr, *d_active = nullptr, *d_ntiles = nullptr, *d_nk = nullptr;
     uint64_t *d_slot_off = nullptr;
     int32_t *d_row_slot = nullptr;
-    uint16_t *d_klist = nullptr;
+    uint8_t *d_stage_list = nullptr;
     PhaseTrace tr("decode", cs);
 
     uint64_t target_rows = kRowQuantum * (io ? 4 : 32);
@@ -1665,7 +1665,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         target_rows = std::max<uint64_t>(c->wave_frames, 1);
     uint64_t max_wave_rows = 0;
     const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows);
-    const uint64_t wave_tiles = (max_wave_rows + kBM - 1) / kBM;
+    const uint64_t wave_tiles = (max_wave_rows + kImdctBM - 1) / kImdctBM;
 
     CUDA_TRY(dmalloc(&d_files, n_files, cs));
     CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(DecFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
@@ -1681,7 +1681,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     CUDA_TRY(dmalloc(&d_active, max_wave_rows, cs));
     CUDA_TRY(dmalloc(&d_ntiles, 1, cs));
     CUDA_TRY(dmalloc(&d_nk, wave_tiles, cs));
-    CUDA_TRY(dmalloc(&d_klist, wave_tiles * kHop, cs));
+    CUDA_TRY(dmalloc(&d_stage_list, wave_tiles * kImdctStages, cs));
     CUDA_TRY(dmalloc(&d_out, total_out, cs));
     tr.mark("alloc");
 
@@ -1804,8 +1804,8 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             q.slot_off = d_slot_off;
             q.active_rows = d_active;
             q.n_tiles = d_ntiles;
-            q.klist = d_klist;
-            q.n_k = d_nk;
+            q.stage_list = d_stage_list;
+            q.n_stages = d_nk;
             q.a_tiles = d_atiles;
             CUDA_TRY(launch_dequant(q, cs));
         }
@@ -1814,10 +1814,10 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             LaunchScope ls(c, GLC_K_IMDCT_EXACT, cs);
             ImdctLaunch m{};
             m.a_tiles = d_atiles;
-            m.klist = d_klist;
-            m.n_k = d_nk;
+            m.stage_list = d_stage_list;
+            m.n_stages = d_nk;
             m.n_tiles = d_ntiles;
-            m.max_slots = (w.r1 - w.r0 + kBM - 1) / kBM * kBM;
+            m.max_slots = (w.r1 - w.r0 + kImdctBM - 1) / kImdctBM * kImdctBM;
             m.tab = c->d_tab_imdct;
             m.window = c->d_window;
             m.norm = c->host.norm;
@@ -1876,7 +1876,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     dfree(d_active, cs);
     dfree(d_ntiles, cs);
     dfree(d_nk, cs);
-    dfree(d_klist, cs);
+    dfree(d_stage_list, cs);
     dfree(d_files, cs);
     tr.mark("free");
     *d_out_ret = d_out;

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const DequantLaunch p)
     const uint64_t local = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t row = p.row_begin + local;
     if (local == 0)
-        *p.n_tiles = (uint32_t)((p.slot_off[p.row_end - p.row_begin] + kBM - 1) / kBM);
+        *p.n_tiles = (uint32_t)((p.slot_off[p.row_end - p.row_begin] + kImdctBM - 1) / kImdctBM);
     if (row >= p.row_end)
         return;
     if (p.flags[local])
@@ -347,34 +347,31 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const DequantLaunch p)
         p.row_slot[row] = -1;
 }
 
-// One CTA per tile of kBM compacted rows: union of the coefficient indices present in the tile
-// (ascending), then the dequantised values (src/codec.rs:651-665) laid out as the A operand of the
-// IMDCT over that union only: per stage [kKC][kBM] values followed by one step mask per warp of the
-// IMDCT kernel (bit b of mask g = "one of rows 8g..8g+7 has a coefficient at step b of this stage").
+// One CTA per tile of kImdctBM compacted rows: the A operand of the IMDCT.  The coefficient axis is cut
+// into kImdctStages stages of kImdctKC consecutive indices; per stage the tile stores the dequantised
+// values (src/codec.rs:651-665) as [kImdctKC][kImdctBM] followed by one step mask per warp of the IMDCT
+// kernel (bit b of mask g = "a row of group g has a pair at index stage*kImdctKC + b").  Stages in
+// which no row of the tile has a pair are neither written nor listed in stage_list.
 __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p)
 {
-    __shared__ uint32_t s_bits[kHop / 32];
-    __shared__ uint32_t s_gbits[kImdctWarps][kHop / 32]; // per 8-row group
-    __shared__ uint32_t s_prefix[kHop / 32];
-    __shared__ uint32_t s_nk;
+    __shared__ uint32_t s_gbits[kImdctWarps][kHop / 32]; // index sets per 8-row group
+    __shared__ uint32_t s_present[kImdctStages];         // OR of the group masks per stage
     const uint64_t n_active = p.slot_off[p.row_end - p.row_begin];
     const uint64_t tile = blockIdx.x;
-    if (tile * kBM >= n_active)
+    if (tile * kImdctBM >= n_active)
         return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t rows_here = (uint32_t)min((uint64_t)kBM, n_active - tile * kBM);
-    if (tid < kHop / 32)
-        s_bits[tid] = 0;
+    const uint32_t rows_here = (uint32_t)min((uint64_t)kImdctBM, n_active - tile * kImdctBM);
     for (int e = tid; e < kImdctWarps * (kHop / 32); e += 256)
         (&s_gbits[0][0])[e] = 0;
     __syncthreads();
 
-    // pass 1: index union (any pair with idx < 1024 counts, also ones a later duplicate overwrites).
+    // pass 1: index sets (any pair with idx < 1024 counts, also ones a later duplicate overwrites).
     // Each lane walks a contiguous chunk of the row's pairs and merges bits of the same 32-bin word
     // before touching shared memory: ascending indices would otherwise make all 32 lanes hit one word.
     for (uint32_t r = warp; r < rows_here; r += 8)
     {
-        const uint64_t row = p.active_rows[tile * kBM + r];
+        const uint64_t row = p.active_rows[tile * kImdctBM + r];
         const uint64_t b = p.pair_off[row];
         const uint32_t n = (uint32_t)(p.pair_off[row + 1] - b);
         const uint32_t chunk = (n + 31) / 32;
@@ -390,62 +387,73 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
             if (w != cur)
             {
                 if (mask)
-                {
-                    atomicOr(&s_bits[cur], mask);
                     atomicOr(&gb[cur], mask);
-                }
                 cur = w;
                 mask = 0;
             }
             mask |= 1u << (idx & 31);
         }
         if (mask)
-        {
-            atomicOr(&s_bits[cur], mask);
             atomicOr(&gb[cur], mask);
+    }
+    __syncthreads();
+
+    // step masks and the list of stages that are present
+    float *a = p.a_tiles + tile * kImdctATileFloats;
+    static_assert(32 % kImdctKC == 0, "a stage must not straddle a 32-bit word of the index sets");
+    if (tid < kImdctStages)
+    {
+        const uint32_t st = tid;
+        uint32_t any = 0;
+        uint32_t *masks = reinterpret_cast<uint32_t *>(a + (size_t)st * kImdctAStageFloats + kImdctKC * kImdctBM);
+        uint32_t mm[kImdctWarps];
+#pragma unroll
+        for (int g = 0; g < kImdctWarps; ++g)
+        {
+            mm[g] = (s_gbits[g][(st * kImdctKC) >> 5] >> ((st * kImdctKC) & 31)) & ((1u << kImdctKC) - 1u);
+            any |= mm[g];
+#if defined(GLC_EXPERIMENT_NO_STEPS) // timing experiment: the pipeline alone (results are wrong)
+            mm[g] = 0;
+#elif defined(GLC_EXPERIMENT_DENSE_MASKS) // timing experiment: every warp executes every step
+            mm[g] = (1u << kImdctKC) - 1u;
+#endif
         }
+        s_present[st] = any;
+        if (any)
+#pragma unroll
+            for (int g = 0; g < kImdctWarps; ++g)
+                masks[g] = mm[g];
     }
     __syncthreads();
     if (warp == 0)
     {
-        const uint32_t c = __popc(s_bits[lane]);
-        uint32_t incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
+        // ordered compaction of the present stages (2 per lane)
+        uint8_t *sl = p.stage_list + tile * kImdctStages;
+        uint32_t total = 0;
+        for (int base = 0; base < kImdctStages; base += 32)
         {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += t;
+            const bool pr = s_present[base + lane] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, pr);
+            if (pr)
+                sl[total + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)(base + lane);
+            total += __popc(bal);
         }
-        s_prefix[lane] = incl - c;
-        if (lane == 31)
-            s_nk = incl;
+        if (lane == 0)
+            p.n_stages[tile] = total;
+    }
+
+    // pass 2: zero the values of the present stages, then scatter
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t e = tid; e < (uint32_t)kImdctStages * (kImdctKC * kImdctBM / 4); e += 256)
+    {
+        const uint32_t st = e / (kImdctKC * kImdctBM / 4), o = e % (kImdctKC * kImdctBM / 4);
+        if (s_present[st])
+            reinterpret_cast<float4 *>(a + (size_t)st * kImdctAStageFloats)[o] = z;
     }
     __syncthreads();
-    const uint32_t nk = s_nk;
-    const uint32_t nk_pad = (nk + kKC - 1) / kKC * kKC;
-    const uint32_t n_stages = nk_pad / kKC;
-    uint16_t *kl = p.klist + tile * kHop;
-    for (uint32_t k = tid; k < kHop; k += 256)
-    {
-        const uint32_t w = s_bits[k >> 5];
-        if ((w >> (k & 31)) & 1u)
-            kl[s_prefix[k >> 5] + __popc(w & ((1u << (k & 31)) - 1u))] = (uint16_t)k;
-    }
-    for (uint32_t j = nk + tid; j < nk_pad; j += 256)
-        kl[j] = 0; // padding steps: no warp's mask selects them (and their A column is all zero)
-    if (tid == 0)
-        p.n_k[tile] = nk_pad;
-
-    // pass 2: zero the tile's A region (values and masks), then scatter the values
-    float *a = p.a_tiles + tile * kImdctATileFloats;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t e = tid; e < n_stages * (kImdctAStageFloats / 4); e += 256)
-        reinterpret_cast<float4 *>(a)[e] = z;
-    __syncthreads(); // also makes kl[] visible to the mask pass below
     for (uint32_t r = warp; r < rows_here; r += 8)
     {
-        const uint64_t row = p.active_rows[tile * kBM + r];
+        const uint64_t row = p.active_rows[tile * kImdctBM + r];
         const uint64_t b = p.pair_off[row];
         const uint32_t n = (uint32_t)(p.pair_off[row + 1] - b);
         const glc_pair *pr = p.pairs + b;
@@ -459,12 +467,8 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         auto put = [&](uint32_t j) {
             const glc_pair q = pr[j];
             if (q.idx < kHop)
-            {
-                const uint32_t w = s_bits[q.idx >> 5];
-                const uint32_t pos = s_prefix[q.idx >> 5] + __popc(w & ((1u << (q.idx & 31)) - 1u));
-                a[(size_t)(pos / kKC) * kImdctAStageFloats + (pos % kKC) * kBM + r] =
+                a[(size_t)(q.idx / kImdctKC) * kImdctAStageFloats + (q.idx % kImdctKC) * kImdctBM + r] =
                     __fmul_rn(__fdiv_rn((float)q.q, 32768.0f), scale);
-            }
         };
         if (ascending)
             for (uint32_t j = lane; j < n; j += 32)
@@ -472,23 +476,6 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         else if (lane == 0)
             for (uint32_t j = 0; j < n; ++j)
                 put(j);
-    }
-    // step masks: presence of the index in the group's rows (a present pair whose value happens to be
-    // zero is simply not skipped, which is exact as well)
-    for (uint32_t e = tid; e < n_stages * kImdctWarps; e += 256)
-    {
-        const uint32_t st = e / kImdctWarps, g = e % kImdctWarps;
-        uint32_t m = 0;
-        for (uint32_t bpos = 0; bpos < (uint32_t)kKC; ++bpos)
-        {
-            const uint32_t pos = st * kKC + bpos;
-            if (pos < nk)
-            {
-                const uint32_t k = kl[pos];
-                m |= ((s_gbits[g][k >> 5] >> (k & 31)) & 1u) << bpos;
-            }
-        }
-        reinterpret_cast<uint32_t *>(a + (size_t)st * kImdctAStageFloats + kKC * kBM)[g] = m;
     }
 }
 
@@ -728,7 +715,7 @@ cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s)
     row_flag_kernel<<<grid, 256, 0, s>>>(p);
     scan_kernel<<<1, kScanThreads, 0, s>>>(p.flags, p.slot_off, n, nullptr);
     row_scatter_kernel<<<grid, 256, 0, s>>>(p);
-    dequant_tile_kernel<<<(unsigned)((n + kBM - 1) / kBM), 256, 0, s>>>(p);
+    dequant_tile_kernel<<<(unsigned)((n + kImdctBM - 1) / kImdctBM), 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

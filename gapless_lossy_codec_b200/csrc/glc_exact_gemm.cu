@@ -21,13 +21,10 @@
 //         window multiply, i.e. block[i]), one contiguous 16 KiB block per (row tile, stage); T comes
 //         from a host re-tiled copy of the table, also one contiguous block per (output block, stage).
 //   * IMDCT (imdct_sparse_kernel below) keeps the ring and the TMA feed but is SPARSE at warp
-//     granularity: the reduction runs over the ascending UNION of the coefficient indices present in
-//     the 128 rows of the tile (dequant_tile_kernel builds the list and the compacted A tiles), and
-//     every warp owns 8 rows and executes only the steps at which one of ITS rows has a coefficient
-//     (a 32-bit mask per warp and stage, delivered with the A stage).  Skipping a k whose coefficient
-//     is zero in a row is exact: the product is +-0 and the running sum (which starts at +0.0 and can
-//     never become -0) is unchanged.  T rows are gathered from the natural-layout table: 32 bulk
-//     copies of 1 KiB per stage, one per lane of warp 0.
+//     granularity: a warp owns 4 rows and executes only the reduction steps at which one of ITS rows
+//     has a coefficient (a step mask per warp and stage, delivered with the A stage).  Skipping a k
+//     whose coefficient is zero in a row is exact: the product is +-0 and the running sum (which starts
+//     at +0.0 and can never become -0) is unchanged.
 //   * Epilogue: * norm (and * window for IMDCT), two float4 stores per row.
 #include "glc_internal.cuh"
 
@@ -94,8 +91,8 @@ struct GemmParams
     const float *a_tiles;    // [m_tile][stage][kKC][kBM]
     const float *tab;        // MDCT: re-tiled [n_block][stage][kKC][kBN]; IMDCT: natural [1024][2048]
     const float *window;     // IMDCT epilogue
-    const uint16_t *klist;   // IMDCT: [m_tile][1024] ascending k of the tile's union (padded with 0)
-    const uint32_t *n_k;     // IMDCT: [m_tile] reduction length, multiple of kKC (0 = nothing to do)
+    const uint8_t *stage_list; // IMDCT: [m_tile][kImdctStages] ascending stages that hold a coefficient
+    const uint32_t *n_k;     // IMDCT: [m_tile] number of listed stages (0 = nothing to do)
     const uint32_t *n_tiles; // IMDCT: device-side count of live row tiles (grid is sized for the worst case)
     uint64_t tile_begin;     // first row tile of this launch
     uint64_t n_rows;         // rows (MDCT: frame-channels; IMDCT: compacted slots) that exist; stores are clipped
@@ -243,32 +240,39 @@ cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
 // ---------------------------------------------------------------------------------------------
 // imdct_sparse_kernel: direct IMDCT (src/codec.rs:377-390) + synthesis window (:672-675) over the
 // compacted rows of a decode wave.
-//   CTA  = 128 rows x 256 outputs, 16 warps, one CTA per SM (128 registers);
-//   warp = 8 rows x 256 outputs (thread: 8 rows x 2 float4 of outputs), so a reduction step is needed
-//          by the whole warp or by none of it: the warp walks the set bits of its step mask and the
-//          branch is uniform.  On the bench workload the union of 128 rows holds ~945 of the 1024
-//          indices while a row holds ~258; 8 rows hold ~560, which is the work that is left.
-//   ring = 4 slots of {A stage 16 448 B (values + masks), T stage 32 KiB}, full/empty mbarriers, both
-//          operands by cp.async.bulk; a warp that has nothing to do in a stage releases it at once, the
-//          warps may drift up to 4 stages apart, and a slot is refilled by the last warp that leaves it.
-constexpr int kImdctRing = 4;
+//   CTA   = 32 rows x 256 outputs, 8 warps, 62 registers: 4 CTAs = 32 warps per SM.
+//   warp  = 4 rows x 256 outputs (thread: 4 rows x 2 float4 of outputs), so a reduction step is needed
+//           by the whole warp or by none of it: the warp walks the set bits of its step mask and the
+//           branch is uniform.  On the bench workload a row holds ~258 of the 1024 indices, the union of
+//           4 rows ~446, of 8 rows ~560, of 128 rows ~945 (the dense contraction of the first version).
+//   stage = 16 consecutive coefficient indices: A = [16][32 rows] values + 8 masks (2 080 B) written by
+//           dequant_tile_kernel, T = 16 rows x 256 outputs of the table, contiguous in the re-tiled copy
+//           (tile_table_for_imdct): two bulk copies per stage.  Stages in which the tile has no
+//           coefficient at all are not listed and never loaded.
+//   ring  = 3 slots, full/empty mbarriers; a warp with nothing to do in a stage releases it at once;
+//           there is no producer warp: a slot is refilled by the last warp that leaves it.
+// Measured on the hour-long bench signal: 26.5 ms (dense over the 128-row union) -> 16.2 ms.  What is
+// left is the per-step bookkeeping (13 of 77 instructions) and warps of one CTA waiting for each
+// other at the ring (issue slots 86 % busy); with every mask forced to all-ones the same kernel runs
+// at the full issue rate, i.e. the pipeline itself is not the limit.
+constexpr int kImdctRing = 3;
 struct ImdctSmem
 {
     float a[kImdctRing][kImdctAStageFloats];
-    float t[kImdctRing][kKC * kImdctBN];
+    float t[kImdctRing][kImdctKC * kImdctBN];
     uint64_t full[kImdctRing];
     uint64_t empty[kImdctRing];
     uint32_t released[kImdctRing]; // consumer warps that have left the slot (running count)
-    uint16_t klist[kHop];          // the tile's reduction list
+    uint8_t stage_list[kImdctStages]; // the tile's stages
 };
 static_assert((kImdctAStageFloats * 4) % 16 == 0, "bulk copies need 16-byte granularity");
 
-__global__ void __launch_bounds__(kImdctThreads, 1) imdct_sparse_kernel(const __grid_constant__ GemmParams p)
+__global__ void __launch_bounds__(kImdctThreads, 4) imdct_sparse_kernel(const __grid_constant__ GemmParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ImdctSmem &sm = *reinterpret_cast<ImdctSmem *>(smem_raw);
     constexpr int kNBlocks = kFrame / kImdctBN;
-    constexpr uint32_t kTxBytes = kImdctAStageFloats * 4 + kKC * kImdctBN * 4;
+    constexpr uint32_t kTxBytes = kImdctAStageFloats * 4 + kImdctKC * kImdctBN * 4;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(kImdctThreads, 1) imdct_sparse_kernel(const __
     const uint64_t m_tile = p.tile_begin + blockIdx.x / kNBlocks;
     if (m_tile >= (uint64_t)__ldg(p.n_tiles))
         return;
-    const int n_stages = (int)(__ldg(p.n_k + m_tile) / kKC);
+    const int n_stages = (int)__ldg(p.n_k + m_tile);
 
     if (tid == 0)
     {
@@ -291,39 +295,37 @@ __global__ void __launch_bounds__(kImdctThreads, 1) imdct_sparse_kernel(const __
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.klist + (size_t)m_tile * kHop);
-        for (int e = tid; e < n_stages * (kKC / 2); e += kImdctThreads)
-            reinterpret_cast<uint32_t *>(sm.klist)[e] = __ldg(src + e);
-    }
+    if (tid < n_stages)
+        sm.stage_list[tid] = __ldg(p.stage_list + (size_t)m_tile * kImdctStages + tid);
     __syncthreads();
 
     const float *a_src = p.a_tiles + (size_t)m_tile * kImdctATileFloats;
-    const float *t_src = p.tab + (size_t)n_block * kImdctBN;
+    const float *t_src = p.tab + (size_t)n_block * kHop * kImdctBN;
 
-    // Fill ring slot `s % ring` with stage s; executed by one whole warp.  There is no producer warp:
-    // the first `ring` stages are issued by warp 0, and stage s + ring is issued by whichever warp is the
-    // LAST to leave stage s, i.e. at the moment the slot becomes free, by the only warp that nobody is
-    // waiting for any more.
-    auto issue = [&](int s) {
-        const int slot = s % kImdctRing;
-        const uint32_t k = sm.klist[s * kKC + lane];
+    // Fill ring slot `j % ring` with the j-th listed stage: two bulk copies (the table is re-tiled so that
+    // the kImdctKC rows of a stage are contiguous for every output block).  There is no producer warp:
+    // the first `ring` stages are issued by warp 0 and stage j + ring by whichever warp is the last to
+    // leave stage j, i.e. at the moment the slot becomes free.
+    auto issue = [&](int j) {
         if (lane == 0)
         {
+            const int slot = j % kImdctRing;
+            const uint32_t st = sm.stage_list[j];
             mbar_expect_tx(&sm.full[slot], kTxBytes);
-            bulk_g2s(sm.a[slot], a_src + (size_t)s * kImdctAStageFloats, kImdctAStageFloats * 4, &sm.full[slot]);
+            bulk_g2s(sm.a[slot], a_src + (size_t)st * kImdctAStageFloats, kImdctAStageFloats * 4, &sm.full[slot]);
+            bulk_g2s(sm.t[slot], t_src + (size_t)st * kImdctKC * kImdctBN, kImdctKC * kImdctBN * 4, &sm.full[slot]);
         }
         __syncwarp();
-        bulk_g2s(sm.t[slot] + lane * kImdctBN, t_src + (size_t)k * kFrame, kImdctBN * 4, &sm.full[slot]);
     };
 
     if (warp == 0)
         for (int s = 0; s < kImdctRing && s < n_stages; ++s)
             issue(s);
 
-    float acc[8][8];
+    constexpr int RW = kImdctRowsPerWarp;
+    float acc[RW][8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < RW; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             acc[r][c] = 0.0f;
@@ -334,42 +336,28 @@ __global__ void __launch_bounds__(kImdctThreads, 1) imdct_sparse_kernel(const __
         mbar_wait(&sm.full[slot], (uint32_t)(s / kImdctRing) & 1u);
 
         // bit-reversed step mask: the next step in ascending order is clz(rm)
-        uint32_t rm = __brev(reinterpret_cast<const uint32_t *>(sm.a[slot] + kKC * kBM)[warp]);
-        const float *As = sm.a[slot] + warp * kImdctRowsPerWarp;
+        uint32_t rm = __brev(reinterpret_cast<const uint32_t *>(sm.a[slot] + kImdctKC * kImdctBM)[warp]);
+        const float *As = sm.a[slot] + warp * RW;
         const float *Ts = sm.t[slot] + lane * 4;
-        // Software pipeline: the operands of the next selected step are loaded BEFORE the 128 FMUL/FADD of
-        // the current one are issued (the empty asm statements pin that order), so that the find-bit ->
-        // address -> LDS latency chain is covered by the warp's own arithmetic and a warp that runs alone
-        // on its scheduler (the slowest of a stage, which the others are waiting for) runs at full rate.
-        // When no step is left the loads fetch step 0 again, which is harmless and keeps the loop free of
-        // divergence bookkeeping.
-        float4 na_lo, na_hi, nt_lo, nt_hi;
-        bool have = rm != 0;
+        while (rm)
         {
-            const int ii = have ? __clz((int)rm) : 0;
+            const int ii = __clz((int)rm);
             rm &= ~(0x80000000u >> ii);
-            na_lo = *reinterpret_cast<const float4 *>(As + ii * kBM);
-            na_hi = *reinterpret_cast<const float4 *>(As + ii * kBM + 4);
-            nt_lo = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN);
-            nt_hi = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN + 128);
-        }
-        while (have)
-        {
-            const float a[8] = {na_lo.x, na_lo.y, na_lo.z, na_lo.w, na_hi.x, na_hi.y, na_hi.z, na_hi.w};
-            const float t[8] = {nt_lo.x, nt_lo.y, nt_lo.z, nt_lo.w, nt_hi.x, nt_hi.y, nt_hi.z, nt_hi.w};
-            have = rm != 0;
-            {
-                const int ii = have ? __clz((int)rm) : 0;
-                rm &= ~(0x80000000u >> ii);
-                asm volatile("" ::: "memory");
-                na_lo = *reinterpret_cast<const float4 *>(As + ii * kBM);
-                na_hi = *reinterpret_cast<const float4 *>(As + ii * kBM + 4);
-                nt_lo = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN);
-                nt_hi = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN + 128);
-                asm volatile("" ::: "memory");
-            }
+            float a[RW];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r4 = 0; r4 < RW / 4; ++r4)
+            {
+                const float4 v = *reinterpret_cast<const float4 *>(As + ii * kImdctBM + r4 * 4);
+                a[r4 * 4 + 0] = v.x;
+                a[r4 * 4 + 1] = v.y;
+                a[r4 * 4 + 2] = v.z;
+                a[r4 * 4 + 3] = v.w;
+            }
+            const float4 t_lo = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN);
+            const float4 t_hi = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN + 128);
+            const float t[8] = {t_lo.x, t_lo.y, t_lo.z, t_lo.w, t_hi.x, t_hi.y, t_hi.z, t_hi.w};
+#pragma unroll
+            for (int r = 0; r < RW; ++r)
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
@@ -396,9 +384,9 @@ __global__ void __launch_bounds__(kImdctThreads, 1) imdct_sparse_kernel(const __
     const int n_hi = n_lo + 128;
     const float4 w_lo = __ldg(reinterpret_cast<const float4 *>(p.window + n_lo));
     const float4 w_hi = __ldg(reinterpret_cast<const float4 *>(p.window + n_hi));
-    const uint64_t row0 = m_tile * kBM + warp * kImdctRowsPerWarp;
+    const uint64_t row0 = m_tile * kImdctBM + warp * RW;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < RW; ++r)
     {
         const uint64_t row = row0 + r;
         if (row >= p.n_rows)
@@ -541,8 +529,8 @@ cudaError_t launch_imdct_exact(const ImdctLaunch &l, cudaStream_t s)
     p.a_tiles = l.a_tiles;
     p.tab = l.tab;
     p.window = l.window;
-    p.klist = l.klist;
-    p.n_k = l.n_k;
+    p.stage_list = l.stage_list;
+    p.n_k = l.n_stages;
     p.n_tiles = l.n_tiles;
     p.tile_begin = 0;
     p.n_rows = l.max_slots;
@@ -557,7 +545,7 @@ cudaError_t launch_imdct_exact(const ImdctLaunch &l, cudaStream_t s)
             return e;
         configured = true;
     }
-    const uint64_t m_tiles = (l.max_slots + kBM - 1) / kBM;
+    const uint64_t m_tiles = (l.max_slots + kImdctBM - 1) / kImdctBM;
     if (m_tiles == 0)
         return cudaSuccess;
     const uint64_t n_ctas = m_tiles * (kFrame / kImdctBN);

@@ -21,14 +21,18 @@ constexpr int kBM = 128;     // frame-channels (rows) per CTA tile
 constexpr int kBN = 128;     // outputs per CTA tile (coefficients for MDCT, samples for IMDCT)
 constexpr int kKC = 32;      // reduction steps per pipeline stage
 constexpr int kGemmThreads = 256;
-// IMDCT (warp-sparse variant): a warp owns kImdctRowsPerWarp rows of the tile and all kImdctBN outputs
-// of the CTA; one A stage carries, after its [kKC][kBM] values, one 32-bit step mask per warp.
+// IMDCT (warp-sparse variant): tiles of kImdctBM compacted rows; a warp owns kImdctRowsPerWarp rows of
+// the tile and all kImdctBN outputs of the CTA; a pipeline stage is kImdctKC consecutive coefficient
+// indices and one A stage carries, after its [kImdctKC][kImdctBM] values, one step mask per warp.
+constexpr int kImdctBM = 32;
 constexpr int kImdctBN = 256;
-constexpr int kImdctRowsPerWarp = 8;
-constexpr int kImdctWarps = kBM / kImdctRowsPerWarp;        // 16
-constexpr int kImdctThreads = kImdctWarps * 32;             // 512
-constexpr int kImdctAStageFloats = kKC * kBM + kImdctWarps; // 4096 values + 16 masks = 16 448 B
-constexpr size_t kImdctATileFloats = (size_t)(kHop / kKC) * kImdctAStageFloats;
+constexpr int kImdctKC = 16;
+constexpr int kImdctStages = kHop / kImdctKC;                          // 64
+constexpr int kImdctRowsPerWarp = 4;
+constexpr int kImdctWarps = kImdctBM / kImdctRowsPerWarp;              // 8
+constexpr int kImdctThreads = kImdctWarps * 32;                        // 256
+constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctWarps;  // 512 values + 8 masks = 2 080 B
+constexpr size_t kImdctATileFloats = (size_t)kImdctStages * kImdctAStageFloats;
 
 // One input file inside a batched encode (device copy lives in FileTable::d_files).
 struct FileDesc
@@ -66,6 +70,7 @@ void free_host_tables(HostTables *t);
 void build_host_perceptual(uint32_t sample_rate, HostPerceptual *p);
 // Re-tile the cosine table for the two transform kernels: [n_block][stage][kKC][kBN]
 void tile_table_for_mdct(const float *cos_tab, float *out);  // rows = i (2048), cols = k (1024)
+void tile_table_for_imdct(const float *cos_tab, float *out); // [n_block][k][kImdctBN]
 
 // Device-side perceptual model, passed by value-pointer to the quantize/pack kernel.
 struct DevPerceptual
@@ -100,12 +105,12 @@ cudaError_t launch_mdct_exact(const MdctLaunch &p, cudaStream_t s);   // a_tiles
 
 struct ImdctLaunch
 {
-    const float *a_tiles;    // [tile][stage]{[kKC][kBM] compacted dequantised coefficients, [kImdctWarps] step masks}
-    const uint16_t *klist;   // [tile][1024]
-    const uint32_t *n_k;     // [tile] reduction length (multiple of kKC)
-    const uint32_t *n_tiles; // device-side number of live tiles
-    uint64_t max_slots;      // worst-case number of compacted rows (sizes the grid and `blocks`)
-    const float *tab;        // natural layout [1024][2048]
+    const float *a_tiles;      // [tile][stage]{[kImdctKC][kImdctBM] dequantised coefficients, [kImdctWarps] step masks}
+    const uint8_t *stage_list; // [tile][kImdctStages] ascending indices of the stages that hold a coefficient
+    const uint32_t *n_stages;  // [tile] entries of stage_list
+    const uint32_t *n_tiles;   // device-side number of live tiles
+    uint64_t max_slots;        // worst-case number of compacted rows (sizes the grid and `blocks`)
+    const float *tab;          // tile_table_for_imdct layout
     const float *window;
     float norm;
     float *blocks; // [slot][2048] windowed IMDCT output
@@ -154,7 +159,7 @@ struct GatherLaunch
 cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s);
 
 // Decode front end: which rows go through the IMDCT at all (sparse frames with at least one pair),
-// their compaction into tiles of kBM rows, and per tile the ascending union of coefficient indices.
+// their compaction into tiles of kImdctBM rows, and per tile the ascending union of coefficient indices.
 struct DequantLaunch
 {
     const glc_pair *pairs;
@@ -171,8 +176,8 @@ struct DequantLaunch
     uint64_t *slot_off;       // [n+1] exclusive scan of flags
     uint32_t *active_rows;    // [n]   local slot -> absolute row
     uint32_t *n_tiles;        // [1]
-    uint16_t *klist;          // [max_tiles][1024]
-    uint32_t *n_k;            // [max_tiles]
+    uint8_t *stage_list;      // [max_tiles][kImdctStages]
+    uint32_t *n_stages;       // [max_tiles]
     float *a_tiles;           // [max_tiles][kImdctATileFloats]
 };
 cudaError_t launch_dequant(const DequantLaunch &p, cudaStream_t s); // flags -> scan -> scatter -> tiles

@@ -127,18 +127,16 @@ void tile_table_for_mdct(const float *tab, float *out)
                 }
 }
 
+// IMDCT: [n_block][k][kImdctBN] floats, so that the kImdctKC table rows of a pipeline stage are ONE
+// contiguous block for every output block (a single bulk copy).
 void tile_table_for_imdct(const float *tab, float *out)
 {
     // reduction index = k (1024), output index = i (2048): element (k, i) = tab[k][i]
-    const int n_blocks = kFrame / kBN, stages = kHop / kKC;
+    const int n_blocks = kFrame / kImdctBN;
     for (int nb = 0; nb < n_blocks; ++nb)
-        for (int s = 0; s < stages; ++s)
-            for (int r = 0; r < kKC; ++r)
-                for (int c = 0; c < kBN; ++c)
-                {
-                    const int k = s * kKC + r, i = nb * kBN + c;
-                    out[(((size_t)nb * stages + s) * kKC + r) * kBN + c] = tab[(size_t)k * kFrame + i];
-                }
+        for (int k = 0; k < kHop; ++k)
+            for (int c = 0; c < kImdctBN; ++c)
+                out[((size_t)nb * kHop + k) * kImdctBN + c] = tab[(size_t)k * kFrame + nb * kImdctBN + c];
 }
 
 } // namespace glc
