@@ -213,6 +213,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         import torch.distributed as dist_mod
 
         torch.cuda.set_device(local_rank)
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
@@ -369,6 +371,34 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     e2e16_ms = max_over_ranks(e2e16_s / args.steps * 1e3)
     launches += sum(st3["launches"].values())
 
+    # ---- timed region 4: 16-bit PCM in AND out (glc_encode_i16 + glc_decode_i16: what `glc` does between
+    #      a 16-bit WAV and the WAV it writes back, src/audio.rs:11-16, 51-59; both conversions on the device) ----
+    def host_step_i16_io():
+        out = C.POINTER(_ffi.Encoded)()
+        chk(L.glc_encode_i16(enc_h, x16.ctypes.data, x16.size, CH, C.byref(out)))
+        p, n = C.POINTER(C.c_int16)(), C.c_uint64()
+        chk(L.glc_decode_i16(dec_h, out, C.byref(p), C.byref(n)))
+        got = n.value
+        L.glc_free(ctx.handle, p)
+        L.glc_encoded_free(ctx.handle, out)
+        return got
+
+    for _ in range(2):
+        host_step_i16_io()
+    ctx.stats_reset()
+    barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        assert host_step_i16_io() == x16.size
+    ctx.sync()
+    e2e16io_s = time.perf_counter() - t0
+    barrier()
+    t_region1 = time.perf_counter()
+    st4 = ctx.stats()
+    e2e16io_ms = max_over_ranks(e2e16io_s / args.steps * 1e3)
+    launches += sum(st4["launches"].values())
+
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
 
     # ---- roofline of the dominant kernel (rank 0's own launches) ----
@@ -439,6 +469,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "e2e_int16_ingest": {"value": total_secs / (e2e16_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e16_ms,
                              "h2d_bytes_per_step": st3["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st3["d2h_bytes"] // args.steps,
                              "api": "glc_encode_i16 + glc_decode (16-bit PCM in, f32 PCM out)"},
+        "e2e_int16_io": {"value": total_secs / (e2e16io_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e16io_ms,
+                         "h2d_bytes_per_step": st4["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st4["d2h_bytes"] // args.steps,
+                         "api": "glc_encode_i16 + glc_decode_i16 (16-bit PCM in and out, as between two WAV files)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks,

@@ -73,6 +73,7 @@ EXPORTS = [
     "glc_encoder_new", "glc_encoder_free", "glc_encode", "glc_encode_batch", "glc_encoded_free",
     "glc_encode_i16", "glc_encode_batch_i16", "glc_encode_i32",
     "glc_decoder_new", "glc_decoder_free", "glc_decode", "glc_decode_untrimmed", "glc_decode_batch",
+    "glc_decode_i16", "glc_decode_batch_i16",
     "glc_decode_stream_open", "glc_decode_stream_next", "glc_decode_stream_close",
     "glc_flac_encode", "glc_flac_encode_batch", "glc_decode_to_flac", "glc_decode_to_flac_batch",
     "glc_encoded_to_bincode", "glc_encoded_from_bincode",
@@ -120,6 +121,8 @@ def load() -> C.CDLL:
         "glc_decode": (C.c_int, [vp, pp(Encoded), pp(fp), pp(u64)]),
         "glc_decode_untrimmed": (C.c_int, [vp, pp(Encoded), pp(fp), pp(u64)]),
         "glc_decode_batch": (C.c_int, [vp, u32, pp(pp(Encoded)), pp(fp), pp(u64)]),
+        "glc_decode_i16": (C.c_int, [vp, pp(Encoded), pp(pp(C.c_int16)), pp(u64)]),
+        "glc_decode_batch_i16": (C.c_int, [vp, u32, pp(pp(Encoded)), pp(pp(C.c_int16)), pp(u64)]),
         "glc_decode_stream_open": (C.c_int, [vp, pp(Encoded), pp(vp)]),
         "glc_decode_stream_next": (C.c_int, [vp, pp(fp), pp(u64), pp(C.c_int), pp(C.c_float)]),
         "glc_decode_stream_close": (None, [vp]),

@@ -336,6 +336,34 @@ class Decoder:
             progress(Progress("Complete", f"Decoded {encoded.n_frames} frames"))
         return self._take(p, n.value)
 
+    def decode_pcm16(self, encoded: EncodedAudio) -> np.ndarray:
+        """The samples `glc -d file.glc` writes to its WAV (src/main.rs:95-105): Decoder::decode followed by
+        audio::convert_f32_to_i16 (src/audio.rs:11-16), converted on the device so that 16-bit samples
+        cross PCIe."""
+        st = encoded._as_struct()
+        p = C.POINTER(C.c_int16)()
+        n = C.c_uint64()
+        check(self._lib.glc_decode_i16(self.handle, C.byref(st), C.byref(p), C.byref(n)))
+        try:
+            return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.int16)
+        finally:
+            self._lib.glc_free(self.ctx.handle, p)
+
+    def decode_batch_pcm16(self, encoded: Sequence[EncodedAudio]) -> List[np.ndarray]:
+        n = len(encoded)
+        structs = [e._as_struct() for e in encoded]
+        ptrs = (C.POINTER(_ffi.Encoded) * n)(*[C.pointer(s) for s in structs])
+        outs = (C.POINTER(C.c_int16) * n)()
+        ns = (C.c_uint64 * n)()
+        check(self._lib.glc_decode_batch_i16(self.handle, n, ptrs, outs, ns))
+        res = []
+        for i in range(n):
+            try:
+                res.append(np.ctypeslib.as_array(outs[i], shape=(ns[i],)).copy() if ns[i] else np.zeros(0, np.int16))
+            finally:
+                self._lib.glc_free(self.ctx.handle, outs[i])
+        return res
+
     def decode_to_flac(self, encoded: EncodedAudio, compression_level: int = 5) -> bytes:
         """`glc -d file.glc --flac-level N` (src/main.rs:55-113): decode, then FLAC-encode the decoded
         samples, with the PCM kept on the device in between."""

@@ -1636,6 +1636,7 @@ struct DecodeHostIO
     const uint64_t *h_pair_off;     // [rows+1] batch-wide exclusive scan (host copy)
     const uint64_t *h_raw_off;      // [frames+1]
     float *const *h_out;            // [n_files] pinned outputs
+    bool out16;                     // outputs are 16-bit PCM (h_out entries are int16_t*): converted on the device
     const uint64_t *win_off;        // [n_files] first untrimmed value that is kept (gapless trim)
     const uint64_t *win_len;        // [n_files] number of values kept
     glc_pair *d_pairs;              // device arrays being filled wave by wave
@@ -1683,6 +1684,9 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     CUDA_TRY(dmalloc(&d_nk, wave_tiles, cs));
     CUDA_TRY(dmalloc(&d_stage_list, wave_tiles * kImdctStages, cs));
     CUDA_TRY(dmalloc(&d_out, total_out, cs));
+    int16_t *d_out16 = nullptr;
+    if (io && io->h_out && io->out16)
+        CUDA_TRY(dmalloc(&d_out16, total_out, cs));
     tr.mark("alloc");
 
     auto out_index = [&](uint64_t fr) -> uint64_t { // first output value that needs frame `fr`
@@ -1840,6 +1844,11 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             o.out = d_out;
             CUDA_TRY(launch_ola(o, cs));
         }
+        if (d_out16 && o1 > o0)
+        {
+            LaunchScope ls(c, GLC_K_MISC, cs);
+            CUDA_TRY(launch_pcm_to_i16(d_out + o0, d_out16 + o0, o1 - o0, cs));
+        }
         if (io && io->h_out)
         {
             // D2H of the finished range, clipped to every file's gapless window
@@ -1851,7 +1860,13 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             {
                 const uint64_t w0 = files[i].out_off + io->win_off[i], w1 = w0 + io->win_len[i];
                 const uint64_t a = std::max(o0, w0), b = std::min(o1, w1);
-                if (a < b)
+                if (a < b && d_out16)
+                {
+                    CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int16_t *>(io->h_out[i]) + (a - w0), d_out16 + a,
+                                             (b - a) * 2, cudaMemcpyDeviceToHost, c->d2h));
+                    c->stats.d2h_bytes += (b - a) * 2;
+                }
+                else if (a < b)
                 {
                     CUDA_TRY(cudaMemcpyAsync(io->h_out[i] + (a - w0), d_out + a, (b - a) * 4, cudaMemcpyDeviceToHost,
                                              c->d2h));
@@ -1878,6 +1893,8 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     dfree(d_nk, cs);
     dfree(d_stage_list, cs);
     dfree(d_files, cs);
+    if (d_out16)
+        dfree(d_out16, cs); // stream-ordered: the d2h stream is drained above
     tr.mark("free");
     *d_out_ret = d_out;
     return GLC_OK;
@@ -1906,7 +1923,7 @@ struct DeviceSink
 };
 
 static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc, bool trim,
-                                    float **pcm, uint64_t *n_out, DeviceSink *sink = nullptr)
+                                    float **pcm, uint64_t *n_out, DeviceSink *sink = nullptr, bool out16 = false)
 {
     if (!dec || !enc || (!sink && (!pcm || !n_out)) || n_files == 0)
         return fail(GLC_ERR_INVALID_ARG, "null/empty argument");
@@ -2052,7 +2069,7 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
     {
         std::vector<uint64_t> bytes(n_files);
         for (uint32_t i = 0; i < n_files; ++i)
-            bytes[i] = win_len[i] * 4;
+            bytes[i] = win_len[i] * (out16 ? 2 : 4);
         if (!slab_alloc(c, n_files, bytes.data(), (void **)h_out.data()))
         {
             cleanup(false);
@@ -2064,6 +2081,7 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
     io.h_pair_off = h_pair_off;
     io.h_raw_off = h_raw_off;
     io.h_out = sink ? nullptr : h_out.data();
+    io.out16 = out16;
     io.win_off = win_off.data();
     io.win_len = win_len.data();
     io.d_pairs = d_pairs;
@@ -2131,6 +2149,20 @@ extern "C" glc_status glc_decode_to_flac(glc_decoder *dec, const glc_encoded *en
                                          uint64_t *len)
 {
     return glc_decode_to_flac_batch(dec, 1, &enc, level, bytes, len);
+}
+
+// The CLI's default `glc -d file.glc` output (src/main.rs:95-105): Decoder::decode, then audio::export_to_wav,
+// whose first step is convert_f32_to_i16 (src/audio.rs:11-16).  The conversion runs on the device and
+// 16-bit samples cross PCIe: half the D2H bytes of glc_decode.
+extern "C" glc_status glc_decode_batch_i16(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
+                                           int16_t **pcm, uint64_t *n_samples)
+{
+    return decode_batch_impl(dec, n_files, enc, true, reinterpret_cast<float **>(pcm), n_samples, nullptr, true);
+}
+
+extern "C" glc_status glc_decode_i16(glc_decoder *dec, const glc_encoded *enc, int16_t **pcm, uint64_t *n_samples)
+{
+    return decode_batch_impl(dec, 1, &enc, true, reinterpret_cast<float **>(pcm), n_samples, nullptr, true);
 }
 
 extern "C" glc_status glc_decode_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,

@@ -611,6 +611,18 @@ __global__ void pcm_convert_kernel(const void *stage, int elem_bytes, uint64_t o
     }
 }
 
+// f32 -> 16-bit PCM exactly as the reference's WAV export does it (audio::convert_f32_to_i16,
+// src/audio.rs:11-16: `(sample * 32767.0).clamp(-32768.0, 32767.0) as i16`, NaN -> 0 as Rust's `as`).
+__global__ void pcm_to_i16_kernel(const float *in, int16_t *out, uint64_t n)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const float v = __fmul_rn(in[i], 32767.0f);
+        out[i] = (v != v) ? (int16_t)0 : (int16_t)__float2int_rz(fminf(fmaxf(v, -32768.0f), 32767.0f));
+    }
+}
+
 __global__ void fill_kernel(float *p, uint64_t n, float v)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -734,6 +746,15 @@ cudaError_t launch_pcm_convert(const void *stage, int elem_bytes, uint64_t off, 
         return cudaSuccess;
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 16);
     pcm_convert_kernel<<<grid, 256, 0, s>>>(stage, elem_bytes, off, n, inv_max, arena);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pcm_to_i16(const float *in, int16_t *out, uint64_t n, cudaStream_t s)
+{
+    if (n == 0)
+        return cudaSuccess;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 16);
+    pcm_to_i16_kernel<<<grid, 256, 0, s>>>(in, out, n);
     return cudaGetLastError();
 }
 

@@ -106,6 +106,7 @@ struct Smem
     float t[kRing][kStageFloats];
     uint64_t full[kRing];
     uint64_t empty[kRing];
+    uint32_t released[kRing]; // warps that have left the slot (running count)
 };
 
 // MDCT: reduce over i (64 stages of 32 steps)
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
         {
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], kGemmThreads / 32);
+            sm.released[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -140,14 +142,13 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
     const float *a_src = p.a_tiles + (size_t)m_tile * (kFrame * kBM);
     const float *t_src = p.tab + (size_t)n_block * (kFrame / kKC) * kStageFloats;
 
-    // producer step, executed by lane 0 of warp 0: fill ring slot `s % kRing` with stage s
+    // Fill ring slot `s % kRing` with stage s (two bulk copies).  The first kRing stages are issued by
+    // warp 0; stage s + kRing is issued by the last warp that leaves stage s, at the moment the slot
+    // becomes free, so no warp ever blocks on the others in order to feed the ring.
     auto issue = [&](int s) {
         const int slot = s % kRing;
         if (lane == 0)
         {
-            // the (s/kRing)-th refill waits for the (s/kRing - 1)-th release of this slot
-            if (s >= kRing)
-                mbar_wait(&sm.empty[slot], (uint32_t)((s / kRing) - 1) & 1u);
             mbar_expect_tx(&sm.full[slot], 2 * kStageBytes);
             bulk_g2s(sm.a[slot], a_src + (size_t)s * kStageFloats, kStageBytes, &sm.full[slot]);
             bulk_g2s(sm.t[slot], t_src + (size_t)s * kStageFloats, kStageBytes, &sm.full[slot]);
@@ -156,10 +157,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
     };
 
     if (warp == 0)
-    {
-        issue(0);
-        issue(1);
-    }
+        for (int s = 0; s < kRing; ++s)
+            issue(s);
 
     float acc[8][8];
 #pragma unroll
@@ -171,8 +170,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
     for (int s = 0; s < n_stages; ++s)
     {
         const int slot = s % kRing;
-        if (warp == 0 && s + 2 < n_stages)
-            issue(s + 2);
         mbar_wait(&sm.full[slot], (uint32_t)(s / kRing) & 1u);
 
         const float *As = sm.a[slot] + ty * 8;
@@ -193,8 +190,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
                     acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
         }
         __syncwarp();
+        uint32_t nth = 0;
         if (lane == 0)
+        {
             mbar_arrive(&sm.empty[slot]);
+            nth = atomicAdd(&sm.released[slot], 1u);
+        }
+        nth = __shfl_sync(0xffffffffu, nth, 0);
+        if (nth % (kGemmThreads / 32) == kGemmThreads / 32 - 1 && s + kRing < n_stages)
+        {
+            // last warp out: all arrivals precede their counts, so this wait returns at once; it orders
+            // the other warps' reads of the slot before the refill
+            mbar_wait(&sm.empty[slot], (uint32_t)(s / kRing) & 1u);
+            issue(s + kRing);
+        }
     }
 
     // ---- epilogue: * norm, two float4 stores per row ----

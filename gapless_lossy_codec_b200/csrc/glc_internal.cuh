@@ -249,6 +249,7 @@ cudaError_t launch_fast_decode(const FastDecodeLaunch &p, cudaStream_t s);
 
 cudaError_t launch_pcm_convert(const void *stage, int elem_bytes, uint64_t off, uint64_t n, float inv_max, float *arena,
                                cudaStream_t s);
+cudaError_t launch_pcm_to_i16(const float *in, int16_t *out, uint64_t n, cudaStream_t s); // WAV export conversion
 cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s);
 cudaError_t launch_fp32_issue_bench(int packed, int iters, float *sink, int blocks, cudaStream_t s);
 

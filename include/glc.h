@@ -32,7 +32,7 @@ extern "C" {
 #define GLC_FRAME_SIZE 2048u      /* src/codec.rs:15 */
 #define GLC_HOP_SIZE 1024u        /* src/codec.rs:16 */
 #define GLC_FRAMES_PER_CHUNK 500u /* src/codec.rs:18 */
-#define GLC_ABI_VERSION 4u
+#define GLC_ABI_VERSION 5u
 
 typedef enum glc_status
 {
@@ -157,6 +157,15 @@ glc_status glc_decode_untrimmed(glc_decoder *dec, const glc_encoded *enc, float 
                                 uint64_t *n_samples);
 glc_status glc_decode_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
                             float **pcm /* [n_files] */, uint64_t *n_samples /* [n_files] */);
+
+/* 16-bit PCM output ("next" row of SURVEY.md 8f, WAV side): what `glc -d file.glc` writes by default
+ * (src/main.rs:95-105: Decoder::decode, then audio::export_to_wav), i.e. the decoded samples after
+ * convert_f32_to_i16, `(s * 32767.0).clamp(-32768.0, 32767.0) as i16` (src/audio.rs:11-16).  The
+ * conversion runs on the device; the result equals that conversion applied to glc_decode's output and
+ * half the bytes cross PCIe.  Release with glc_free. */
+glc_status glc_decode_i16(glc_decoder *dec, const glc_encoded *enc, int16_t **pcm, uint64_t *n_samples);
+glc_status glc_decode_batch_i16(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
+                                int16_t **pcm /* [n_files] */, uint64_t *n_samples /* [n_files] */);
 
 /* Decoder::decode_streaming: pull API.  Each _next yields one AudioChunk: exactly
  * FRAMES_PER_CHUNK*HOP_SIZE*channels values while more frames remain, then the tail with

@@ -402,6 +402,19 @@ class Decoder
         return ChunkReceiver(h_, std::move(encoded), std::move(progress));
     }
 
+    /* the samples `glc -d x.glc` writes to its WAV (main.rs:95-105 -> audio::convert_f32_to_i16, audio.rs:11-16),
+     * converted on the device */
+    std::vector<std::int16_t> decode_pcm16(const EncodedAudio &encoded)
+    {
+        detail::Flat flat(encoded);
+        std::int16_t *p = nullptr;
+        std::uint64_t n = 0;
+        check(glc_decode_i16(h_, &flat.e, &p, &n), "Decoder::decode_pcm16");
+        std::vector<std::int16_t> out(p, p + n);
+        glc_free(ctx_.handle(), p);
+        return out;
+    }
+
     /* `glc -d x.glc --flac-level N` (main.rs:55-113) with the decoded PCM kept on the device */
     std::vector<std::uint8_t> decode_to_flac(const EncodedAudio &encoded, std::uint8_t level = 5)
     {

@@ -259,3 +259,31 @@ def test_decode_to_flac_equals_two_step_path(gpu_ctx):
         assert got == want, (ch, sr, level, len(got), len(want))
         info = oracle.flac_decode(got)
         assert info["md5_ok"] and info["total_samples"] == len(x) // ch  # gapless count survives the whole chain
+
+
+def _wav_i16(pcm: np.ndarray) -> np.ndarray:
+    """audio::convert_f32_to_i16, src/audio.rs:11-16: (s * 32767.0).clamp(-32768.0, 32767.0) as i16."""
+    v = pcm.astype(np.float32) * np.float32(32767.0)
+    return np.trunc(np.clip(v, np.float32(-32768.0), np.float32(32767.0))).astype(np.int16)
+
+
+def test_decode_pcm16_equals_wav_export_conversion(gpu_ctx):
+    """WAV side of SURVEY 8(f): `glc -d x.glc` = Decoder::decode, then export_to_wav, whose samples are
+    convert_f32_to_i16 of the decoded PCM (src/main.rs:95-105, src/audio.rs:11-16).  The fused call converts on
+    the device; every 16-bit sample must equal the conversion of the oracle's decoded PCM."""
+    from gapless_lossy_codec_b200 import Decoder
+
+    cases = [(signals.music_like(44100, 2, 1.3), 2, 44100),
+             (signals.sine(440, 48000, 1, 0.7) * np.float32(2.2), 1, 48000),  # clips: the clamp is exercised
+             (signals.sweep(100, 8000, 48000, 6, 0.3), 6, 48000),
+             (signals.white_noise(44100, 2, 0.4, 7), 2, 44100)]
+    refs = [oracle.encode(x, ch, sr) for x, ch, sr in cases]
+    dec = Decoder(2, 44100, gpu_ctx)
+    for (x, ch, sr), ref in zip(cases, refs):
+        want = _wav_i16(oracle.decode(ref))
+        got = dec.decode_pcm16(to_product(ref))
+        assert got.dtype == np.int16 and len(got) == len(x)  # gapless count
+        assert np.array_equal(got, want), (ch, sr, int(np.count_nonzero(got != want)))
+    outs = dec.decode_batch_pcm16([to_product(r) for r in refs])
+    for (x, ch, sr), ref, got in zip(cases, refs, outs):
+        assert np.array_equal(got, _wav_i16(oracle.decode(ref))), ("batch", ch, sr)

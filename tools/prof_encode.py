@@ -10,10 +10,11 @@ import numpy as np
 
 import signals
 from gapless_lossy_codec_b200 import default_context
+from gapless_lossy_codec_b200.codec import Context
 
 secs = float(os.environ.get("PROF_SECONDS", "120"))
 reps = int(os.environ.get("PROF_REPS", "2"))
-ctx = default_context(0)
+ctx = Context(0, 1) if os.environ.get("GLC_PROF_MODE") == "1" else default_context(0)  # 1 = FAST mode
 L = ctx._lib
 ctx.set_tuning(int(os.environ.get("GLC_GEMM_VARIANT", "0")), 0)
 x = np.tile(signals.music_like(44100, 2, 10.0), max(1, int(secs / 10)))
