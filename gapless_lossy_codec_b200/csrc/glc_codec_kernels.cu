@@ -556,6 +556,73 @@ __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
         (is_cur ? s_cur : s_prev)[c] = d;
     }
     __syncthreads();
+    if (ch <= 2)
+    {
+        // mono / stereo: four consecutive output values per thread (two loads of 8 bytes per source and
+        // channel, one 16-byte store); the arithmetic is the same single f32 add per value.
+        // Value e of a hop is (sample i = e / ch, channel c = e % ch).
+        auto fetch4 = [&](const OlaSrc *src, bool present, uint32_t e0, bool second_half, float v[4]) {
+            v[0] = v[1] = v[2] = v[3] = 0.0f; // absent frame / no coefficients: +0.0
+            if (!present)
+                return;
+            if (src[0].raw) // the flag is per frame: every channel reads the same raw body, interleaved
+            {
+                const uint32_t si = e0 + (second_half ? kHop * ch : 0u);
+                const int16_t *r = src[0].raw;
+                if (si + 3 < src[0].raw_len && (reinterpret_cast<uintptr_t>(r + si) & 7u) == 0) // foreign streams may be odd
+                {
+                    const short4 q = *reinterpret_cast<const short4 *>(r + si);
+                    v[0] = __fdiv_rn((float)q.x, 32767.0f);
+                    v[1] = __fdiv_rn((float)q.y, 32767.0f);
+                    v[2] = __fdiv_rn((float)q.z, 32767.0f);
+                    v[3] = __fdiv_rn((float)q.w, 32767.0f);
+                }
+                else
+                    for (int j = 0; j < 4; ++j)
+                        v[j] = si + j < src[0].raw_len ? __fdiv_rn((float)r[si + j], 32767.0f) : 0.0f;
+                return;
+            }
+            if (ch == 1)
+            {
+                if (src[0].blk)
+                {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(src[0].blk + e0));
+                    v[0] = b.x;
+                    v[1] = b.y;
+                    v[2] = b.z;
+                    v[3] = b.w;
+                }
+                return;
+            }
+            const uint32_t i0 = e0 >> 1;
+            if (src[0].blk)
+            {
+                const float2 b = __ldg(reinterpret_cast<const float2 *>(src[0].blk + i0));
+                v[0] = b.x;
+                v[2] = b.y;
+            }
+            if (src[1].blk)
+            {
+                const float2 b = __ldg(reinterpret_cast<const float2 *>(src[1].blk + i0));
+                v[1] = b.x;
+                v[3] = b.y;
+            }
+        };
+        for (uint32_t e0 = threadIdx.x * 4; e0 < kHop * ch; e0 += blockDim.x * 4)
+        {
+            float a[4], b[4];
+            fetch4(s_prev, has_prev, e0, true, a);
+            if (has_cur)
+            {
+                fetch4(s_cur, true, e0, false, b);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    a[j] = __fadd_rn(has_prev ? a[j] : 0.0f, b[j]);
+            }
+            *reinterpret_cast<float4 *>(out + e0) = make_float4(a[0], a[1], a[2], a[3]);
+        }
+        return;
+    }
     if (fast_path)
     {
         auto fetch = [&](const OlaSrc &d, uint32_t c, uint32_t i) -> float {
