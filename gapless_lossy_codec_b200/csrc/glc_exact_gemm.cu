@@ -77,6 +77,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!done);
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // One TMA-engine bulk copy global -> shared, completing `bytes` on the mbarrier.
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -344,26 +351,27 @@ __global__ void __launch_bounds__(kImdctThreads, 4) imdct_sparse_kernel(const __
         const int slot = s % kImdctRing;
         mbar_wait(&sm.full[slot], (uint32_t)(s / kImdctRing) & 1u);
 
-        // bit-reversed step mask: the next step in ascending order is clz(rm)
+        // bit-reversed step mask: the next step in ascending order is clz(rm).  Operand addresses are
+        // formed as 32-bit shared-memory addresses (one shift-add each per step).
         uint32_t rm = __brev(reinterpret_cast<const uint32_t *>(sm.a[slot] + kImdctKC * kImdctBM)[warp]);
-        const float *As = sm.a[slot] + warp * RW;
-        const float *Ts = sm.t[slot] + lane * 4;
+        const uint32_t a_base = smem_addr(sm.a[slot] + warp * RW);
+        const uint32_t t_base = smem_addr(sm.t[slot] + lane * 4);
         while (rm)
         {
-            const int ii = __clz((int)rm);
-            rm &= ~(0x80000000u >> ii);
+            const uint32_t ii = (uint32_t)__clz((int)rm);
+            rm ^= 0x80000000u >> ii; // the bit is known to be set
             float a[RW];
 #pragma unroll
             for (int r4 = 0; r4 < RW / 4; ++r4)
             {
-                const float4 v = *reinterpret_cast<const float4 *>(As + ii * kImdctBM + r4 * 4);
+                const float4 v = lds128(a_base + ii * (kImdctBM * 4) + r4 * 16);
                 a[r4 * 4 + 0] = v.x;
                 a[r4 * 4 + 1] = v.y;
                 a[r4 * 4 + 2] = v.z;
                 a[r4 * 4 + 3] = v.w;
             }
-            const float4 t_lo = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN);
-            const float4 t_hi = *reinterpret_cast<const float4 *>(Ts + ii * kImdctBN + 128);
+            const float4 t_lo = lds128(t_base + ii * (kImdctBN * 4));
+            const float4 t_hi = lds128(t_base + ii * (kImdctBN * 4) + 512);
             const float t[8] = {t_lo.x, t_lo.y, t_lo.z, t_lo.w, t_hi.x, t_hi.y, t_hi.z, t_hi.w};
 #pragma unroll
             for (int r = 0; r < RW; ++r)
