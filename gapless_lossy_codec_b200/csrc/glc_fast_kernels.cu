@@ -289,6 +289,42 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                 if ((uint32_t)fc < fcs_here && sm.st_interior[fc])
                     interior_mask |= 1u << fc;
             }
+            // Common case (every frame-channel of a full group lies inside its file): no validity tests,
+            // no per-frame-channel descriptors, 32 independent loads in flight per thread.
+            const bool all_interior = fcs_here == (uint32_t)kFastFcs && interior_mask == (1u << kFastFcs) - 1u;
+            if (all_interior)
+            {
+#pragma unroll 1
+                for (int it = 0; it < (kHop / 2) / kFastThreads; ++it)
+                {
+                    const int n = tid + it * kFastThreads;
+                    const float wa = __ldg(p.window + 512 + 2 * n);
+                    const float wo = __ldg(p.window + (n < 256 ? 511 - 2 * n : 2 * n - 512));
+                    const bool lo_half = n < 256;
+                    // lo_half: u0 = -b[i0] wa - b[i1] wo, u1 =  b[i2] wo - b[i3] wa
+                    // else   : u0 =  b[i0] wo - b[i1] wa, u1 = -b[i2] wa - b[i3] wo
+                    const int i0 = lo_half ? 1535 - 2 * n : 2 * n - 512;
+                    const int i1 = lo_half ? 1536 + 2 * n : 1535 - 2 * n;
+                    const int i2 = lo_half ? 511 - 2 * n : 512 + 2 * n;
+                    const int i3 = lo_half ? 512 + 2 * n : 2559 - 2 * n;
+                    const float *q0 = gb + i0 * ich, *q1 = gb + i1 * ich, *q2 = gb + i2 * ich, *q3 = gb + i3 * ich;
+                    const float c00 = lo_half ? -wa : wo, c01 = lo_half ? -wo : -wa;
+                    const float c10 = lo_half ? wo : -wa, c11 = lo_half ? -wa : -wo;
+                    float x[kFastFcs][4];
+#pragma unroll
+                    for (int fc = 0; fc < kFastFcs; ++fc)
+                    {
+                        x[fc][0] = __ldg(q0 + foff[fc]);
+                        x[fc][1] = __ldg(q1 + foff[fc]);
+                        x[fc][2] = __ldg(q2 + foff[fc]);
+                        x[fc][3] = __ldg(q3 + foff[fc]);
+                    }
+#pragma unroll
+                    for (int fc = 0; fc < kFastFcs; ++fc)
+                        sm.u[fc][n] = make_float2(x[fc][0] * c00 + x[fc][1] * c01, x[fc][2] * c10 + x[fc][3] * c11);
+                }
+            }
+            else
 #pragma unroll 1
             for (int it = 0; it < (kHop / 2) / kFastThreads; ++it)
             {
