@@ -209,8 +209,9 @@ glc_status glc::flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *co
 
     FL_CUDA(cudaSetDevice(ctx_device(ctx)));
     cudaStream_t cs = ctx_compute_stream(ctx);
-    cudaDeviceProp prop;
-    FL_CUDA(cudaGetDeviceProperties(&prop, ctx_device(ctx)));
+    // (cudaGetDeviceProperties costs milliseconds per call; one attribute is all that is needed)
+    int sm_count = 148;
+    FL_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx_device(ctx)));
 
     std::vector<FlacFileDesc> files(n_files);
     uint64_t tot_pcm = 0, tot_blocks = 0;
@@ -248,6 +249,8 @@ glc_status glc::flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *co
     };
     std::vector<std::vector<CopyOp>> ops(n_files);
     std::vector<cudaEvent_t> chunk_events;
+    const uint64_t kInlineMd5Samples = 4ull << 20; // 8 MB of 16-bit samples: about 12 ms of hashing
+    bool inline_md5 = false;
     int16_t *h_i16 = nullptr;
     auto join_all = [&]() {
         for (auto &w : workers)
@@ -357,8 +360,11 @@ glc_status glc::flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *co
                 break;
             }
             ctx_count_bytes(ctx, 0, tot_pcm * 2);
+            // Small calls hash on the calling thread once everything else is queued (a new thread costs
+            // milliseconds: creation plus binding the CUDA context, against microseconds of kernels).
+            inline_md5 = tot_pcm <= kInlineMd5Samples;
             const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-            const unsigned nthreads = std::min<unsigned>(hw, n_files);
+            const unsigned nthreads = inline_md5 ? 0u : std::min<unsigned>(hw, n_files);
             const int device = ctx_device(ctx);
             for (unsigned t = 0; t < nthreads; ++t)
                 workers.emplace_back([&, t, nthreads, device]() {
@@ -400,12 +406,12 @@ glc_status glc::flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *co
             tot_bytes += file_bytes[i];
         }
         FL_STEP(dev_alloc(ctx, (void **)&d_out, std::max<uint64_t>(tot_bytes, 1), cs));
-        if (const size_t sw = flac_emit_scratch_words(tot_blocks, max_ch, max_bs, max_frame, prop.multiProcessorCount))
+        if (const size_t sw = flac_emit_scratch_words(tot_blocks, max_ch, max_bs, max_frame, sm_count))
             FL_STEP(dev_alloc(ctx, (void **)&d_scratch, sw * 4, cs));
         ctx_count_launch(ctx, GLC_K_FLAC_GATHER, 1);
         ctx_time_begin(ctx, GLC_K_FLAC_GATHER, &tok);
         FL_STEP(launch_flac_emit(fl, d_k, max_ch, max_bs, max_frame, d_foff, d_out, d_scratch,
-                                 prop.multiProcessorCount, cs));
+                                 sm_count, cs));
         ctx_time_end(ctx, tok);
 
         // outputs: 4 + 38 header bytes, then the file's frames copied straight from the device
@@ -429,6 +435,17 @@ glc_status glc::flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *co
         if (st != GLC_OK)
             break;
         ctx_count_bytes(ctx, 0, tot_bytes + tot_blocks * 4);
+        if (inline_md5)
+            for (uint32_t i = 0; i < n_files; ++i)
+            {
+                Md5 m;
+                for (const CopyOp &op : ops[i])
+                {
+                    cudaEventSynchronize(chunk_events[op.event]);
+                    m.update(reinterpret_cast<const uint8_t *>(h_i16 + files[i].i16_off + op.off), op.cnt * 2);
+                }
+                m.finish(md5[i].data());
+            }
         FL_STEP(cudaStreamSynchronize(cs));
     } while (0);
 
