@@ -21,7 +21,7 @@
 //         window multiply, i.e. block[i]), one contiguous 16 KiB block per (row tile, stage); T comes
 //         from a host re-tiled copy of the table, also one contiguous block per (output block, stage).
 //   * IMDCT (imdct_sparse_kernel below) keeps the ring and the TMA feed but is SPARSE at warp
-//     granularity: a warp owns 4 rows and executes only the reduction steps at which one of ITS rows
+//     granularity: a warp owns 2 rows and executes only the reduction steps at which one of ITS rows
 //     has a coefficient (a step mask per warp and stage, delivered with the A stage).  Skipping a k
 //     whose coefficient is zero in a row is exact: the product is +-0 and the running sum (which starts
 //     at +0.0 and can never become -0) is unchanged.
@@ -256,20 +256,21 @@ cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
 // ---------------------------------------------------------------------------------------------
 // imdct_sparse_kernel: direct IMDCT (src/codec.rs:377-390) + synthesis window (:672-675) over the
 // compacted rows of a decode wave.
-//   CTA   = 32 rows x 256 outputs, 8 warps, 62 registers: 4 CTAs = 32 warps per SM.
-//   warp  = 4 rows x 256 outputs (thread: 4 rows x 2 float4 of outputs), so a reduction step is needed
+//   CTA   = 32 rows x 256 outputs, 16 warps, 40 registers: 3 CTAs = 48 warps per SM.
+//   warp  = 2 rows x 256 outputs (thread: 2 rows x 2 float4 of outputs), so a reduction step is needed
 //           by the whole warp or by none of it: the warp walks the set bits of its step mask and the
 //           branch is uniform.  On the bench workload a row holds ~258 of the 1024 indices, the union of
-//           4 rows ~446, of 8 rows ~560, of 128 rows ~945 (the dense contraction of the first version).
-//   stage = 16 consecutive coefficient indices: A = [16][32 rows] values + 8 masks (2 080 B) written by
+//           2 rows ~344, of 4 rows ~446, of 8 rows ~560, of 128 rows ~945 (the dense contraction of the
+//           first version).
+//   stage = 16 consecutive coefficient indices: A = [16][32 rows] values + 16 masks (2 112 B) written by
 //           dequant_tile_kernel, T = 16 rows x 256 outputs of the table, contiguous in the re-tiled copy
 //           (tile_table_for_imdct): two bulk copies per stage.  Stages in which the tile has no
 //           coefficient at all are not listed and never loaded.
 //   ring  = 3 slots, full/empty mbarriers; a warp with nothing to do in a stage releases it at once;
 //           there is no producer warp: a slot is refilled by the last warp that leaves it.
-// Measured on the hour-long bench signal: 26.5 ms (dense over the 128-row union) -> 16.2 ms.  What is
-// left is the per-step bookkeeping (13 of 77 instructions) and warps of one CTA waiting for each
-// other at the ring (issue slots 86 % busy); with every mask forced to all-ones the same kernel runs
+// Measured on the hour-long bench signal: 26.5 ms (dense over the 128-row union) -> 15.2 ms (8-row warps
+// 20.1, 4-row warps 15.7).  What is left is the per-step bookkeeping (12 of 44 instructions) and warps of
+// one CTA waiting for each other at the ring; with every mask forced to all-ones the same kernel runs
 // at the full issue rate, i.e. the pipeline itself is not the limit.
 constexpr int kImdctRing = 3;
 struct ImdctSmem
@@ -283,7 +284,7 @@ struct ImdctSmem
 };
 static_assert((kImdctAStageFloats * 4) % 16 == 0, "bulk copies need 16-byte granularity");
 
-__global__ void __launch_bounds__(kImdctThreads, 4) imdct_sparse_kernel(const __grid_constant__ GemmParams p)
+__global__ void __launch_bounds__(kImdctThreads, kImdctRowsPerWarp == 2 ? 3 : 4) imdct_sparse_kernel(const __grid_constant__ GemmParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ImdctSmem &sm = *reinterpret_cast<ImdctSmem *>(smem_raw);
@@ -361,14 +362,21 @@ __global__ void __launch_bounds__(kImdctThreads, 4) imdct_sparse_kernel(const __
             const uint32_t ii = (uint32_t)__clz((int)rm);
             rm ^= 0x80000000u >> ii; // the bit is known to be set
             float a[RW];
-#pragma unroll
-            for (int r4 = 0; r4 < RW / 4; ++r4)
+            if constexpr (RW == 2)
             {
-                const float4 v = lds128(a_base + ii * (kImdctBM * 4) + r4 * 16);
-                a[r4 * 4 + 0] = v.x;
-                a[r4 * 4 + 1] = v.y;
-                a[r4 * 4 + 2] = v.z;
-                a[r4 * 4 + 3] = v.w;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[0]), "=f"(a[1]) : "r"(a_base + ii * (kImdctBM * 4)));
+            }
+            else
+            {
+#pragma unroll
+                for (int r4 = 0; r4 < RW / 4; ++r4)
+                {
+                    const float4 v = lds128(a_base + ii * (kImdctBM * 4) + r4 * 16);
+                    a[r4 * 4 + 0] = v.x;
+                    a[r4 * 4 + 1] = v.y;
+                    a[r4 * 4 + 2] = v.z;
+                    a[r4 * 4 + 3] = v.w;
+                }
             }
             const float4 t_lo = lds128(t_base + ii * (kImdctBN * 4));
             const float4 t_hi = lds128(t_base + ii * (kImdctBN * 4) + 512);

@@ -28,10 +28,10 @@ constexpr int kImdctBM = 32;
 constexpr int kImdctBN = 256;
 constexpr int kImdctKC = 16;
 constexpr int kImdctStages = kHop / kImdctKC;                          // 64
-constexpr int kImdctRowsPerWarp = 4;
-constexpr int kImdctWarps = kImdctBM / kImdctRowsPerWarp;              // 8
-constexpr int kImdctThreads = kImdctWarps * 32;                        // 256
-constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctWarps;  // 512 values + 8 masks = 2 080 B
+constexpr int kImdctRowsPerWarp = 2;
+constexpr int kImdctWarps = kImdctBM / kImdctRowsPerWarp;              // 16
+constexpr int kImdctThreads = kImdctWarps * 32;                        // 512
+constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctWarps;  // 512 values + 16 masks = 2 112 B
 constexpr size_t kImdctATileFloats = (size_t)kImdctStages * kImdctAStageFloats;
 
 // One input file inside a batched encode (device copy lives in FileTable::d_files).
