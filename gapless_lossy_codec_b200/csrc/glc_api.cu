@@ -2018,7 +2018,9 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
             {
                 h_raw_off[f.first_frame + k] = rb + e->raw_offset[k];
                 const uint64_t rl = e->raw_offset[k + 1] - e->raw_offset[k];
-                if (e->raw_offset[k + 1] < e->raw_offset[k] || (e->frame_is_raw[k] != 0) != (rl != 0))
+                // raw_pcm = Some(v) may hold any number of values, also none (the reference reads what is
+                // there and leaves the rest of the block at zero, src/codec.rs:633-640); None holds nothing
+                if (e->raw_offset[k + 1] < e->raw_offset[k] || (e->frame_is_raw[k] == 0 && rl != 0))
                 {
                     cleanup(false);
                     return fail(GLC_ERR_CORRUPT, "stream %u: frame %llu raw flag/length mismatch", i,

@@ -287,3 +287,24 @@ def test_decode_pcm16_equals_wav_export_conversion(gpu_ctx):
     outs = dec.decode_batch_pcm16([to_product(r) for r in refs])
     for (x, ch, sr), ref, got in zip(cases, refs, outs):
         assert np.array_equal(got, _wav_i16(oracle.decode(ref))), ("batch", ch, sr)
+
+
+def test_foreign_raw_frames_of_any_length(gpu_ctx):
+    """raw_pcm = Some(v) with a v of any length, also empty: the reference reads the values that exist and
+    leaves the rest of the block at zero (src/codec.rs:626-644).  Hand-built stream, compared with the oracle."""
+    from gapless_lossy_codec_b200 import Decoder
+
+    for ch in (1, 2):
+        x = np.concatenate([signals.sine(440, 44100, ch, 0.2), signals.white_noise(44100, ch, 0.3, 11)])
+        ref = oracle.encode(x, ch, 44100)
+        raw_frames = np.flatnonzero(ref.frame_is_raw)
+        assert len(raw_frames) >= 4
+        lens = (ref.raw_offset[1:] - ref.raw_offset[:-1]).astype(np.int64)
+        bodies = [ref.raw[int(ref.raw_offset[f]):int(ref.raw_offset[f + 1])] for f in range(ref.n_frames)]
+        new_len = {int(raw_frames[0]): 0, int(raw_frames[1]): 101, int(raw_frames[2]): 2048 * ch - 3,
+                   int(raw_frames[3]): 1024 * ch}
+        bodies = [b[:new_len.get(f, len(b))] for f, b in enumerate(bodies)]
+        ref.raw = np.concatenate(bodies).astype(np.int16)
+        ref.raw_offset = np.concatenate([[0], np.cumsum([len(b) for b in bodies])]).astype(np.uint64)
+        pcm = Decoder(ch, 44100, gpu_ctx).decode(to_product(ref))
+        assert_pcm_bits_equal(pcm, oracle.decode(ref), f"short raw frames, {ch} ch")

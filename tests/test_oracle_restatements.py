@@ -1,0 +1,72 @@
+"""Two restatements of the reference's codec, written separately from the Rust source -- the C oracle
+(oracle/codec_oracle.c) and a numpy one (oracle/codec_restatement_np.py) -- must agree bit for bit:
+streams (flags, indices, quantised values, scale bit patterns, raw bodies, gapless metadata) and
+decoded PCM.  This does not pin the oracle to the reference binary (no Rust toolchain here), but it
+rules out slips of transcription in either restatement."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+import signals  # noqa: E402
+from oracle import codec_restatement_np as npr  # noqa: E402
+
+
+def _cases():
+    rng = np.random.default_rng(42)
+    return [
+        ("sine_mono_44k", signals.sine(440, 44100, 1, 0.12), 1, 44100),
+        ("music_noise_stereo_44k", np.concatenate([signals.music_like(44100, 2, 0.1),
+                                                   signals.white_noise(44100, 2, 0.08, 9)]), 2, 44100),
+        ("sweep_3ch_48k", signals.sweep(200, 9000, 48000, 3, 0.07), 3, 48000),
+        ("loud_clipping_mono_8k", (rng.standard_normal(1500) * 1.5).astype(np.float32), 1, 8000),
+    ]
+
+
+def test_tables_agree():
+    t = npr.MdctTables.get()
+    cos_tab, window, norm = oracle.tables()
+    assert np.array_equal(t.cos_table.view(np.uint32).ravel(), np.asarray(cos_tab, np.float32).view(np.uint32).ravel())
+    assert np.array_equal(t.window.view(np.uint32), np.asarray(window, np.float32).view(np.uint32))
+    assert np.float32(t.norm).view(np.uint32) == np.float32(norm).view(np.uint32) == np.uint32(0x3D3504F3)
+
+
+@pytest.mark.parametrize("sr", [8000, 44100, 48000, 96000])
+def test_perceptual_model_agrees(sr):
+    p = npr.PerceptualWeights(1024, sr)
+    weights, bands = oracle.perceptual(sr)
+    assert list(bands) == p.critical_bands
+    assert np.array_equal(np.asarray(weights, np.float32).view(np.uint32), p.weights.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,x,ch,sr", _cases(), ids=[c[0] for c in _cases()])
+def test_encode_and_decode_agree(name, x, ch, sr):
+    a = npr.encode(x, ch, sr)
+    b = oracle.encode(x, ch, sr)
+    assert (a.sample_rate, a.channels, a.total_samples) == (b.sample_rate, b.channels, b.total_samples)
+    assert (a.encoder_delay, a.padding, a.original_length) == (b.encoder_delay, b.padding, b.original_length)
+    assert len(a.frames) == b.n_frames
+    kinds = set()
+    for f, fr in enumerate(a.frames):
+        assert (fr.raw_pcm is not None) == bool(b.frame_is_raw[f]), f"frame {f} raw flag"
+        kinds.add(fr.raw_pcm is not None)
+        if fr.raw_pcm is not None:
+            assert np.array_equal(fr.raw_pcm, b.raw[int(b.raw_offset[f]):int(b.raw_offset[f + 1])]), f"frame {f} raw body"
+            continue
+        for c in range(ch):
+            row = f * ch + c
+            lo, hi = int(b.pair_offset[row]), int(b.pair_offset[row + 1])
+            assert [k for k, _ in fr.sparse[c]] == b.pair_idx[lo:hi].tolist(), f"row {row} indices"
+            assert [q for _, q in fr.sparse[c]] == b.pair_q[lo:hi].tolist(), f"row {row} values"
+            assert np.float32(fr.scales[c]).view(np.uint32) == b.scales[row:row + 1].view(np.uint32)[0], f"row {row} scale"
+    if name.startswith("music_noise"):
+        assert kinds == {True, False}, "both frame kinds must occur"
+    pa = npr.decode(a)
+    pb = oracle.decode(b, literal_imdct=True)
+    assert pa.size == pb.size == x.size
+    assert np.array_equal(pa.view(np.uint32), np.asarray(pb, np.float32).view(np.uint32)), "decoded PCM bits"
