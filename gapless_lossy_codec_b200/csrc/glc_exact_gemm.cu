@@ -37,6 +37,13 @@ namespace
 constexpr int kStageFloats = kKC * kBN;        // 4096 floats = 16 KiB per operand per stage
 constexpr int kStageBytes = kStageFloats * 4;
 constexpr int kRing = 3;
+// Outputs per thread of the MDCT contraction.  Measured on the hour-long bench signal: 8 (256 threads,
+// 126 registers, 16 warps/SM) 39.6 ms; 4 (512 threads, 64 registers, 32 warps/SM) 41.7 ms -- twice the
+// warps do not make up for 3 instead of 4 operand loads per 64 instead of 128 arithmetic instructions.
+#ifndef GLC_MDCT_NC
+#define GLC_MDCT_NC 8
+#endif
+constexpr int kMdctNC = GLC_MDCT_NC;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p)
 {
@@ -116,9 +123,12 @@ struct Smem
     uint32_t released[kRing]; // warps that have left the slot (running count)
 };
 
-// MDCT: reduce over i (64 stages of 32 steps)
-__global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __grid_constant__ GemmParams p)
+// MDCT: reduce over i (64 stages of 32 steps).  NC = outputs per thread (8 rows x NC outputs):
+// NC = 8 -> 256 threads, 16 warps/SM; NC = 4 -> 512 threads, 64 registers, 32 warps/SM.
+template <int NC>
+__global__ void __launch_bounds__(kGemmThreads * 8 / NC, 2) exact_gemm_kernel(const __grid_constant__ GemmParams p)
 {
+    constexpr int kThreads = kGemmThreads * 8 / NC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     constexpr int kNBlocks = kHop / kBN;
@@ -127,8 +137,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int tx = tid & 15;
-    const int ty = tid >> 4;
+    const int tx = NC == 8 ? (tid & 15) : (tid & 31);
+    const int ty = NC == 8 ? (tid >> 4) : (tid >> 5);
     // linear grid, output block fastest: the CTAs that run together share A tiles in L2
     const int n_block = (int)(blockIdx.x % kNBlocks);
     const uint64_t m_tile = p.tile_begin + blockIdx.x / kNBlocks;
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
         for (int s = 0; s < kRing; ++s)
         {
             mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], kGemmThreads / 32);
+            mbar_init(&sm.empty[s], kThreads / 32);
             sm.released[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,11 +177,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
         for (int s = 0; s < kRing; ++s)
             issue(s);
 
-    float acc[8][8];
+    float acc[8][NC];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < NC; ++c)
             acc[r][c] = 0.0f;
 
     for (int s = 0; s < n_stages; ++s)
@@ -187,13 +197,15 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
             const float4 a_lo = *reinterpret_cast<const float4 *>(As + ii * kBM);
             const float4 a_hi = *reinterpret_cast<const float4 *>(As + ii * kBM + 4);
             const float4 t_lo = *reinterpret_cast<const float4 *>(Ts + ii * kBN);
-            const float4 t_hi = *reinterpret_cast<const float4 *>(Ts + ii * kBN + 64);
+            float4 t_hi = t_lo;
+            if (NC == 8)
+                t_hi = *reinterpret_cast<const float4 *>(Ts + ii * kBN + 64);
             const float a[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
             const float t[8] = {t_lo.x, t_lo.y, t_lo.z, t_lo.w, t_hi.x, t_hi.y, t_hi.z, t_hi.w};
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
+                for (int c = 0; c < NC; ++c)
                     acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
         }
         __syncwarp();
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
             nth = atomicAdd(&sm.released[slot], 1u);
         }
         nth = __shfl_sync(0xffffffffu, nth, 0);
-        if (nth % (kGemmThreads / 32) == kGemmThreads / 32 - 1 && s + kRing < n_stages)
+        if (nth % (kThreads / 32) == kThreads / 32 - 1 && s + kRing < n_stages)
         {
             // last warp out: all arrivals precede their counts, so this wait returns at once; it orders
             // the other warps' reads of the slot before the refill
@@ -223,13 +235,14 @@ __global__ void __launch_bounds__(kGemmThreads, 2) exact_gemm_kernel(const __gri
         const uint64_t row = row0 + r;
         if (row >= p.n_rows)
             continue;
-        float v[8];
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < NC; ++c)
             v[c] = __fmul_rn(acc[r][c], p.norm);
         float *orow = p.out + row * kHop;
         *reinterpret_cast<float4 *>(orow + n_lo) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(orow + n_hi) = make_float4(v[4], v[5], v[6], v[7]);
+        if (NC == 8)
+            *reinterpret_cast<float4 *>(orow + n_hi) = make_float4(v[4], v[5], v[6], v[7]);
     }
 }
 
@@ -239,7 +252,7 @@ cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
     const size_t smem = sizeof(Smem);
     if (!configured)
     {
-        cudaError_t e = cudaFuncSetAttribute(exact_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(exact_gemm_kernel<kMdctNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
         configured = true;
@@ -249,7 +262,7 @@ cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
     const uint64_t n_ctas = m_tiles * (kHop / kBN);
     if (n_ctas > 0x7fffffffull)
         return cudaErrorInvalidValue;
-    exact_gemm_kernel<<<(unsigned)n_ctas, kGemmThreads, smem, s>>>(p);
+    exact_gemm_kernel<kMdctNC><<<(unsigned)n_ctas, kGemmThreads * 8 / kMdctNC, smem, s>>>(p);
     return cudaGetLastError();
 }
 
