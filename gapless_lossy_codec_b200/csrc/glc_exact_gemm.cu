@@ -279,13 +279,13 @@ cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
 //           dequant_tile_kernel, T = 16 rows x 256 outputs of the table, contiguous in the re-tiled copy
 //           (tile_table_for_imdct): two bulk copies per stage.  Stages in which the tile has no
 //           coefficient at all are not listed and never loaded.
-//   ring  = 3 slots, full/empty mbarriers; a warp with nothing to do in a stage releases it at once;
+//   ring  = 4 slots (3 CTAs x 74 KB fill the SM; 8 stages of 8 indices measured slower), full/empty mbarriers; a warp with nothing to do in a stage releases it at once;
 //           there is no producer warp: a slot is refilled by the last warp that leaves it.
-// Measured on the hour-long bench signal: 26.5 ms (dense over the 128-row union) -> 15.2 ms (8-row warps
-// 20.1, 4-row warps 15.7).  What is left is the per-step bookkeeping (12 of 44 instructions) and warps of
+// Measured on the hour-long bench signal: 26.5 ms (dense over the 128-row union) -> 14.8 ms (8-row warps
+// 20.1, 4-row warps 15.7, 2-row warps with a 3-slot ring 15.2).  What is left is the per-step bookkeeping (12 of 44 instructions) and warps of
 // one CTA waiting for each other at the ring; with every mask forced to all-ones the same kernel runs
 // at the full issue rate, i.e. the pipeline itself is not the limit.
-constexpr int kImdctRing = 3;
+constexpr int kImdctRing = 4;
 struct ImdctSmem
 {
     float a[kImdctRing][kImdctAStageFloats];
