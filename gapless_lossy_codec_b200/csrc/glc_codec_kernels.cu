@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
     // step masks and the list of stages that are present
     float *a = p.a_tiles + tile * kImdctATileFloats;
     static_assert(32 % kImdctKC == 0, "a stage must not straddle a 32-bit word of the index sets");
+    constexpr uint32_t kStageMask = kImdctKC == 32 ? 0xffffffffu : ((1u << (kImdctKC & 31)) - 1u);
     if (tid < kImdctStages)
     {
         const uint32_t st = tid;
@@ -410,12 +411,12 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
 #pragma unroll
         for (int g = 0; g < kImdctWarps; ++g)
         {
-            mm[g] = (s_gbits[g][(st * kImdctKC) >> 5] >> ((st * kImdctKC) & 31)) & ((1u << kImdctKC) - 1u);
+            mm[g] = (s_gbits[g][(st * kImdctKC) >> 5] >> ((st * kImdctKC) & 31)) & kStageMask;
             any |= mm[g];
 #if defined(GLC_EXPERIMENT_NO_STEPS) // timing experiment: the pipeline alone (results are wrong)
             mm[g] = 0;
 #elif defined(GLC_EXPERIMENT_DENSE_MASKS) // timing experiment: every warp executes every step
-            mm[g] = (1u << kImdctKC) - 1u;
+            mm[g] = kStageMask;
 #endif
         }
         s_present[st] = any;

@@ -275,17 +275,18 @@ cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
 //           branch is uniform.  On the bench workload a row holds ~258 of the 1024 indices, the union of
 //           2 rows ~344, of 4 rows ~446, of 8 rows ~560, of 128 rows ~945 (the dense contraction of the
 //           first version).
-//   stage = 16 consecutive coefficient indices: A = [16][32 rows] values + 16 masks (2 112 B) written by
-//           dequant_tile_kernel, T = 16 rows x 256 outputs of the table, contiguous in the re-tiled copy
+//   stage = 32 consecutive coefficient indices: A = [32][32 rows] values + 16 masks (4 160 B) written by
+//           dequant_tile_kernel, T = 32 rows x 256 outputs of the table, contiguous in the re-tiled copy
 //           (tile_table_for_imdct): two bulk copies per stage.  Stages in which the tile has no
 //           coefficient at all are not listed and never loaded.
-//   ring  = 4 slots (3 CTAs x 74 KB fill the SM; 8 stages of 8 indices measured slower), full/empty mbarriers; a warp with nothing to do in a stage releases it at once;
+//   ring  = 2 slots (3 CTAs x 74 KB fill the SM; the same memory as 4 stages of 16 indices or 8 of 8
+//           measured slower: 14.8 and 17.3 ms, the per-stage bookkeeping counts), full/empty mbarriers; a warp with nothing to do in a stage releases it at once;
 //           there is no producer warp: a slot is refilled by the last warp that leaves it.
-// Measured on the hour-long bench signal: 26.5 ms (dense over the 128-row union) -> 14.8 ms (8-row warps
-// 20.1, 4-row warps 15.7, 2-row warps with a 3-slot ring 15.2).  What is left is the per-step bookkeeping (12 of 44 instructions) and warps of
+// Measured on the hour-long bench signal: 26.5 ms (dense over the 128-row union) -> 13.8 ms (8-row warps
+// 20.1, 4-row warps 15.7, 2-row warps with 16-index stages 14.8).  What is left is the per-step bookkeeping (12 of 44 instructions) and warps of
 // one CTA waiting for each other at the ring; with every mask forced to all-ones the same kernel runs
 // at the full issue rate, i.e. the pipeline itself is not the limit.
-constexpr int kImdctRing = 4;
+constexpr int kImdctRing = 2;
 struct ImdctSmem
 {
     float a[kImdctRing][kImdctAStageFloats];

@@ -26,12 +26,12 @@ constexpr int kGemmThreads = 256;
 // indices and one A stage carries, after its [kImdctKC][kImdctBM] values, one step mask per warp.
 constexpr int kImdctBM = 32;
 constexpr int kImdctBN = 256;
-constexpr int kImdctKC = 16;
-constexpr int kImdctStages = kHop / kImdctKC;                          // 64
+constexpr int kImdctKC = 32;
+constexpr int kImdctStages = kHop / kImdctKC;                          // 32
 constexpr int kImdctRowsPerWarp = 2;
 constexpr int kImdctWarps = kImdctBM / kImdctRowsPerWarp;              // 16
 constexpr int kImdctThreads = kImdctWarps * 32;                        // 512
-constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctWarps;  // 512 values + 16 masks = 2 112 B
+constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctWarps;  // 1024 values + 16 masks = 4 160 B
 constexpr size_t kImdctATileFloats = (size_t)kImdctStages * kImdctAStageFloats;
 
 // One input file inside a batched encode (device copy lives in FileTable::d_files).
