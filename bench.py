@@ -19,6 +19,8 @@ What the single JSON line holds
                 construction (SURVEY.md section 0, F2 / DESIGN.md section 5): `bound` says so, `peak` is the
                 non-FMA FMUL+FADD issue rate measured on this GPU in the same run, and `hbm` carries
                 the HBM view of the same kernel against MEASURED_PEAKS.json.
+  fast_mode     side figure (EXACT runs, rank 0): the same workload in FAST mode -- the fused window + FFT-MDCT +
+                quantise + pack kernel named by BASELINE.json's north_star -- with its HBM roofline.
   cpu_baseline  the oracle (C restatement of the reference; the Rust crate cannot be built in this
                 image) timed on this box's host cores on a bounded prefix of the same workload.
 Multi-GPU: the path shards by file / frame range with no collective: every rank
@@ -62,6 +64,7 @@ def parse_args():
                          "fast = FFT-based true MDCT (tolerance class, HBM-roofline showcase)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flac", action="store_true")
+    ap.add_argument("--no-fast-side", action="store_true", help="skip the FAST-mode side figure of the EXACT line")
     ap.add_argument("--flac-seconds", type=float, default=600.0)
     return ap.parse_args()
 
@@ -478,6 +481,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "wall_s_device_region": wall_dev,
     }
 
+    if rank == 0 and not fast and not args.no_fast_side:
+        line["fast_mode"] = bench_fast_side(local_rank, None, args, rows, host_step.pairs, hbm_peak, peak_src)
     if rank == 0 and not args.no_flac:
         line["flac"] = bench_flac(ctx, args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -490,6 +495,59 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_fast_side(device: int, _unused, args, rows: int, pairs: int, hbm_peak: float, peak_src: str) -> dict:
+    """Side figure of the default (EXACT) line: the same workload in FAST mode, i.e. the fused window +
+    FFT-MDCT + quantise + pack kernel that BASELINE.json's north_star names, with its HBM roofline
+    (device-resident, CUDA events, same synthetic input).  Tolerance class -- not part of `value`."""
+    from gapless_lossy_codec_b200 import _ffi
+    from gapless_lossy_codec_b200.codec import Context
+
+    ctx = Context(device, mode=1)
+    L = ctx._lib
+    x = synth(args.seconds)
+    enc_h, dec_h, dpcm = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _ffi.check(L.glc_encoder_new(ctx.handle, SR, C.byref(enc_h)))
+    _ffi.check(L.glc_decoder_new(ctx.handle, CH, SR, C.byref(dec_h)))
+    _ffi.check(L.glc_dev_upload(ctx.handle, x.ctypes.data, x.size, CH, C.byref(dpcm)))
+
+    def step():
+        de, dq = C.c_void_p(), C.c_void_p()
+        ms_e, ms_d = C.c_float(), C.c_float()
+        _ffi.check(L.glc_timer_begin(ctx.handle))
+        _ffi.check(L.glc_dev_encode(enc_h, dpcm, C.byref(de)))
+        _ffi.check(L.glc_timer_end(ctx.handle, C.byref(ms_e)))
+        _ffi.check(L.glc_timer_begin(ctx.handle))
+        _ffi.check(L.glc_dev_decode(dec_h, de, C.byref(dq)))
+        _ffi.check(L.glc_timer_end(ctx.handle, C.byref(ms_d)))
+        L.glc_dev_pcm_free(dq)
+        L.glc_dev_encoded_free(de)
+        return ms_e.value + ms_d.value
+
+    for _ in range(3):
+        step()
+    ctx.enable_kernel_timing(True)
+    ctx.stats_reset()
+    steps = max(3, min(args.steps, 10))
+    ms = sum(step() for _ in range(steps)) / steps
+    st = ctx.stats()
+    ctx.enable_kernel_timing(False)
+    fe_ms = st["kernel_ms"]["fast_encode"] / max(st["launches"]["fast_encode"], 1)
+    fe_bytes = rows * 4096.0 + pairs * 4.0 + rows * 8.0  # SURVEY.md 8(d); `pairs` from the EXACT stream (same order of magnitude)
+    out = {
+        "mode": "FAST (FFT-based true MDCT fused with the quantiser; tolerance class, NOT bit-exact)",
+        "value": args.seconds / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        "roofline": {"kernel": "fast_encode_kernel", "bound": "hbm", "achieved": fe_bytes / (fe_ms * 1e-3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / hbm_peak,
+                     "peak_source": peak_src, "ms_per_launch": fe_ms, "algorithmic_bytes_per_launch": fe_bytes},
+        "kernel_ms_per_step": {k: v / steps for k, v in st["kernel_ms"].items() if v},
+    }
+    L.glc_dev_pcm_free(dpcm)
+    L.glc_encoder_free(enc_h)
+    L.glc_decoder_free(dec_h)
+    ctx.close()
+    return out
 
 
 def bench_flac(ctx, args) -> dict:

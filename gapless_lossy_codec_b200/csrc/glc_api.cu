@@ -778,8 +778,11 @@ struct Wave
 // With group_align, wave boundaries inside a file fall on multiples of that file's frame-group size
 // (quant_frames_per_group), so that the per-group kernels never see half a group.
 template <typename Desc>
+// first_rows (0 = like the others): size of the first wave.  With host buffers the pipeline can only start
+// once the first wave has crossed PCIe, so that one is kept short.
 static std::vector<Wave> plan_waves(const std::vector<Desc> &files, uint64_t tot_frames, uint64_t tot_rows,
-                                    uint64_t target_rows, uint64_t *max_wave_rows, bool group_align = false)
+                                    uint64_t target_rows, uint64_t *max_wave_rows, bool group_align = false,
+                                    uint64_t first_rows = 0)
 {
     const uint32_t n_files = (uint32_t)files.size();
     auto file_of_frame = [&](uint64_t fr) -> uint32_t {
@@ -817,7 +820,7 @@ static std::vector<Wave> plan_waves(const std::vector<Desc> &files, uint64_t tot
         while (lo < hi)
         {
             const uint64_t mid = (lo + hi + 1) >> 1;
-            if (row_of_frame(mid) - r0 <= target_rows)
+            if (row_of_frame(mid) - r0 <= ((waves.empty() && first_rows) ? first_rows : target_rows))
                 lo = mid;
             else
                 hi = mid - 1;
@@ -1063,7 +1066,8 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     if (fast && !host_pcm)
         target_rows = UINT64_MAX; // device-resident: the fused FFT kernel takes the whole batch in one launch
     uint64_t max_wave_rows = 0;
-    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, true);
+    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, true,
+                                               (host_pcm && !c->wave_frames) ? kRowQuantum : 0);
     float *d_atiles = nullptr;
     uint64_t *d_first_group = nullptr;
     // frame groups (max(1, 8/ch) frames of one file): the unit of work of quant_pack and of the FAST kernel
@@ -1665,7 +1669,8 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1);
     uint64_t max_wave_rows = 0;
-    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows);
+    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, false,
+                                               (io && !c->wave_frames) ? kRowQuantum : 0);
     const uint64_t wave_tiles = (max_wave_rows + kImdctBM - 1) / kImdctBM;
 
     CUDA_TRY(dmalloc(&d_files, n_files, cs));
