@@ -542,6 +542,7 @@ struct OlaSrc
 };
 
 constexpr int kOlaMaxCh = 16;
+constexpr int kOlaTileCh = 8; // channel counts whose hop (1024 x ch floats) is staged in shared memory
 
 __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
 {
@@ -651,6 +652,50 @@ __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
             }
             *reinterpret_cast<float4 *>(out + e0) = make_float4(a[0], a[1], a[2], a[3]);
         }
+        return;
+    }
+    if (fast_path && ch <= kOlaTileCh)
+    {
+        // 3..8 channels: per channel, four consecutive samples per thread (16-byte loads from the block
+        // rows), the sums staged interleaved in shared memory, then one coalesced copy to the stream.
+        __shared__ __align__(16) float s_tile[kHop * kOlaTileCh];
+        auto fetch4 = [&](const OlaSrc &d, uint32_t c, uint32_t i0, bool second_half, float v[4]) {
+            v[0] = v[1] = v[2] = v[3] = 0.0f; // no coefficients: +0.0
+            if (d.blk)
+            {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(d.blk + i0));
+                v[0] = b.x;
+                v[1] = b.y;
+                v[2] = b.z;
+                v[3] = b.w;
+            }
+            else if (d.raw)
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t si = (i0 + j + (second_half ? kHop : 0u)) * ch + c; // interleaved read, :633-640
+                    v[j] = si < d.raw_len ? __fdiv_rn((float)d.raw[si], 32767.0f) : 0.0f;
+                }
+        };
+        for (uint32_t c = 0; c < ch; ++c)
+            for (uint32_t i0 = threadIdx.x * 4; i0 < (uint32_t)kHop; i0 += blockDim.x * 4)
+            {
+                float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4];
+                if (has_prev)
+                    fetch4(s_prev[c], c, i0, true, a);
+                if (has_cur)
+                {
+                    fetch4(s_cur[c], c, i0, false, b);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        a[j] = __fadd_rn(a[j], b[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    s_tile[(i0 + j) * ch + c] = a[j];
+            }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x * 4; e < kHop * ch; e += blockDim.x * 4)
+            *reinterpret_cast<float4 *>(out + e) = *reinterpret_cast<const float4 *>(s_tile + e);
         return;
     }
     if (fast_path)
