@@ -1723,6 +1723,10 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         }
         return fr + lo;
     };
+    uint32_t ola_tile_channels = 0;
+    for (const DecFileDesc &f : files)
+        if (f.channels >= 3 && f.channels <= 8)
+            ola_tile_channels = std::max(ola_tile_channels, f.channels);
     std::vector<cudaEvent_t> used_events;
     if (io)
     {
@@ -1847,6 +1851,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             o.hop_begin = hop_id(w.f0);
             o.hop_end = hop_id(w.f1);
             o.out = d_out;
+            o.tile_channels = ola_tile_channels;
             CUDA_TRY(launch_ola(o, cs));
         }
         if (d_out16 && o1 > o0)

@@ -54,7 +54,7 @@ constexpr int kQPWarps = kQPThreads / 32;
 // keeps up to 64 such chains in flight per SM instead of 8.
 //   lane l holds bins 128 j + 4 l + {0..3}, j = 0..7 (eight float4 loads), so the ordered compaction
 //   is a warp scan per j.
-__global__ void __launch_bounds__(kQPThreads) quant_pack_kernel(const QuantPackLaunch p)
+__global__ void __launch_bounds__(kQPThreads, 4) quant_pack_kernel(const QuantPackLaunch p)
 {
     __shared__ float s_sq[kQPWarps][kHop];
     __shared__ float s_base[kQPWarps][kMaxBands];
@@ -544,7 +544,7 @@ struct OlaSrc
 constexpr int kOlaMaxCh = 16;
 constexpr int kOlaTileCh = 8; // channel counts whose hop (1024 x ch floats) is staged in shared memory
 
-__global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
+__global__ void __launch_bounds__(256, 6) ola_kernel(const OlaLaunch p)
 {
     __shared__ OlaSrc s_prev[kOlaMaxCh], s_cur[kOlaMaxCh];
     const uint64_t hop_id = p.hop_begin + blockIdx.x;
@@ -654,11 +654,11 @@ __global__ void __launch_bounds__(256) ola_kernel(const OlaLaunch p)
         }
         return;
     }
-    if (fast_path && ch <= kOlaTileCh)
+    if (fast_path && ch <= p.tile_channels)
     {
         // 3..8 channels: per channel, four consecutive samples per thread (16-byte loads from the block
         // rows), the sums staged interleaved in shared memory, then one coalesced copy to the stream.
-        __shared__ __align__(16) float s_tile[kHop * kOlaTileCh];
+        extern __shared__ __align__(16) float s_tile[]; // kHop * tile_channels floats (launch_ola)
         auto fetch4 = [&](const OlaSrc &d, uint32_t c, uint32_t i0, bool second_half, float v[4]) {
             v[0] = v[1] = v[2] = v[3] = 0.0f; // no coefficients: +0.0
             if (d.blk)
@@ -877,7 +877,9 @@ cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s)
 {
     if (p.hop_end <= p.hop_begin)
         return cudaSuccess;
-    ola_kernel<<<(unsigned)(p.hop_end - p.hop_begin), 256, 0, s>>>(p);
+    // streams with 3..8 channels stage a hop in shared memory; mono / stereo batches need none
+    const size_t smem = (size_t)kHop * std::min<uint32_t>(p.tile_channels, kOlaTileCh) * sizeof(float);
+    ola_kernel<<<(unsigned)(p.hop_end - p.hop_begin), 256, smem, s>>>(p);
     return cudaGetLastError();
 }
 

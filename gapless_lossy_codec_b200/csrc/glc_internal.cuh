@@ -204,6 +204,7 @@ struct OlaLaunch
     uint32_t n_files;
     uint64_t hop_begin, hop_end; // batch-wide hop ids (frame index + file index) produced by this launch
     float *out;               // per file interleaved, (n_frames+1)*1024*ch values at out_off
+    uint32_t tile_channels;   // largest channel count in 3..8 of the batch (0 = none): sizes the shared-memory tile
 };
 cudaError_t launch_ola(const OlaLaunch &p, cudaStream_t s);
 
