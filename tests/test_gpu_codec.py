@@ -308,3 +308,55 @@ def test_foreign_raw_frames_of_any_length(gpu_ctx):
         ref.raw_offset = np.concatenate([[0], np.cumsum([len(b) for b in bodies])]).astype(np.uint64)
         pcm = Decoder(ch, 44100, gpu_ctx).decode(to_product(ref))
         assert_pcm_bits_equal(pcm, oracle.decode(ref), f"short raw frames, {ch} ch")
+
+
+def _slice_frames(enc, f0, n):
+    """frames [f0, f0 + n) of a flat stream as a stream of its own (oracle.EncodedArrays)."""
+    ch = enc.channels
+    r0, r1 = f0 * ch, (f0 + n) * ch
+    p0, p1 = int(enc.pair_offset[r0]), int(enc.pair_offset[r1])
+    q0, q1 = int(enc.raw_offset[f0]), int(enc.raw_offset[f0 + n])
+    return oracle.EncodedArrays(
+        sample_rate=enc.sample_rate, channels=ch, total_samples=n * 1024 * ch, encoder_delay=0, padding=0,
+        original_length=(n + 1) * 1024 * ch, n_frames=n, frame_is_raw=enc.frame_is_raw[f0:f0 + n].copy(),
+        nnz=enc.nnz[r0:r1].copy(), pair_offset=(enc.pair_offset[r0:r1 + 1] - np.uint64(p0)).astype(np.uint64),
+        pair_idx=enc.pair_idx[p0:p1].copy(), pair_q=enc.pair_q[p0:p1].copy(), scales=enc.scales[r0:r1].copy(),
+        raw_offset=(enc.raw_offset[f0:f0 + n + 1] - np.uint64(q0)).astype(np.uint64), raw=enc.raw[q0:q1].copy())
+
+
+def test_full_size_spot_checks_against_oracle(gpu_ctx):
+    """Bit-exactness deep inside a large batch (many row tiles, several pipeline waves), at a size the oracle
+    cannot process whole: windows of a few frames are cut out and checked against the oracle.
+      encode: frames f0+1 .. f0+n-2 of the big stream must equal frames 1 .. n-2 of the oracle's encode of
+              the PCM slice that starts at sample f0*1024 (frame j of the slice then covers the same samples
+              as frame f0+j of the file; the first and last frames of the slice see padding instead);
+      decode: hops f0+1 .. f0+n-1 of the big untrimmed PCM must equal hops 1 .. n-1 of the oracle's decode of
+              the sub-stream made of frames f0 .. f0+n-1 (hop h needs frames h-1 and h only)."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    ch, sr = 2, 44100
+    x = np.tile(signals.music_like(sr, ch, 20.0, seed=12345), 15)  # 5 minutes stereo: 12 920 frames, 3 host waves
+    L = len(x) // ch
+    enc = Encoder(sr, gpu_ctx).encode(x, ch)
+    big = Decoder(ch, sr, gpu_ctx).decode_untrimmed(enc)
+    assert len(big) == (enc.n_frames + 1) * 1024 * ch
+    n = 7
+    rng = np.random.default_rng(1)
+    # around the wave boundaries of the host pipeline (rows 4 736 and 4 736 + 18 944), around raw/sparse
+    # transitions, and at random places
+    trans = np.flatnonzero(np.diff(enc.frame_is_raw.astype(np.int8)) != 0)
+    starts = [2365, 11837, int(trans[0]) - 3, int(trans[len(trans) // 2]) - 3] + \
+        [int(v) for v in rng.integers(10, enc.n_frames - n - 10, 4)]
+    eo = to_oracle(enc)
+    xs = x.reshape(L, ch)
+    for f0 in starts:
+        sl = xs[f0 * 1024:(f0 + n) * 1024 + 512].reshape(-1)
+        ref = oracle.encode(sl, ch, sr)
+        got = _slice_frames(eo, f0 + 1, n - 2)
+        want = _slice_frames(ref, 1, n - 2)
+        assert_encoded_equal(got, want, f"encode window at frame {f0}")
+        sub = _slice_frames(eo, f0, n)
+        pcm = oracle.decode(sub, trimmed=False)
+        a = big[(f0 + 1) * 1024 * ch:(f0 + n) * 1024 * ch]
+        b = pcm[1024 * ch:n * 1024 * ch]
+        assert_pcm_bits_equal(a, b, f"decode window at frame {f0}")
