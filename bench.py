@@ -216,9 +216,19 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         import torch.distributed as dist_mod
 
         torch.cuda.set_device(local_rank)
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: NCCL prints its version banner with printf when the first
+        # communicator is created, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         dist = dist_mod
 
     def barrier():
@@ -481,7 +491,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "wall_s_device_region": wall_dev,
     }
 
-    if rank == 0 and not fast and not args.no_fast_side:
+    if rank == 0 and world == 1 and not fast and not args.no_fast_side:
         line["fast_mode"] = bench_fast_side(local_rank, None, args, rows, host_step.pairs, hbm_peak, peak_src)
     if rank == 0 and not args.no_flac:
         line["flac"] = bench_flac(ctx, args)
