@@ -77,6 +77,7 @@ EXPORTS = [
     "glc_decode_stream_open", "glc_decode_stream_next", "glc_decode_stream_close",
     "glc_flac_encode", "glc_flac_encode_batch", "glc_decode_to_flac", "glc_decode_to_flac_batch",
     "glc_encoded_to_bincode", "glc_encoded_from_bincode",
+    "glc_plan_shards", "glc_encode_batch_sharded", "glc_decode_batch_sharded", "glc_flac_encode_batch_sharded",
     "glc_stats_reset", "glc_stats_get", "glc_stats_enable_kernel_timing",
     "glc_dev_upload", "glc_dev_pcm_free", "glc_dev_encode", "glc_dev_decode",
     "glc_dev_encoded_download", "glc_dev_pcm_download", "glc_dev_encoded_free",
@@ -133,6 +134,11 @@ def load() -> C.CDLL:
         "glc_decode_to_flac_batch": (C.c_int, [vp, u32, pp(pp(Encoded)), u8, pp(pp(u8)), pp(u64)]),
         "glc_encoded_to_bincode": (C.c_int, [vp, pp(Encoded), pp(pp(u8)), pp(u64)]),
         "glc_encoded_from_bincode": (C.c_int, [vp, vp, u64, pp(pp(Encoded))]),
+        "glc_plan_shards": (C.c_int, [u32, pp(u64), u32, pp(u32)]),
+        "glc_encode_batch_sharded": (C.c_int, [pp(vp), u32, u32, pp(vp), pp(u64), pp(u16), pp(pp(Encoded)), pp(u32)]),
+        "glc_decode_batch_sharded": (C.c_int, [pp(vp), u32, u32, pp(pp(Encoded)), pp(fp), pp(u64), pp(u32)]),
+        "glc_flac_encode_batch_sharded": (C.c_int, [pp(vp), u32, u32, pp(vp), pp(u64), pp(u32), pp(u16), u8,
+                                                    pp(pp(u8)), pp(u64), pp(u32)]),
         "glc_stats_reset": (None, [vp]),
         "glc_stats_get": (None, [vp, pp(Stats)]),
         "glc_stats_enable_kernel_timing": (None, [vp, C.c_int]),

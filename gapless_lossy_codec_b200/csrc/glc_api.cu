@@ -757,17 +757,6 @@ static uint64_t frames_for(uint64_t L)
     return (padded_len(L) - kFrame) / kHop + 1; // src/codec.rs:449-455 (L > 512 guaranteed by caller)
 }
 
-static bool is_device_accessible_host(const void *p)
-{
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
-    {
-        (void)cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
 // Contiguous frame ranges of a batch ("waves"): f0..f1 frames, r0..r1 rows.  Waves are sized in
 // multiples of 37 row tiles so that the MDCT grids fill every resident CTA slot (see encode_core).
 struct Wave

@@ -248,15 +248,8 @@ __global__ void __launch_bounds__(kGemmThreads * 8 / NC, 2) exact_gemm_kernel(co
 
 cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
 {
-    static bool configured = false;
     const size_t smem = sizeof(Smem);
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(exact_gemm_kernel<kMdctNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
+    GLC_SET_MAX_DYN_SMEM_ONCE(exact_gemm_kernel<kMdctNC>, smem);
     if (m_tiles == 0)
         return cudaSuccess;
     const uint64_t n_ctas = m_tiles * (kHop / kBN);
@@ -575,15 +568,7 @@ cudaError_t launch_imdct_exact(const ImdctLaunch &l, cudaStream_t s)
     p.n_rows = l.max_slots;
     p.norm = l.norm;
     p.out = l.blocks;
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(imdct_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(ImdctSmem));
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
+    GLC_SET_MAX_DYN_SMEM_ONCE(imdct_sparse_kernel, sizeof(ImdctSmem));
     const uint64_t m_tiles = (l.max_slots + kImdctBM - 1) / kImdctBM;
     if (m_tiles == 0)
         return cudaSuccess;

@@ -148,21 +148,6 @@ __device__ __forceinline__ void dct4_pair(float2 *pair, const LaneTw &tw, int la
     __syncwarp();
 }
 
-__device__ __forceinline__ float warp_max_f(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_sum_f(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 struct GroupGeom
 {
     uint32_t file;
@@ -733,15 +718,7 @@ cudaError_t launch_fast_encode(const FastEncodeLaunch &p, cudaStream_t s)
 {
     if (p.group_end <= p.group_begin)
         return cudaSuccess;
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(fast_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(FastSmem));
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
+    GLC_SET_MAX_DYN_SMEM_ONCE(fast_encode_kernel, sizeof(FastSmem));
     // persistent CTAs: 4 resident per SM, grid-stride over the frame groups
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -755,15 +732,7 @@ cudaError_t launch_fast_decode(const FastDecodeLaunch &p, cudaStream_t s)
 {
     if (p.row_end <= p.row_begin)
         return cudaSuccess;
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(fast_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(FastSmem));
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
+    GLC_SET_MAX_DYN_SMEM_ONCE(fast_decode_kernel, sizeof(FastSmem));
     const uint64_t n = p.row_end - p.row_begin;
     fast_decode_kernel<<<(unsigned)((n + kFastFcs - 1) / kFastFcs), kFastThreads, sizeof(FastSmem), s>>>(p);
     return cudaGetLastError();

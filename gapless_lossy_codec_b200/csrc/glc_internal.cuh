@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <vector>
 
 #include "glc.h"
@@ -85,6 +86,24 @@ struct DevPerceptual
     float noise_floor_factor;
     float pad;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: one process may drive several
+// devices (glc_*_batch_sharded), so "configured" is remembered per device, not per process.
+// `mask` is a static std::atomic<uint64_t> of the call site.
+#define GLC_SET_MAX_DYN_SMEM_ONCE(kernel, bytes)                                                              \
+    do                                                                                                        \
+    {                                                                                                         \
+        static std::atomic<unsigned long long> configured_mask_{0};                                           \
+        int dev_ = 0;                                                                                         \
+        cudaGetDevice(&dev_);                                                                                 \
+        if (!((configured_mask_.load(std::memory_order_acquire) >> (dev_ & 63)) & 1ull))                      \
+        {                                                                                                     \
+            cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+            if (e_ != cudaSuccess)                                                                            \
+                return e_;                                                                                    \
+            configured_mask_.fetch_or(1ull << (dev_ & 63), std::memory_order_release);                        \
+        }                                                                                                     \
+    } while (0)
 
 // ---- kernel launchers (each returns the launch error) ----
 struct MdctLaunch

@@ -85,3 +85,109 @@ def encode_sharded(files: Sequence, channels: Sequence[int], sample_rate: int, r
         for idx, enc in part:
             out[idx] = enc
     return out
+
+
+# ------------------------------------------------------------------ one process, several devices
+
+
+def encode_batch_devices(encoders: Sequence, files: Sequence, channels: Sequence[int]):
+    """glc_encode_batch_sharded: the files of one call split over `encoders` (one Encoder per context,
+    normally one context per GPU) by longest-processing-time-first in the library, one host thread per
+    context, outputs in input order.  Returns (list of EncodedAudio, shard index per file)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _ffi
+    from .codec import EncodedAudio
+
+    lib = encoders[0]._lib
+    n, k = len(files), len(encoders)
+    arrs = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1) for f in files]
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    ns = (C.c_uint64 * n)(*[a.size for a in arrs])
+    chs = (C.c_uint16 * n)(*[int(c) for c in channels])
+    encs = (C.c_void_p * k)(*[e.handle.value for e in encoders])
+    outs = (C.POINTER(_ffi.Encoded) * n)()
+    shard_of = (C.c_uint32 * n)()
+    _ffi.check(lib.glc_encode_batch_sharded(encs, k, n, ptrs, ns, chs, outs, shard_of))
+    res = []
+    try:
+        for i in range(n):
+            res.append(EncodedAudio._from_struct(outs[i].contents))
+    finally:
+        for i in range(n):
+            if outs[i]:
+                lib.glc_encoded_free(encoders[shard_of[i]].ctx.handle, outs[i])
+    return res, list(shard_of)
+
+
+def decode_batch_devices(decoders: Sequence, encoded: Sequence):
+    """glc_decode_batch_sharded: see encode_batch_devices.  Returns (list of PCM arrays, shard per file)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _ffi
+
+    lib = decoders[0]._lib
+    n, k = len(encoded), len(decoders)
+    structs = [e._as_struct() for e in encoded]
+    ptrs = (C.POINTER(_ffi.Encoded) * n)(*[C.pointer(s) for s in structs])
+    decs = (C.c_void_p * k)(*[d.handle.value for d in decoders])
+    outs = (C.POINTER(C.c_float) * n)()
+    ns = (C.c_uint64 * n)()
+    shard_of = (C.c_uint32 * n)()
+    _ffi.check(lib.glc_decode_batch_sharded(decs, k, n, ptrs, outs, ns, shard_of))
+    res = []
+    for i in range(n):
+        try:
+            res.append(np.ctypeslib.as_array(outs[i], shape=(ns[i],)).copy() if ns[i] else np.zeros(0, np.float32))
+        finally:
+            lib.glc_free(decoders[shard_of[i]].ctx.handle, outs[i])
+    return res, list(shard_of)
+
+
+def flac_encode_batch_devices(contexts: Sequence, files: Sequence, sample_rates: Sequence[int], channels: Sequence[int],
+                              level: int = 5):
+    """glc_flac_encode_batch_sharded.  Returns (list of FLAC byte strings, shard per file)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _ffi
+
+    lib = contexts[0]._lib
+    n, k = len(files), len(contexts)
+    arrs = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1) for f in files]
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    ns = (C.c_uint64 * n)(*[a.size for a in arrs])
+    srs = (C.c_uint32 * n)(*[int(v) for v in sample_rates])
+    chs = (C.c_uint16 * n)(*[int(c) for c in channels])
+    ctxs = (C.c_void_p * k)(*[c.handle.value for c in contexts])
+    outs = (C.POINTER(C.c_uint8) * n)()
+    lens = (C.c_uint64 * n)()
+    shard_of = (C.c_uint32 * n)()
+    _ffi.check(lib.glc_flac_encode_batch_sharded(ctxs, k, n, ptrs, ns, srs, chs, int(level), outs, lens, shard_of))
+    res = []
+    for i in range(n):
+        try:
+            res.append(C.string_at(outs[i], lens[i]))
+        finally:
+            lib.glc_free(contexts[shard_of[i]].handle, outs[i])
+    return res, list(shard_of)
+
+
+def plan_shards_native(work: Sequence[int], world: int) -> List[int]:
+    """glc_plan_shards (the C++ planner the *_sharded calls use): shard index per file."""
+    import ctypes as C
+
+    from . import _ffi
+
+    lib = _ffi.load()
+    n = len(work)
+    w = (C.c_uint64 * max(n, 1))(*[int(v) for v in work])
+    out = (C.c_uint32 * max(n, 1))()
+    _ffi.check(lib.glc_plan_shards(n, w, int(world), out))
+    return list(out)[:n]
+

@@ -32,7 +32,7 @@ extern "C" {
 #define GLC_FRAME_SIZE 2048u      /* src/codec.rs:15 */
 #define GLC_HOP_SIZE 1024u        /* src/codec.rs:16 */
 #define GLC_FRAMES_PER_CHUNK 500u /* src/codec.rs:18 */
-#define GLC_ABI_VERSION 5u
+#define GLC_ABI_VERSION 6u
 
 typedef enum glc_status
 {
@@ -197,6 +197,29 @@ glc_status glc_decode_to_flac(glc_decoder *dec, const glc_encoded *enc, uint8_t 
                               uint64_t *len);
 glc_status glc_decode_to_flac_batch(glc_decoder *dec, uint32_t n_files, const glc_encoded *const *enc,
                                     uint8_t level, uint8_t **bytes /* [n_files] */, uint64_t *len /* [n_files] */);
+
+/* ------------------------------------------------- one call, several devices */
+
+/* The path shards by file with no exchange step: the reference loops over files (src/main.rs:546-583)
+ * and parallelises inside a file (rayon, src/codec.rs:462, 620).  These calls split the files of ONE
+ * batch over n_shards encoders / decoders / contexts (normally one per GPU of the box, each made from its
+ * own glc_ctx), run the ordinary batch call of every shard on its own host thread and hand the outputs
+ * back in input order -- a host-side gather, no collective.  shard_of[i] (required) receives the shard
+ * that processed file i: its context owns out[i] / pcm[i] / bytes[i] and must be passed to
+ * glc_encoded_free / glc_free.  On failure nothing is returned (outputs already produced stay owned by
+ * their contexts until those are destroyed). */
+glc_status glc_plan_shards(uint32_t n_files, const uint64_t *weights, uint32_t n_shards, uint32_t *shard_of);
+glc_status glc_encode_batch_sharded(glc_encoder *const *encs, uint32_t n_shards, uint32_t n_files,
+                                    const float *const *pcm, const uint64_t *n_samples, const uint16_t *channels,
+                                    glc_encoded **out /* [n_files] */, uint32_t *shard_of /* [n_files] */);
+glc_status glc_decode_batch_sharded(glc_decoder *const *decs, uint32_t n_shards, uint32_t n_files,
+                                    const glc_encoded *const *enc, float **pcm /* [n_files] */,
+                                    uint64_t *n_samples /* [n_files] */, uint32_t *shard_of /* [n_files] */);
+glc_status glc_flac_encode_batch_sharded(glc_ctx *const *ctxs, uint32_t n_shards, uint32_t n_files,
+                                         const float *const *pcm, const uint64_t *n_samples,
+                                         const uint32_t *sample_rate, const uint16_t *channels, uint8_t level,
+                                         uint8_t **bytes /* [n_files] */, uint64_t *len /* [n_files] */,
+                                         uint32_t *shard_of /* [n_files] */);
 
 /* ---------------------------------------------------------------- container */
 

@@ -360,3 +360,48 @@ def test_full_size_spot_checks_against_oracle(gpu_ctx):
         a = big[(f0 + 1) * 1024 * ch:(f0 + n) * 1024 * ch]
         b = pcm[1024 * ch:n * 1024 * ch]
         assert_pcm_bits_equal(a, b, f"decode window at frame {f0}")
+
+
+def test_sharded_batch_over_several_contexts(gpu_ctx):
+    """glc_*_batch_sharded: one call, the files split over several contexts (here: the visible devices, or two
+    contexts on the one device), one host thread per context, outputs in input order and identical to the
+    single-context batch."""
+    import ctypes as C
+
+    from gapless_lossy_codec_b200 import Decoder, Encoder, _ffi, shard
+    from gapless_lossy_codec_b200.codec import Context
+
+    n_dev = C.c_int()
+    _ffi.load().glc_device_count(C.byref(n_dev))
+    devs = list(range(min(n_dev.value, 4))) if n_dev.value > 1 else [0, 0]
+    ctxs = [Context(d) for d in devs]
+    try:
+        files = [signals.music_like(44100, 2, 0.6), signals.sine(440, 44100, 2, 2.0), signals.white_noise(44100, 2, 0.3, 5),
+                 signals.sweep(100, 8000, 44100, 2, 1.1), signals.sine(880, 44100, 1, 0.4), signals.music_like(44100, 1, 0.9),
+                 signals.sweep(300, 3000, 48000, 6, 0.2)]
+        chans = [2, 2, 2, 2, 1, 1, 6]
+        encs = [Encoder(44100, c) for c in ctxs]
+        got, where = shard.encode_batch_devices(encs, files, chans)
+        assert len(set(where)) == len(ctxs), where  # every context got work
+        want = Encoder(44100, gpu_ctx).encode_batch(files, chans)
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert_encoded_equal(g, to_oracle(w), f"sharded encode, file {i}")
+        decs = [Decoder(2, 44100, c) for c in ctxs]
+        pcm, where_d = shard.decode_batch_devices(decs, got)
+        ref = Decoder(2, 44100, gpu_ctx).decode_batch(want)
+        for i, (a, b) in enumerate(zip(pcm, ref)):
+            assert_pcm_bits_equal(a, b, f"sharded decode, file {i}")
+            assert len(a) == len(files[i])
+        from gapless_lossy_codec_b200 import flac
+
+        fl, _ = shard.flac_encode_batch_devices(ctxs, files[:6], [44100] * 6, chans[:6], 5)
+        for i in range(6):
+            assert fl[i] == flac.encode_flac_with_level(files[i], 44100, chans[i], 5, gpu_ctx), f"sharded flac, file {i}"
+        # a failing shard fails the call with that shard's message
+        with pytest.raises(Exception) as e:
+            shard.encode_batch_devices(encs, [files[0], np.zeros(100, np.float32)], [2, 1])
+        assert "shard" in str(e.value)
+    finally:
+        del encs
+        for c in ctxs:
+            c.close()

@@ -89,3 +89,22 @@ def test_world2_gloo_shard_and_gather():
         assert p.exitcode == 0
     got = dict(q.get(timeout=5) for _ in range(2))
     assert sum(sum(c) for c in got.values()) == 5 and all(len(c) == 1 for c in got.values())
+
+
+def test_native_planner_matches_python_planner():
+    """glc_plan_shards (C++, used by the glc_*_batch_sharded calls) and shard.plan_by_file make the same plan."""
+    import numpy as np
+
+    from gapless_lossy_codec_b200 import shard
+
+    rng = np.random.default_rng(3)
+    for n, world in [(1, 1), (5, 2), (40, 8), (1000, 8), (7, 16)]:
+        work = [int(v) for v in rng.integers(1, 5000, n)]
+        work[0] = work[-1]  # ties
+        native = shard.plan_shards_native(work, world)
+        plan = shard.plan_by_file(work, world)
+        want = [None] * n
+        for r, files in enumerate(plan):
+            for i in files:
+                want[i] = r
+        assert native == want, (n, world)
