@@ -622,6 +622,27 @@ TEST("codec.rs", streaming_chunks_and_progress)
            "Decoding percentage %f (codec.rs:712: idx is still 499 when the first chunk is flushed)", events[1].value);
 }
 
+TEST("main.rs", decode_to_wav_samples_and_flac_bytes)
+{ // `glc -d x.glc` (src/main.rs:55-113): decode, then export_to_wav (convert_f32_to_i16, src/audio.rs:11-16) or
+  // export_to_flac_with_level; the fused calls must equal the two-step paths
+    auto samples = generate_frequency_sweep(300.0f, 5000.0f, 44100, 2, 1.5f);
+    Encoder encoder(44100);
+    EncodedAudio encoded = encoder.encode(samples, 2);
+    Decoder decoder(2, 44100);
+    auto pcm = decoder.decode(encoded);
+    auto pcm16 = decoder.decode_pcm16(encoded);
+    ASSERT_EQ(pcm16.size(), pcm.size(), "16-bit sample count");
+    for (size_t i = 0; i < pcm.size(); ++i)
+    {
+        const float v = pcm[i] * 32767.0f;
+        const int16_t want = (int16_t)std::fmin(std::fmax(v, -32768.0f), 32767.0f); // truncation, as Rust's `as i16`
+        ASSERT(pcm16[i] == want, "sample %zu: %d vs %d", i, (int)pcm16[i], (int)want);
+    }
+    auto fused = decoder.decode_to_flac(encoded, 8);
+    auto two_step = glc::flac::encode_flac_with_level(pcm, 44100, 2, 8);
+    ASSERT(fused == two_step, "decode_to_flac differs from decode + encode_flac_with_level (%zu vs %zu bytes)", fused.size(), two_step.size());
+}
+
 TEST("codec.rs", short_input_is_an_error_not_a_crash)
 { // the reference panics on <= 512 samples per channel (codec.rs:449-452, :474)
     Encoder encoder(44100);
