@@ -178,7 +178,7 @@ struct GatherLaunch
 cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s);
 
 // Decode front end: which rows go through the IMDCT at all (sparse frames with at least one pair),
-// their compaction into tiles of kImdctBM rows, and per tile the ascending union of coefficient indices.
+// their compaction into tiles of kImdctBM rows, and per tile the step masks / stage list / A stages of the IMDCT.
 struct DequantLaunch
 {
     const glc_pair *pairs;

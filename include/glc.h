@@ -238,8 +238,8 @@ enum
     GLC_K_QUANT_PACK = 1,   /* scale, masking thresholds, quantize, ordered compaction, raw decision */
     GLC_K_SCAN = 2,
     GLC_K_GATHER = 3,       /* stream compaction + raw-PCM frames */
-    GLC_K_DEQUANT = 4,      /* row selection, per-tile index union, sparse -> compacted A tiles (4 launches) */
-    GLC_K_IMDCT_EXACT = 5,  /* direct IMDCT + synthesis window (dominant decode kernel) */
+    GLC_K_DEQUANT = 4,      /* row selection, per-tile step masks and stage list, sparse -> A stages (4 launches) */
+    GLC_K_IMDCT_EXACT = 5,  /* direct IMDCT (sparse per 2-row warp) + synthesis window (dominant decode kernel) */
     GLC_K_OLA = 6,          /* raw frames, overlap-add, interleave */
     GLC_K_FLAC_BLOCK = 7,   /* one CTA per FLAC block */
     GLC_K_FLAC_GATHER = 8,
