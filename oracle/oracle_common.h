@@ -14,7 +14,7 @@
  * (ported in tests/test_oracle_*.py), (b) independent anchors: RFC 9639
  * decodability with CRC-8/CRC-16/MD5 verification, hashlib MD5, README size
  * example, (c) bit-for-bit agreement with a second restatement written separately in numpy
- * (codec_restatement_np.py, tests/test_oracle_restatements.py).
+ * / plain Python (codec_restatement_np.py, flac_restatement_py.py, tests/test_oracle_restatements.py).
  *
  * Build flags that matter: -O2 -ffp-contract=off -fno-fast-math (Rust never
  * contracts a*b+c and never reassociates float reductions).

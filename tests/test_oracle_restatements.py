@@ -70,3 +70,37 @@ def test_encode_and_decode_agree(name, x, ch, sr):
     pb = oracle.decode(b, literal_imdct=True)
     assert pa.size == pb.size == x.size
     assert np.array_equal(pa.view(np.uint32), np.asarray(pb, np.float32).view(np.uint32)), "decoded PCM bits"
+
+
+# ---------------------------------------------------------------------------- FLAC
+
+from oracle import flac_restatement_py as fpy  # noqa: E402
+
+
+def _flac_cases():
+    rng = np.random.default_rng(7)
+    return [
+        ("sine_mono_44k", signals.sine(440, 44100, 1, 0.12), 44100, 1),               # 5292 samples: 4096 + tail 1196
+        ("stereo_48k", signals.sweep(100, 6000, 48000, 2, 0.06), 48000, 2),
+        ("noise_loud_clipping", (rng.standard_normal(3000) * 0.9).astype(np.float32), 22050, 1),
+        ("six_channels_odd_rate", (rng.standard_normal(6 * 700) * 0.2).astype(np.float32), 37000, 6),
+        ("minimum_16_samples", np.linspace(-1, 1, 16, dtype=np.float32), 8000, 1),     # block size 16: 8-bit size code
+        ("uncommon_block_300", signals.sine(300, 96000, 1, 300 / 96000), 96000, 1),    # block size 300: 16-bit size code
+        ("silence", np.zeros(2000, np.float32), 44100, 2),
+    ]
+
+
+@pytest.mark.parametrize("level", range(9))
+def test_flac_restatements_agree(level):
+    for name, x, sr, ch in _flac_cases():
+        a = fpy.encode_flac_with_level(x, sr, ch, level)
+        b = oracle.flac_encode(x, sr, ch, level)
+        assert a == b, (name, level, len(a), len(b), next((i for i, (p, q) in enumerate(zip(a, b)) if p != q), None))
+
+
+def test_flac_crcs_agree():
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 7, 300):
+        data = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        assert fpy.crc8(data) == oracle.crc8(data)
+        assert fpy.crc16(data) == oracle.crc16(data)
