@@ -104,3 +104,38 @@ def test_flac_crcs_agree():
         data = bytes(rng.integers(0, 256, n, dtype=np.uint8))
         assert fpy.crc8(data) == oracle.crc8(data)
         assert fpy.crc16(data) == oracle.crc16(data)
+
+
+# ------------------------------------------------------------------ .glc container (bincode 1.3 image)
+
+
+def _bincode_py(e) -> bytes:
+    """save_encoded's byte image (src/codec.rs:774-779) from the derive order of the structs (:31-69): bincode 1.3
+    defaults = little-endian fixed-width integers, u64 length prefix per Vec, one tag byte per Option."""
+    import struct
+
+    ch = e.channels
+    out = [struct.pack("<IHQ", e.sample_rate, ch, e.total_samples), struct.pack("<Q", e.n_frames)]
+    for f in range(e.n_frames):
+        if e.frame_is_raw[f]:
+            body = e.raw[int(e.raw_offset[f]):int(e.raw_offset[f + 1])]
+            out += [struct.pack("<Q", 0), struct.pack("<Q", 0), b"\x01", struct.pack("<Q", len(body)),
+                    body.astype("<i2").tobytes()]
+        else:
+            out.append(struct.pack("<Q", ch))
+            for c in range(ch):
+                lo, hi = int(e.pair_offset[f * ch + c]), int(e.pair_offset[f * ch + c + 1])
+                out.append(struct.pack("<Q", hi - lo))
+                pr = np.empty(hi - lo, dtype=[("i", "<u2"), ("q", "<i2")])
+                pr["i"], pr["q"] = e.pair_idx[lo:hi], e.pair_q[lo:hi]
+                out.append(pr.tobytes())
+            out += [struct.pack("<Q", ch), e.scales[f * ch:(f + 1) * ch].astype("<f4").tobytes(), b"\x00"]
+    out.append(struct.pack("<IIQ", e.encoder_delay, e.padding, e.original_length))
+    return b"".join(out)
+
+
+def test_bincode_image_agrees():
+    x = np.concatenate([signals.music_like(44100, 2, 0.3), signals.white_noise(44100, 2, 0.2, 4)])
+    e = oracle.encode(x, 2, 44100)
+    assert e.frame_is_raw.any() and not e.frame_is_raw.all()
+    assert _bincode_py(e) == oracle.bincode_serialize(e)
