@@ -112,7 +112,18 @@ __global__ void __launch_bounds__(kQPThreads, 4) quant_pack_kernel(const QuantPa
         {
             const int blo = pm.band_edges[b], bhi = pm.band_edges[b + 1];
             float acc = 0.0f;
-            for (int k = blo; k < bhi; ++k)
+            int k = blo;
+            // same left-to-right order; the long top band reads eight squares ahead of the add chain
+            for (; k < bhi && (k & 3); ++k)
+                acc = __fadd_rn(acc, s_sq[warp][k]);
+            for (; k + 8 <= bhi; k += 8)
+            {
+                const float4 q0 = *reinterpret_cast<const float4 *>(&s_sq[warp][k]);
+                const float4 q1 = *reinterpret_cast<const float4 *>(&s_sq[warp][k + 4]);
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q0.x), q0.y), q0.z), q0.w);
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q1.x), q1.y), q1.z), q1.w);
+            }
+            for (; k < bhi; ++k)
                 acc = __fadd_rn(acc, s_sq[warp][k]);
             const float energy = sqrtf(__fdiv_rn(acc, pm.band_cnt[b]));
             // energy * 0.01 * compression_factor * perceptual_factor, left to right (:223)
