@@ -668,19 +668,30 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_decode_kernel(const Fast
             const float *v = reinterpret_cast<const float *>(sm.u[fa]) + h * kCoefStride;
             float *out = p.blocks + (row0 + fa + h) * kFrame;
             // unfold (transpose of the fold) + synthesis window           src/codec.rs:672-675
+            // four consecutive outputs per lane: [0,512) = v[512+i], [512,1536) = -v[1535-i] (read reversed),
+            // [1536,2048) = -v[i-1536]; the segment is uniform over the warp in every iteration
 #pragma unroll 4
-            for (int i = lane; i < kFrame; i += 32)
+            for (int it = 0; it < kFrame / 128; ++it)
             {
-                float val;
-                if (i < 512)
-                    val = v[512 + i];
-                else if (i < 1024)
-                    val = -v[512 + (1023 - i)];
-                else if (i < 1536)
-                    val = -v[1535 - i];
+                const int i0 = it * 128 + lane * 4;
+                const float4 w = __ldg(reinterpret_cast<const float4 *>(p.window + i0));
+                float4 r;
+                if (it < 4)
+                {
+                    const float4 q = *reinterpret_cast<const float4 *>(v + 512 + i0);
+                    r = make_float4(q.x * w.x, q.y * w.y, q.z * w.z, q.w * w.w);
+                }
+                else if (it < 12)
+                {
+                    const float4 q = *reinterpret_cast<const float4 *>(v + 1532 - i0);
+                    r = make_float4(-q.w * w.x, -q.z * w.y, -q.y * w.z, -q.x * w.w);
+                }
                 else
-                    val = -v[i - 1536];
-                out[i] = val * __ldg(p.window + i);
+                {
+                    const float4 q = *reinterpret_cast<const float4 *>(v + i0 - 1536);
+                    r = make_float4(-q.x * w.x, -q.y * w.y, -q.z * w.z, -q.w * w.w);
+                }
+                *reinterpret_cast<float4 *>(out + i0) = r;
             }
         }
         __syncwarp();
