@@ -296,13 +296,32 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
                     const float c00 = lo_half ? -wa : wo, c01 = lo_half ? -wo : -wa;
                     const float c10 = lo_half ? wo : -wa, c11 = lo_half ? -wa : -wo;
                     float x[kFastFcs][4];
-#pragma unroll
-                    for (int fc = 0; fc < kFastFcs; ++fc)
+                    if (ich == 2)
                     {
-                        x[fc][0] = __ldg(q0 + foff[fc]);
-                        x[fc][1] = __ldg(q1 + foff[fc]);
-                        x[fc][2] = __ldg(q2 + foff[fc]);
-                        x[fc][3] = __ldg(q3 + foff[fc]);
+                        // stereo: the two channels of a frame sit side by side, one 8-byte load serves both
+#pragma unroll
+                        for (int fc = 0; fc < kFastFcs; fc += 2)
+                        {
+                            const float2 a0 = __ldg(reinterpret_cast<const float2 *>(q0 + foff[fc]));
+                            const float2 a1 = __ldg(reinterpret_cast<const float2 *>(q1 + foff[fc]));
+                            const float2 a2 = __ldg(reinterpret_cast<const float2 *>(q2 + foff[fc]));
+                            const float2 a3 = __ldg(reinterpret_cast<const float2 *>(q3 + foff[fc]));
+                            x[fc][0] = a0.x, x[fc + 1][0] = a0.y;
+                            x[fc][1] = a1.x, x[fc + 1][1] = a1.y;
+                            x[fc][2] = a2.x, x[fc + 1][2] = a2.y;
+                            x[fc][3] = a3.x, x[fc + 1][3] = a3.y;
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int fc = 0; fc < kFastFcs; ++fc)
+                        {
+                            x[fc][0] = __ldg(q0 + foff[fc]);
+                            x[fc][1] = __ldg(q1 + foff[fc]);
+                            x[fc][2] = __ldg(q2 + foff[fc]);
+                            x[fc][3] = __ldg(q3 + foff[fc]);
+                        }
                     }
 #pragma unroll
                     for (int fc = 0; fc < kFastFcs; ++fc)
