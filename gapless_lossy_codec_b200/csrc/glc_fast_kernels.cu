@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const Fast
 // ------------------------------------------------------------------ decode
 
 // One CTA per 8 rows: dequantise into the (c[2n], c[N-1-2n]) layout, DCT-IV, unfold, synthesis window.
-__global__ void __launch_bounds__(kFastThreads, 4) fast_decode_kernel(const FastDecodeLaunch p)
+__global__ void __launch_bounds__(kFastThreads, 5) fast_decode_kernel(const FastDecodeLaunch p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
