@@ -630,6 +630,7 @@ void pinned_release(glc_ctx *ctx, void *p) { ctx->pool.release(p); }
 cudaError_t dev_alloc(glc_ctx *ctx, void **out, size_t bytes, cudaStream_t s) { return ctx->dpool.alloc(out, bytes, s); }
 void dev_free(glc_ctx *ctx, void *p, cudaStream_t s) { ctx->dpool.release(p, s); }
 int ctx_device(glc_ctx *ctx) { return ctx->device; }
+glc_ctx *decoder_ctx(glc_decoder *dec) { return dec->ctx; }
 cudaStream_t ctx_compute_stream(glc_ctx *ctx) { return ctx->compute; }
 cudaStream_t ctx_d2h_stream(glc_ctx *ctx) { return ctx->d2h; }
 void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n) { ctx->stats.launches[kernel_id] += n; }
@@ -742,6 +743,38 @@ static cudaError_t dmalloc_impl(glc_ctx *c, T **p, size_t count, cudaStream_t s)
     *p = nullptr;
     return c->dpool.alloc((void **)p, std::max<size_t>(count, 1) * sizeof(T), s);
 }
+
+// Device-pool blocks owned by one call: everything still held is returned to the pool when the scope
+// ends, on every exit path (a failing CUDA_TRY included); keep() hands a block to the caller instead.
+struct DevScope
+{
+    glc_ctx *c;
+    cudaStream_t s;
+    std::vector<void *> held;
+    DevScope(glc_ctx *ctx, cudaStream_t st) : c(ctx), s(st) {}
+    DevScope(const DevScope &) = delete;
+    DevScope &operator=(const DevScope &) = delete;
+    template <typename T>
+    cudaError_t alloc(T **p, size_t count)
+    {
+        cudaError_t e = dmalloc_impl(c, p, count, s);
+        if (e == cudaSuccess)
+            held.push_back((void *)*p);
+        return e;
+    }
+    void keep(void *p)
+    {
+        for (auto &h : held)
+            if (h == p)
+                h = nullptr;
+    }
+    ~DevScope()
+    {
+        for (void *h : held)
+            if (h)
+                c->dpool.release(h, s);
+    }
+};
 
 static uint64_t padded_len(uint64_t L)
 {
@@ -1013,17 +1046,24 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     const uint32_t n_files = (uint32_t)files.size();
     PhaseTrace tr("encode", cs);
 
+    DevScope ds(c, cs); // scratch of this call: back to the pool on every exit path
     FileDesc *d_files = nullptr;
-    CUDA_TRY(dmalloc(&d_files, n_files, cs));
+    CUDA_TRY(ds.alloc(&d_files, n_files));
     CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(FileDesc) * n_files, cudaMemcpyHostToDevice, cs));
     c->stats.h2d_bytes += sizeof(FileDesc) * n_files;
 
     glc_dev_encoded *de = new glc_dev_encoded();
+    *out = de; // owned by the caller from here on, also when a later step fails (it frees what is set)
     de->ctx = c;
     de->sample_rate = enc->sample_rate;
     de->files = files;
     de->n_rows = tot_rows;
     de->n_frames = tot_frames;
+    de->d_is_raw = nullptr;
+    de->d_nnz = nullptr;
+    de->d_pair_off = nullptr;
+    de->d_scales = nullptr;
+    de->d_raw_off = nullptr;
     de->d_pairs = nullptr;
     de->d_raw = nullptr;
     de->n_pairs = de->n_raw = 0;
@@ -1036,8 +1076,8 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     CUDA_TRY(dmalloc(&de->d_pair_off, tot_rows + 1, cs));
     CUDA_TRY(dmalloc(&de->d_scales, tot_rows, cs));
     CUDA_TRY(dmalloc(&de->d_raw_off, tot_frames + 1, cs));
-    CUDA_TRY(dmalloc(&d_slots, tot_rows * kHop, cs));
-    CUDA_TRY(dmalloc(&d_raw_len, tot_frames, cs));
+    CUDA_TRY(ds.alloc(&d_slots, tot_rows * kHop));
+    CUDA_TRY(ds.alloc(&d_raw_len, tot_frames));
     // the compact outputs are produced wave by wave, so they are sized for the worst case
     // (every coefficient kept / every frame raw); the live totals stay on the device
     CUDA_TRY(dmalloc(&de->d_pairs, tot_rows * kHop, cs));
@@ -1082,12 +1122,12 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         }
         return first_group[lo] + (fr - files[lo].first_frame) / quant_frames_per_group(files[lo].channels);
     };
-    CUDA_TRY(dmalloc(&d_first_group, n_files + 1, cs));
+    CUDA_TRY(ds.alloc(&d_first_group, n_files + 1));
     CUDA_TRY(cudaMemcpyAsync(d_first_group, first_group.data(), 8 * (n_files + 1), cudaMemcpyHostToDevice, cs));
     if (!fast)
     {
-        CUDA_TRY(dmalloc(&d_coefs, max_wave_rows * kHop, cs));
-        CUDA_TRY(dmalloc(&d_atiles, mdct_a_tile_floats(max_wave_rows), cs));
+        CUDA_TRY(ds.alloc(&d_coefs, max_wave_rows * kHop));
+        CUDA_TRY(ds.alloc(&d_atiles, mdct_a_tile_floats(max_wave_rows)));
     }
     tr.mark("alloc");
 
@@ -1316,14 +1356,6 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     if (ev_copy)
         c->ev_free.push_back(ev_copy);
     tr.mark("waves");
-    dfree(d_slots, cs);
-    dfree(d_raw_len, cs);
-    dfree(d_coefs, cs);
-    dfree(d_atiles, cs);
-    dfree(d_first_group, cs);
-    dfree(d_files, cs);
-    tr.mark("free");
-    *out = de;
     return GLC_OK;
 }
 
@@ -1366,6 +1398,28 @@ static glc_status download_encoded(glc_dev_encoded *de, EncodeHostOut *ho, glc_e
     EncodedBlock *blk = new EncodedBlock();
     blk->ctx = c;
     blk->refs = 0;
+    size_t n_boxes = 0;
+    // a failure below releases the block (pinned buffers included) and the boxes already handed out
+    auto fail_cleanup = [&]() {
+        for (size_t i = 0; i < n_boxes; ++i)
+        {
+            delete reinterpret_cast<EncodedBox *>(out[i]);
+            out[i] = nullptr;
+        }
+        blk->refs = 1;
+        block_unref(blk);
+    };
+#define DL_TRY(expr)                                                                                       \
+    do                                                                                                     \
+    {                                                                                                      \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+        {                                                                                                  \
+            fail_cleanup();                                                                                \
+            return fail(GLC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                        __LINE__);                                                                         \
+        }                                                                                                  \
+    } while (0)
     auto pin = [&](size_t bytes) -> void * {
         void *p = c->pool.alloc(bytes);
         if (p)
@@ -1401,21 +1455,21 @@ static glc_status download_encoded(glc_dev_encoded *de, EncodeHostOut *ho, glc_e
         block_unref(blk);
         return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
     }
-    CUDA_TRY(cudaMemcpyAsync(h_is_raw, de->d_is_raw, F, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaMemcpyAsync(h_nnz, de->d_nnz, R * 4, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaMemcpyAsync(h_pair_off, de->d_pair_off, (R + 1) * 8, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaMemcpyAsync(h_scales, de->d_scales, R * 4, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaMemcpyAsync(h_raw_off, de->d_raw_off, (F + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    DL_TRY(cudaMemcpyAsync(h_is_raw, de->d_is_raw, F, cudaMemcpyDeviceToHost, cs));
+    DL_TRY(cudaMemcpyAsync(h_nnz, de->d_nnz, R * 4, cudaMemcpyDeviceToHost, cs));
+    DL_TRY(cudaMemcpyAsync(h_pair_off, de->d_pair_off, (R + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    DL_TRY(cudaMemcpyAsync(h_scales, de->d_scales, R * 4, cudaMemcpyDeviceToHost, cs));
+    DL_TRY(cudaMemcpyAsync(h_raw_off, de->d_raw_off, (F + 1) * 8, cudaMemcpyDeviceToHost, cs));
     if (!ho)
     {
         if (de->n_pairs)
-            CUDA_TRY(cudaMemcpyAsync(h_pairs, de->d_pairs, de->n_pairs * 4, cudaMemcpyDeviceToHost, cs));
+            DL_TRY(cudaMemcpyAsync(h_pairs, de->d_pairs, de->n_pairs * 4, cudaMemcpyDeviceToHost, cs));
         if (de->n_raw)
-            CUDA_TRY(cudaMemcpyAsync(h_raw, de->d_raw, de->n_raw * 2, cudaMemcpyDeviceToHost, cs));
+            DL_TRY(cudaMemcpyAsync(h_raw, de->d_raw, de->n_raw * 2, cudaMemcpyDeviceToHost, cs));
         c->stats.d2h_bytes += de->n_pairs * 4 + de->n_raw * 2;
     }
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    CUDA_TRY(cudaStreamSynchronize(c->d2h));
+    DL_TRY(cudaStreamSynchronize(cs));
+    DL_TRY(cudaStreamSynchronize(c->d2h));
     c->stats.d2h_bytes += F + R * 4 + (R + 1) * 8 + R * 4 + (F + 1) * 8;
 
     const size_t nf = de->files.size();
@@ -1451,7 +1505,14 @@ static glc_status download_encoded(glc_dev_encoded *de, EncodeHostOut *ho, glc_e
             uint64_t *po = (uint64_t *)malloc((rows + 1) * 8);
             uint64_t *ro = (uint64_t *)malloc(((uint64_t)fd.n_frames + 1) * 8);
             if (!po || !ro)
+            {
+                free(po);
+                free(ro);
+                delete box;
+                blk->refs--;
+                fail_cleanup();
                 return fail(GLC_ERR_NO_MEMORY, "out of host memory");
+            }
             blk->heap.push_back(po);
             blk->heap.push_back(ro);
             const uint64_t pb = h_pair_off[fd.first_row], rb = h_raw_off[fd.first_frame];
@@ -1463,8 +1524,10 @@ static glc_status download_encoded(glc_dev_encoded *de, EncodeHostOut *ho, glc_e
             e.raw_offset = ro;
         }
         out[i] = &box->pub;
+        n_boxes = i + 1;
     }
     return GLC_OK;
+#undef DL_TRY
 }
 
 static glc_status encode_batch_impl(glc_encoder *enc, uint32_t n_files, const void *const *pcm, int elem_bytes,
@@ -1483,8 +1546,9 @@ static glc_status encode_batch_impl(glc_encoder *enc, uint32_t n_files, const vo
     for (uint32_t i = 0; i < n_files; ++i)
         if (!pcm[i])
             return fail(GLC_ERR_INVALID_ARG, "file %u: pcm is null", i);
+    DevScope arena_scope(c, c->copy);
     float *d_arena = nullptr;
-    CUDA_TRY(dmalloc(&d_arena, tot_pcm, c->copy));
+    CUDA_TRY(arena_scope.alloc(&d_arena, tot_pcm));
     HostPcm hp{};
     hp.ptr = pcm;
     hp.elem_bytes = elem_bytes;
@@ -1492,7 +1556,7 @@ static glc_status encode_batch_impl(glc_encoder *enc, uint32_t n_files, const vo
     hp.inv_max = is_int ? 1.0f / (float)(1ull << (bits - 1)) : 1.0f;
     char *d_stage = nullptr;
     if (is_int)
-        CUDA_TRY(dmalloc(&d_stage, tot_pcm * (size_t)elem_bytes, c->copy));
+        CUDA_TRY(arena_scope.alloc(&d_stage, tot_pcm * (size_t)elem_bytes));
     hp.d_stage = d_stage;
     glc_dev_encoded *de = nullptr;
     EncodeHostOut ho;
@@ -1506,9 +1570,7 @@ static glc_status encode_batch_impl(glc_encoder *enc, uint32_t n_files, const vo
         c->pool.release(ho.h_raw);
     if (de)
         glc_dev_encoded_free(de);
-    cudaStreamSynchronize(c->compute);
-    dfree(d_arena, c->copy);
-    dfree(d_stage, c->copy);
+    cudaStreamSynchronize(c->compute); // the arenas (arena_scope) are idle when they return to the pool
     return st;
 }
 
@@ -1582,7 +1644,14 @@ extern "C" glc_status glc_dev_encode(glc_encoder *enc, const glc_dev_pcm *pcm, g
     const uint64_t n = pcm->n;
     const uint16_t ch = pcm->channels;
     GLC_TRY(build_file_table(1, &n, &ch, files, &rows, &frames, &tot_pcm));
-    return encode_core(enc, files, rows, frames, pcm->d + pcm->trim_off, nullptr, nullptr, nullptr, out);
+    *out = nullptr;
+    const glc_status st = encode_core(enc, files, rows, frames, pcm->d + pcm->trim_off, nullptr, nullptr, nullptr, out);
+    if (st != GLC_OK && *out)
+    {
+        glc_dev_encoded_free(*out);
+        *out = nullptr;
+    }
+    return st;
 }
 
 extern "C" glc_status glc_dev_encoded_download(const glc_dev_encoded *de, glc_encoded **out)
@@ -1658,59 +1727,61 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1);
     uint64_t max_wave_rows = 0;
-    const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, false,
-                                               (io && !c->wave_frames) ? kRowQuantum : 0);
+    std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, false,
+                                         (io && !c->wave_frames) ? kRowQuantum : 0);
+    if (waves.empty())
+        waves.push_back(Wave{0, 0, 0, 0}); // only streams without frames: their hops (zeros) are still produced
     const uint64_t wave_tiles = (max_wave_rows + kImdctBM - 1) / kImdctBM;
 
-    CUDA_TRY(dmalloc(&d_files, n_files, cs));
+    DevScope ds(c, cs); // every scratch block below goes back to the pool on any exit path
+    CUDA_TRY(ds.alloc(&d_files, n_files));
     CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(DecFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
     c->stats.h2d_bytes += sizeof(DecFileDesc) * n_files;
     // Worst-case sizes (every row transformed, every k present); the live counts stay on the device,
     // so the decode needs no host round trip.  `blocks` holds every row of the batch (+1 tile of
     // slack for the clipped last tile of a wave) because hop h needs frames h-1 and h.
-    CUDA_TRY(dmalloc(&d_atiles, wave_tiles * kImdctATileFloats, cs));
-    CUDA_TRY(dmalloc(&d_blocks, (tot_rows + kBM) * kFrame, cs));
-    CUDA_TRY(dmalloc(&d_flags, max_wave_rows, cs));
-    CUDA_TRY(dmalloc(&d_slot_off, max_wave_rows + 1, cs));
-    CUDA_TRY(dmalloc(&d_row_slot, tot_rows, cs));
-    CUDA_TRY(dmalloc(&d_active, max_wave_rows, cs));
-    CUDA_TRY(dmalloc(&d_ntiles, 1, cs));
-    CUDA_TRY(dmalloc(&d_nk, wave_tiles, cs));
-    CUDA_TRY(dmalloc(&d_stage_list, wave_tiles * kImdctStages, cs));
-    CUDA_TRY(dmalloc(&d_out, total_out, cs));
+    CUDA_TRY(ds.alloc(&d_atiles, wave_tiles * kImdctATileFloats));
+    CUDA_TRY(ds.alloc(&d_blocks, (tot_rows + kBM) * kFrame));
+    CUDA_TRY(ds.alloc(&d_flags, max_wave_rows));
+    CUDA_TRY(ds.alloc(&d_slot_off, max_wave_rows + 1));
+    CUDA_TRY(ds.alloc(&d_row_slot, tot_rows));
+    CUDA_TRY(ds.alloc(&d_active, max_wave_rows));
+    CUDA_TRY(ds.alloc(&d_ntiles, 1));
+    CUDA_TRY(ds.alloc(&d_nk, wave_tiles));
+    CUDA_TRY(ds.alloc(&d_stage_list, wave_tiles * kImdctStages));
+    CUDA_TRY(ds.alloc(&d_out, total_out));
     int16_t *d_out16 = nullptr;
     if (io && io->h_out && io->out16)
-        CUDA_TRY(dmalloc(&d_out16, total_out, cs));
+        CUDA_TRY(ds.alloc(&d_out16, total_out));
     tr.mark("alloc");
 
+    // A frame boundary `fr` belongs to the LOWEST-numbered file that starts there (streams without frames
+    // share their first_frame with the next file and still own one hop, the all-zero final overlap of
+    // src/codec.rs:723-729), else to the file that contains it.
+    auto file_at_boundary = [&](uint64_t fr) -> uint32_t {
+        uint32_t lo = 0, hi = n_files; // first file with first_frame >= fr
+        while (lo < hi)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (files[mid].first_frame < fr)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo < n_files && files[lo].first_frame == fr)
+            return lo;
+        return lo - 1; // fr > 0 here, so lo >= 1
+    };
     auto out_index = [&](uint64_t fr) -> uint64_t { // first output value that needs frame `fr`
         if (fr >= tot_frames)
             return total_out;
-        uint32_t lo = 0, hi = n_files - 1;
-        while (lo < hi)
-        {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (files[mid].first_frame <= fr)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        return files[lo].out_off + (fr - files[lo].first_frame) * kHop * files[lo].channels;
+        const uint32_t i = file_at_boundary(fr);
+        return files[i].out_off + (fr - files[i].first_frame) * kHop * files[i].channels;
     };
-
     auto hop_id = [&](uint64_t fr) -> uint64_t { // batch-wide hop number of the hop that starts at frame `fr`
         if (fr >= tot_frames)
             return tot_frames + n_files;
-        uint32_t lo = 0, hi = n_files - 1;
-        while (lo < hi)
-        {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (files[mid].first_frame <= fr)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        return fr + lo;
+        return fr + file_at_boundary(fr);
     };
     uint32_t ola_tile_channels = 0;
     for (const DecFileDesc &f : files)
@@ -1826,7 +1897,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             m.blocks = d_blocks + w.r0 * kFrame;
             CUDA_TRY(launch_imdct_exact(m, cs));
         }
-        const uint64_t o0 = out_index(w.f0), o1 = out_index(w.f1);
+        const uint64_t o0 = wi ? out_index(w.f0) : 0, o1 = out_index(w.f1);
         {
             LaunchScope ls(c, GLC_K_OLA, cs);
             OlaLaunch o{};
@@ -1837,7 +1908,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             o.raw = d_raw;
             o.files = d_files;
             o.n_files = n_files;
-            o.hop_begin = hop_id(w.f0);
+            o.hop_begin = wi ? hop_id(w.f0) : 0;
             o.hop_end = hop_id(w.f1);
             o.out = d_out;
             o.tile_channels = ola_tile_channels;
@@ -1882,18 +1953,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     }
     for (cudaEvent_t e : used_events)
         c->ev_free.push_back(e);
-    dfree(d_atiles, cs);
-    dfree(d_blocks, cs);
-    dfree(d_flags, cs);
-    dfree(d_slot_off, cs);
-    dfree(d_row_slot, cs);
-    dfree(d_active, cs);
-    dfree(d_ntiles, cs);
-    dfree(d_nk, cs);
-    dfree(d_stage_list, cs);
-    dfree(d_files, cs);
-    if (d_out16)
-        dfree(d_out16, cs); // stream-ordered: the d2h stream is drained above
+    ds.keep(d_out); // the caller owns the output; the scratch blocks are released by `ds`
     tr.mark("free");
     *d_out_ret = d_out;
     return GLC_OK;

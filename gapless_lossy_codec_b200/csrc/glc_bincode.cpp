@@ -9,6 +9,7 @@
 //   frame = Vec<Vec<(u16,i16)>> , Vec<f32> , Option<Vec<i16>>
 // A raw frame carries two empty Vecs and Some(raw); a sparse frame carries None.
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 
 #include <new>
@@ -130,7 +131,11 @@ extern "C" glc_status glc_encoded_from_bincode(glc_ctx *ctx, const uint8_t *byte
     EncodedBox *box = new (std::nothrow) EncodedBox();
     EncodedBlock *blk = new (std::nothrow) EncodedBlock();
     if (!box || !blk)
+    {
+        delete box; // whichever of the two was allocated
+        delete blk;
         return set_error(GLC_ERR_NO_MEMORY, "out of host memory");
+    }
     blk->ctx = ctx;
     blk->refs = 1;
     box->blk = blk;
@@ -147,9 +152,16 @@ extern "C" glc_status glc_encoded_from_bincode(glc_ctx *ctx, const uint8_t *byte
     e.channels = r.le<uint16_t>();
     e.total_samples = r.le<uint64_t>();
     e.n_frames = r.le<uint64_t>();
-    if (!r.ok || e.channels == 0 || e.n_frames > len)
+    // Sizes come from an untrusted header: a frame serialises to at least 17 bytes (two u64 lengths and the
+    // Option tag) after the 22-byte header and before the 16-byte gapless block, and a sparse frame to at
+    // least 12 bytes per channel, so both counts are bounded by the image size before anything is allocated.
+    // (Raw frames of a foreign producer may carry fewer values than channels; the per-row tables are
+    // capped at 64 bytes per image byte, 64 MiB for small images.)
+    if (!r.ok || e.channels == 0 || len < 38 || e.n_frames > (len - 38) / 17)
         return bail(GLC_ERR_CORRUPT, "truncated or invalid .glc header");
     const uint64_t ch = e.channels, rows = e.n_frames * ch;
+    if (rows * 16 > std::max<uint64_t>((uint64_t)64 << 20, 64 * len))
+        return bail(GLC_ERR_CORRUPT, ".glc header claims more frame-channels than the image can hold");
     auto heap = [&](uint64_t bytes_) -> void * {
         void *p = calloc(bytes_ ? bytes_ : 1, 1);
         if (p)

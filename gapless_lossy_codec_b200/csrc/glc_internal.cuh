@@ -316,6 +316,7 @@ void pinned_release(glc_ctx *ctx, void *p);
 cudaError_t dev_alloc(glc_ctx *ctx, void **out, size_t bytes, cudaStream_t s); // context-owned device pool
 void dev_free(glc_ctx *ctx, void *p, cudaStream_t s);
 int ctx_device(glc_ctx *ctx);
+glc_ctx *decoder_ctx(glc_decoder *dec);
 cudaStream_t ctx_compute_stream(glc_ctx *ctx);
 cudaStream_t ctx_d2h_stream(glc_ctx *ctx);
 void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n);

@@ -93,15 +93,24 @@ extern "C" glc_status glc_encode_batch_sharded(glc_encoder *const *encs, uint32_
     std::vector<uint64_t> w(n_files);
     for (uint32_t i = 0; i < n_files; ++i)
     {
+        // the planner's weights need valid lengths: refuse up front what glc_encode_batch would refuse later
         if (channels[i] == 0)
             return glc::set_error(GLC_ERR_INVALID_ARG, "file %u: 0 channels", i);
+        if (n_samples[i] % channels[i])
+            return glc::set_error(GLC_ERR_INVALID_ARG, "file %u: %llu samples is not a multiple of %u channels", i,
+                                  (unsigned long long)n_samples[i], (unsigned)channels[i]);
+        if (n_samples[i] / channels[i] <= 512)
+            return glc::set_error(GLC_ERR_TOO_SHORT,
+                                  "file %u: %llu samples per channel; the reference panics for <= 512 "
+                                  "(src/codec.rs:449-452,474)",
+                                  i, (unsigned long long)(n_samples[i] / channels[i]));
         w[i] = frames_for(n_samples[i] / channels[i]) * channels[i];
     }
     GLC_TRY(glc_plan_shards(n_files, w.data(), n_shards, shard_of));
     const auto members = members_of(n_files, n_shards, shard_of);
     for (uint32_t i = 0; i < n_files; ++i)
         out[i] = nullptr;
-    return run_shards(n_shards, members, [&](uint32_t s) -> glc_status {
+    const glc_status rs = run_shards(n_shards, members, [&](uint32_t s) -> glc_status {
         const std::vector<uint32_t> &m = members[s];
         std::vector<const float *> p(m.size());
         std::vector<uint64_t> n(m.size());
@@ -119,6 +128,14 @@ extern "C" glc_status glc_encode_batch_sharded(glc_encoder *const *encs, uint32_
                 out[m[k]] = o[k];
         return st;
     });
+    if (rs != GLC_OK) // nothing is returned on failure: release what the other shards produced
+        for (uint32_t i = 0; i < n_files; ++i)
+            if (out[i])
+            {
+                glc_encoded_free(nullptr, out[i]);
+                out[i] = nullptr;
+            }
+    return rs;
 }
 
 extern "C" glc_status glc_decode_batch_sharded(glc_decoder *const *decs, uint32_t n_shards, uint32_t n_files,
@@ -141,7 +158,7 @@ extern "C" glc_status glc_decode_batch_sharded(glc_decoder *const *decs, uint32_
         pcm[i] = nullptr;
         n_samples[i] = 0;
     }
-    return run_shards(n_shards, members, [&](uint32_t s) -> glc_status {
+    const glc_status rs = run_shards(n_shards, members, [&](uint32_t s) -> glc_status {
         const std::vector<uint32_t> &m = members[s];
         std::vector<const glc_encoded *> e(m.size());
         std::vector<float *> o(m.size(), nullptr);
@@ -157,6 +174,15 @@ extern "C" glc_status glc_decode_batch_sharded(glc_decoder *const *decs, uint32_
             }
         return st;
     });
+    if (rs != GLC_OK)
+        for (uint32_t i = 0; i < n_files; ++i)
+            if (pcm[i])
+            {
+                glc_free(glc::decoder_ctx(decs[shard_of[i]]), pcm[i]);
+                pcm[i] = nullptr;
+                n_samples[i] = 0;
+            }
+    return rs;
 }
 
 extern "C" glc_status glc_flac_encode_batch_sharded(glc_ctx *const *ctxs, uint32_t n_shards, uint32_t n_files,
@@ -174,7 +200,7 @@ extern "C" glc_status glc_flac_encode_batch_sharded(glc_ctx *const *ctxs, uint32
         bytes[i] = nullptr;
         len[i] = 0;
     }
-    return run_shards(n_shards, members, [&](uint32_t s) -> glc_status {
+    const glc_status rs = run_shards(n_shards, members, [&](uint32_t s) -> glc_status {
         const std::vector<uint32_t> &m = members[s];
         std::vector<const float *> p(m.size());
         std::vector<uint64_t> n(m.size()), l(m.size(), 0);
@@ -198,4 +224,13 @@ extern "C" glc_status glc_flac_encode_batch_sharded(glc_ctx *const *ctxs, uint32
             }
         return st;
     });
+    if (rs != GLC_OK)
+        for (uint32_t i = 0; i < n_files; ++i)
+            if (bytes[i])
+            {
+                glc_free(ctxs[shard_of[i]], bytes[i]);
+                bytes[i] = nullptr;
+                len[i] = 0;
+            }
+    return rs;
 }

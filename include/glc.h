@@ -206,8 +206,8 @@ glc_status glc_decode_to_flac_batch(glc_decoder *dec, uint32_t n_files, const gl
  * own glc_ctx), run the ordinary batch call of every shard on its own host thread and hand the outputs
  * back in input order -- a host-side gather, no collective.  shard_of[i] (required) receives the shard
  * that processed file i: its context owns out[i] / pcm[i] / bytes[i] and must be passed to
- * glc_encoded_free / glc_free.  On failure nothing is returned (outputs already produced stay owned by
- * their contexts until those are destroyed). */
+ * glc_encoded_free / glc_free.  Every file is validated before any work is planned; on failure nothing is
+ * returned (outputs that other shards had already produced are released by the call). */
 glc_status glc_plan_shards(uint32_t n_files, const uint64_t *weights, uint32_t n_shards, uint32_t *shard_of);
 glc_status glc_encode_batch_sharded(glc_encoder *const *encs, uint32_t n_shards, uint32_t n_files,
                                     const float *const *pcm, const uint64_t *n_samples, const uint16_t *channels,

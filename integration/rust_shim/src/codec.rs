@@ -1,59 +1,3 @@
-# INTEGRATION — dropping `libglc_b200.so` under the reference crate
-
-The reference (`ajcm474/gapless-lossy-codec`) has no plugin or FFI layer; its boundary is the Rust
-module API re-exported by `src/lib.rs:1-5` and re-declared privately by the binary
-(`src/main.rs:1-5`: `mod codec; mod audio; mod flac;`). A drop-in therefore replaces the two module
-files `src/codec.rs` and `src/flac.rs` with thin shims of the same public items over the C ABI of
-`include/glc.h`; `audio.rs`, `main.rs`, `ui.rs`, `playback.rs` and `tests/*.rs` compile unchanged.
-
-This image has no Rust toolchain, so the shim below is source a maintainer would add (complete files, written
-for the crate's edition 2024), not something built or tested here. What IS tested here is the same ABI from C++ (`include/glc.hpp`, the mirror of the
-reference API that `tests/cpp/reference_suite.cpp` runs the reference's own tests through), from plain C
-(`tests/cpp/abi_smoke.c`) and through ctypes (`gapless_lossy_codec_b200/_ffi.py`, `tests/test_abi.py`,
-`tests/test_gpu_*.py`).
-
-## 1. Build and link
-
-```
-make -C gapless_lossy_codec_b200/csrc          # nvcc -gencode arch=compute_100a,code=sm_100a -> libglc_b200.so
-cp integration/rust_shim/build.rs     <reference>/build.rs
-cp integration/rust_shim/src/codec.rs <reference>/src/codec.rs
-cp integration/rust_shim/src/flac.rs  <reference>/src/flac.rs
-cd <reference> && GLC_B200_LIB_DIR=<repo>/gapless_lossy_codec_b200 cargo test --release
-```
-
-The three files are complete (nothing elided) and are reproduced below from `integration/rust_shim/`, which is
-the source of truth. `src/lib.rs:1-5` and `src/main.rs:1-5` stay as they are: both declare
-`mod codec; mod audio; mod flac;`, and the raw bindings live in the private submodule `codec::sys`.
-
-`build.rs`:
-
-```rust
-// build.rs for the reference crate when src/codec.rs and src/flac.rs are replaced by the shims in
-// this directory.  GLC_B200_LIB_DIR = directory that holds libglc_b200.so
-// (gapless_lossy_codec_b200/ of the B200 repo after `make -C gapless_lossy_codec_b200/csrc`).
-fn main()
-{
-    let dir = std::env::var("GLC_B200_LIB_DIR").expect("set GLC_B200_LIB_DIR to the directory of libglc_b200.so");
-    println!("cargo:rustc-link-search=native={dir}");
-    println!("cargo:rustc-link-lib=dylib=glc_b200");
-    println!("cargo:rustc-link-arg=-Wl,-rpath,{dir}");
-    println!("cargo:rerun-if-env-changed=GLC_B200_LIB_DIR");
-}
-```
-
-## 2. Pinning the oracle against the original crate first
-
-`tests/golden/dump_reference.rs` is a Cargo integration test for the UNMODIFIED reference checkout (public API
-only). It writes its own inputs and the crate's outputs (`.glc` images, decoded PCM, streaming chunks, FLAC
-bytes at every level, a fingerprint of the cosine table) to a directory; copied to `tests/golden/ref_v1/`,
-`tests/test_reference_golden.py` compares the oracle (CPU) and the CUDA path (`-m gpu`) with it byte for
-byte, and reports "parity unpinned" while the directory is absent. The header of the `.rs` file has the
-five commands.
-
-## 3. Replacement `src/codec.rs` (complete; the `extern "C"` declarations are its `sys` submodule)
-
-```rust
 //! Drop-in replacement for the reference's `src/codec.rs` (ajcm474/gapless-lossy-codec v0.5.0):
 //! the same public items with the same signatures, implemented over the C ABI of libglc_b200.so
 //! (`include/glc.h`).  `src/lib.rs`, `src/main.rs`, `src/audio.rs`, `src/ui.rs`, `src/playback.rs`
@@ -601,87 +545,3 @@ pub fn load_encoded(path: &std::path::Path) -> Result<EncodedAudio>
     let encoded = bincode::deserialize(&data)?;
     Ok(encoded)
 }
-```
-
-`save_encoded`/`load_encoded` keep using the `bincode` crate on the nested types (it is already a
-dependency); `glc_encoded_to_bincode/_from_bincode` produce/consume the identical byte image for
-hosts without serde (checked against the oracle's image in `tests/`).
-
-## 4. Replacement `src/flac.rs` (complete)
-
-```rust
-//! Drop-in replacement for the reference's `src/flac.rs` (public items of reference
-//! src/flac.rs:947-1088) over libglc_b200.so.  Bytes are identical to the reference encoder's: fixed
-//! predictors, per-partition Rice parameter, 16-bit samples, independent channels.
-use anyhow::Result;
-use std::path::Path;
-use std::ptr;
-use std::slice;
-
-use crate::codec::sys::{glc_flac_encode, glc_free};
-use crate::codec::{check, ctx};
-
-/// reference src/flac.rs:947.  Errors keep the reference's order and wording: "< 16 samples per
-/// channel" first (:963-969), then "Invalid compression level" (:972-978).
-pub fn encode_flac_with_level(samples: &[f32], sample_rate: u32, channels: u16, compression_level: u8) -> Result<Vec<u8>>
-{
-    let c = ctx();
-    let mut p: *mut u8 = ptr::null_mut();
-    let mut n: u64 = 0;
-    check(unsafe
-    {
-        glc_flac_encode(c.0, samples.as_ptr(), samples.len() as u64, sample_rate, channels, compression_level, &mut p, &mut n)
-    })?;
-    let bytes = unsafe { slice::from_raw_parts(p, n as usize) }.to_vec();
-    unsafe { glc_free(c.0, p as *mut std::os::raw::c_void) };
-    Ok(bytes)
-}
-
-/// reference src/flac.rs:1055 (level 5)
-pub fn encode_flac(samples: &[f32], sample_rate: u32, channels: u16) -> Result<Vec<u8>>
-{
-    encode_flac_with_level(samples, sample_rate, channels, 5)
-}
-
-/// reference src/flac.rs:1065
-pub fn export_to_flac_with_level(path: &Path, samples: &[f32], sample_rate: u32, channels: u16, compression_level: u8) -> Result<()>
-{
-    let flac_data = encode_flac_with_level(samples, sample_rate, channels, compression_level)?;
-    std::fs::write(path, flac_data)?;
-    Ok(())
-}
-
-/// reference src/flac.rs:1080
-pub fn export_to_flac(path: &Path, samples: &[f32], sample_rate: u32, channels: u16) -> Result<()>
-{
-    export_to_flac_with_level(path, samples, sample_rate, channels, 5)
-}
-```
-
-## 5. Batch / multi-GPU callers
-
-The CLI loops over files (`src/main.rs:546-583`); a batch caller hands all files of a shard to
-`glc_encode_batch` / `glc_decode_batch` / `glc_flac_encode_batch` on one context per GPU
-(`glc_ctx_create(device, ..)` in one process or thread per device). Files are independent, so there
-is no collective: the host concatenates per-file outputs. `glc_encode_batch_sharded` /
-`glc_decode_batch_sharded` / `glc_flac_encode_batch_sharded` do exactly that inside the library: one call, a list of
-encoders / decoders / contexts (one per GPU), the files split by frame count, one host thread per device, outputs in
-input order plus the shard that owns each of them.
-
-Three optional extensions sit next to the mirrored API (all bit-identical to the two-step paths they
-replace): `glc_encode_i16` / `glc_encode_i32` take the integer samples `audio::load_wav` /
-`load_flac` read (`src/audio.rs:39-83`) and do the `/ 2^(bits-1)` on the device, so a caller can skip
-`audio.rs`'s f32 vector and halve the PCIe traffic; `glc_decode_to_flac` is `decode_file`'s
-decode-then-export (`src/main.rs:55-113`) with the PCM kept on the device; `glc_decode_i16` is the
-WAV branch of the same function (`export_to_wav` → `convert_f32_to_i16`, `src/audio.rs:11-16, 98-131`):
-the 16-bit samples hound would write, converted on the device, so `audio::export_to_wav` can hand
-them to `WavWriter::write_sample` directly.
-
-## 6. The same binding in Python (what the tests use)
-
-```python
-from gapless_lossy_codec_b200 import Encoder, Decoder, save_encoded, load_encoded, flac
-enc = Encoder(44100).encode(samples, 2)          # Encoder::new(44100).encode(&samples, 2)
-pcm = Decoder(2, 44100).decode(enc)              # Decoder::new(2, 44100).decode(&enc, None)
-blob = flac.encode_flac_with_level(pcm, 44100, 2, 8)
-```

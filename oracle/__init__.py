@@ -126,12 +126,17 @@ def lib() -> C.CDLL:
         L.orc_crc16.restype = C.c_uint16
         L.orc_flac_decode.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(FlacInfo)]
         L.orc_flac_decode.restype = C.c_int
+        L.orc_flac_decode_ex.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(FlacInfo), C.POINTER(C.c_uint64),
+                                         C.c_uint64]
+        L.orc_flac_decode_ex.restype = C.c_int
         L.orc_bincode_serialize.argtypes = [C.POINTER(Encoded), C.POINTER(C.POINTER(C.c_uint8)),
                                             C.POINTER(C.c_uint64)]
         L.orc_bincode_serialize.restype = C.c_int
         L.orc_bincode_deserialize.argtypes = [C.c_void_p, C.c_uint64,
                                               C.POINTER(C.POINTER(Encoded))]
         L.orc_bincode_deserialize.restype = C.c_int
+        L.orc_fnv1a64.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_fnv1a64.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -321,11 +326,15 @@ def flac_encode(samples: np.ndarray, sample_rate: int, channels: int, level: int
         lib().orc_free(b)
 
 
-def flac_decode(data: bytes) -> dict:
-    """Independent RFC 9639 decoder (stands in for claxon in tests/test_flac.rs)."""
+def flac_decode(data: bytes, frame_offsets: bool = False) -> dict:
+    """Independent RFC 9639 decoder (stands in for claxon in tests/test_flac.rs).  With frame_offsets the
+    result also holds "frame_off": the byte offset of every frame header, then len(data)."""
     info = FlacInfo()
-    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
-    rc = lib().orc_flac_decode(buf, len(data), C.byref(info))
+    buf = np.frombuffer(data, np.uint8)
+    cap = len(data) // 9 + 2 if frame_offsets else 0  # a frame is at least 9 bytes
+    offs = np.zeros(max(cap, 1), np.uint64)
+    rc = lib().orc_flac_decode_ex(buf.ctypes.data, len(data), C.byref(info),
+                                  offs.ctypes.data_as(C.POINTER(C.c_uint64)) if frame_offsets else None, cap)
     try:
         smp = (np.ctypeslib.as_array(info.samples, shape=(info.n_decoded,)).copy()
                if info.n_decoded else np.zeros(0, np.int32))
@@ -334,11 +343,14 @@ def flac_decode(data: bytes) -> dict:
             lib().orc_free(info.samples)
     if rc:
         raise OracleError(f"flac decode failed rc={rc}")
-    return dict(sample_rate=info.sample_rate, channels=info.channels,
-                bits_per_sample=info.bits_per_sample, min_block=info.min_block,
-                max_block=info.max_block, total_samples=int(info.total_samples),
-                md5=bytes(info.md5), md5_ok=bool(info.md5_ok), n_frames=int(info.n_frames),
-                samples=smp)
+    out = dict(sample_rate=info.sample_rate, channels=info.channels,
+               bits_per_sample=info.bits_per_sample, min_block=info.min_block,
+               max_block=info.max_block, total_samples=int(info.total_samples),
+               md5=bytes(info.md5), md5_ok=bool(info.md5_ok), n_frames=int(info.n_frames),
+               samples=smp)
+    if frame_offsets:
+        out["frame_off"] = offs[: int(info.n_frames) + 1].copy()
+    return out
 
 
 def md5(data: bytes) -> bytes:
@@ -380,3 +392,9 @@ def bincode_deserialize(data: bytes) -> EncodedArrays:
         return arrays_from_struct(out.contents)
     finally:
         lib().orc_encoded_free(out)
+
+
+def fnv1a64(data) -> int:
+    """FNV-1a/64 of a bytes-like / numpy array (the table fingerprint of tests/golden/dump_reference.rs)."""
+    a = np.ascontiguousarray(np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data)
+    return int(lib().orc_fnv1a64(a.ctypes.data, a.nbytes))

@@ -191,3 +191,15 @@ int orc_bincode_deserialize(const uint8_t *bytes, uint64_t len, orc_encoded **ou
     *out = e;
     return 0;
 }
+
+/* FNV-1a/64 (test infrastructure: table fingerprint of the pinning kit, tests/golden/dump_reference.rs) */
+uint64_t orc_fnv1a64(const uint8_t *data, uint64_t len)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t i = 0; i < len; ++i)
+    {
+        h ^= data[i];
+        h *= 0x100000001b3ull;
+    }
+    return h;
+}

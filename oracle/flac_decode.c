@@ -156,7 +156,10 @@ static int decode_subframe(br_t *r, int32_t *out, uint32_t bs, unsigned bps)
     return r->err ? 33 : 0;
 }
 
-int orc_flac_decode(const uint8_t *bytes, uint64_t len, orc_flac_info *info)
+/* frame_off (nullable): receives the byte offset of every frame header, frame_off[n_frames] = len;
+ * at most frame_cap entries are written. */
+int orc_flac_decode_ex(const uint8_t *bytes, uint64_t len, orc_flac_info *info, uint64_t *frame_off,
+                       uint64_t frame_cap)
 {
     memset(info, 0, sizeof *info);
     if (len < 42 || memcmp(bytes, "fLaC", 4) != 0)
@@ -204,6 +207,8 @@ int orc_flac_decode(const uint8_t *bytes, uint64_t len, orc_flac_info *info)
     while ((r.pos >> 3) < len)
     {
         const uint64_t fstart = r.pos >> 3;
+        if (frame_off && info->n_frames < frame_cap)
+            frame_off[info->n_frames] = fstart;
         if (br_bits(&r, 14) != 0x3FFE) { rc = 10; break; }
         if (br_bits(&r, 1) != 0) { rc = 11; break; }
         br_bits(&r, 1); /* blocking strategy */
@@ -273,6 +278,8 @@ int orc_flac_decode(const uint8_t *bytes, uint64_t len, orc_flac_info *info)
         info->n_frames++;
     }
     free(chan);
+    if (frame_off && info->n_frames < frame_cap)
+        frame_off[info->n_frames] = r.pos >> 3;
     info->samples = outp;
     info->n_decoded = written;
     if (rc)
@@ -288,4 +295,9 @@ int orc_flac_decode(const uint8_t *bytes, uint64_t len, orc_flac_info *info)
     free(raw);
     info->md5_ok = memcmp(dg, info->md5, 16) == 0;
     return 0;
+}
+
+int orc_flac_decode(const uint8_t *bytes, uint64_t len, orc_flac_info *info)
+{
+    return orc_flac_decode_ex(bytes, len, info, NULL, 0);
 }

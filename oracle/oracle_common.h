@@ -104,6 +104,11 @@ typedef struct
     int32_t *samples;   /* interleaved */
 } orc_flac_info;
 int orc_flac_decode(const uint8_t *bytes, uint64_t len, orc_flac_info *info);
+int orc_flac_decode_ex(const uint8_t *bytes, uint64_t len, orc_flac_info *info, uint64_t *frame_off,
+                       uint64_t frame_cap);
+
+/* FNV-1a/64 over bytes: fingerprint of the cosine table shared with tests/golden/dump_reference.rs */
+uint64_t orc_fnv1a64(const uint8_t *data, uint64_t len);
 
 /* ---- bincode 1.3 container image (src/codec.rs:774-786) ---- */
 int orc_bincode_serialize(const orc_encoded *enc, uint8_t **bytes, uint64_t *len);
