@@ -1076,8 +1076,10 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     CUDA_TRY(dmalloc(&de->d_pair_off, tot_rows + 1, cs));
     CUDA_TRY(dmalloc(&de->d_scales, tot_rows, cs));
     CUDA_TRY(dmalloc(&de->d_raw_off, tot_frames + 1, cs));
-    CUDA_TRY(ds.alloc(&d_slots, tot_rows * kHop));
-    CUDA_TRY(ds.alloc(&d_raw_len, tot_frames));
+    const bool fast = c->mode == GLC_MODE_FAST;
+    CUDA_TRY(ds.alloc(&d_slots, tot_rows * kHop)); // EXACT: per-row slots; FAST: per-group compact blocks
+    if (!fast)
+        CUDA_TRY(ds.alloc(&d_raw_len, tot_frames));
     // the compact outputs are produced wave by wave, so they are sized for the worst case
     // (every coefficient kept / every frame raw); the live totals stay on the device
     CUDA_TRY(dmalloc(&de->d_pairs, tot_rows * kHop, cs));
@@ -1088,7 +1090,6 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     // resident slot then runs the same number of CTAs and no partial "CTA wave" idles the GPU.
     // Host input: small waves so that the H2D of wave w+1 hides behind the MDCT of wave w.
     // Device-resident input: large waves (fewer launches, scratch still bounded).
-    const bool fast = c->mode == GLC_MODE_FAST;
     uint64_t target_rows = kRowQuantum * (host_pcm ? 4 : 32);
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1); // explicit tuning: rows per wave
@@ -1124,10 +1125,24 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     };
     CUDA_TRY(ds.alloc(&d_first_group, n_files + 1));
     CUDA_TRY(cudaMemcpyAsync(d_first_group, first_group.data(), 8 * (n_files + 1), cudaMemcpyHostToDevice, cs));
+    uint32_t *d_grp_pairs = nullptr, *d_grp_raw = nullptr;
+    uint64_t *d_grp_pair_off = nullptr, *d_grp_raw_off = nullptr;
+    unsigned int *d_tickets = nullptr;
     if (!fast)
     {
         CUDA_TRY(ds.alloc(&d_coefs, max_wave_rows * kHop));
         CUDA_TRY(ds.alloc(&d_atiles, mdct_a_tile_floats(max_wave_rows)));
+    }
+    else
+    {
+        // per-group totals and their exclusive scans (placement of the groups' compact blocks), one ticket
+        // counter per wave
+        CUDA_TRY(ds.alloc(&d_grp_pairs, n_groups));
+        CUDA_TRY(ds.alloc(&d_grp_raw, n_groups));
+        CUDA_TRY(ds.alloc(&d_grp_pair_off, n_groups + 1));
+        CUDA_TRY(ds.alloc(&d_grp_raw_off, n_groups + 1));
+        CUDA_TRY(ds.alloc(&d_tickets, waves.size()));
+        CUDA_TRY(cudaMemsetAsync(d_tickets, 0, sizeof(unsigned int) * waves.size(), cs));
     }
     tr.mark("alloc");
 
@@ -1241,7 +1256,6 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         }
         if (fast)
         {
-            LaunchScope ls(c, GLC_K_FAST_ENCODE, cs);
             FastEncodeLaunch fe{};
             fe.pcm_arena = d_arena;
             fe.files = d_files;
@@ -1253,12 +1267,34 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             fe.twiddles = reinterpret_cast<const float2 *>(c->d_fast_tw);
             fe.norm = c->host.norm;
             fe.perc = enc->d_perc;
-            fe.slots = d_slots;
             fe.nnz = de->d_nnz;
             fe.scales = de->d_scales;
             fe.is_raw = de->d_is_raw;
-            fe.raw_len = d_raw_len;
-            CUDA_TRY(launch_fast_encode(fe, cs));
+            fe.slots = d_slots;
+            fe.grp_pairs = d_grp_pairs;
+            fe.grp_raw = d_grp_raw;
+            fe.ticket = d_tickets + wi;
+            fe.grp_pair_off = d_grp_pair_off;
+            fe.grp_raw_off = d_grp_raw_off;
+            fe.pair_off = de->d_pair_off;
+            fe.raw_off = de->d_raw_off;
+            fe.pairs = de->d_pairs;
+            fe.raw = de->d_raw;
+            {
+                LaunchScope ls(c, GLC_K_FAST_ENCODE, cs);
+                CUDA_TRY(launch_fast_encode(fe, cs));
+            }
+            // placement: scans of the per-group totals (continuing from the previous wave), then the move
+            {
+                LaunchScope ls2(c, GLC_K_SCAN, cs, 2);
+                const uint64_t g0 = fe.group_begin, gn = fe.group_end - fe.group_begin;
+                CUDA_TRY(launch_scan_u32_u64(d_grp_pairs + g0, d_grp_pair_off + g0, gn, cs, wi ? d_grp_pair_off + g0 : nullptr));
+                CUDA_TRY(launch_scan_u32_u64(d_grp_raw + g0, d_grp_raw_off + g0, gn, cs, wi ? d_grp_raw_off + g0 : nullptr));
+            }
+            {
+                LaunchScope ls3(c, GLC_K_GATHER, cs, 1);
+                CUDA_TRY(launch_fast_place(fe, cs));
+            }
         }
         MdctLaunch m{};
         if (!fast)
@@ -1300,6 +1336,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             CUDA_TRY(launch_quant_pack(q, cs));
         }
         // ---- variable-length layout of this wave: the scans continue from the previous wave's totals ----
+        if (!fast)
         {
             LaunchScope ls(c, GLC_K_SCAN, cs, 2);
             CUDA_TRY(launch_scan_u32_u64(de->d_nnz + w.r0, de->d_pair_off + w.r0, w.r1 - w.r0, cs,
@@ -1307,6 +1344,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             CUDA_TRY(launch_scan_u32_u64(d_raw_len + w.f0, de->d_raw_off + w.f0, w.f1 - w.f0, cs,
                                          wi ? de->d_raw_off + w.f0 : nullptr));
         }
+        if (!fast)
         {
             LaunchScope ls(c, GLC_K_GATHER, cs, 2);
             GatherLaunch g{};

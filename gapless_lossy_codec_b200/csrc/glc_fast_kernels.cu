@@ -1,5 +1,6 @@
-// glc_fast_kernels.cu -- FAST transform mode (GLC_MODE_FAST): FFT-based MDCT / IMDCT fused with the
-// quantiser (encode) and the dequantiser + synthesis window (decode), sm_100a.
+// glc_fast_kernels.cu -- FAST transform mode (GLC_MODE_FAST), decode side: FFT-based IMDCT fused with the
+// dequantiser + synthesis window, sm_100a.  (The encode side is glc_fast_encode.cu; the transform notes
+// below apply to both.)
 //
 // This is the "fused MDCT+quantize kernel" of BASELINE.json's north_star: window -> fold -> DCT-IV
 // by a 512-point complex FFT (warp-level, register radix butterflies, one shared-memory exchange)
@@ -148,455 +149,6 @@ __device__ __forceinline__ void dct4_pair(float2 *pair, const LaneTw &tw, int la
     __syncwarp();
 }
 
-struct GroupGeom
-{
-    uint32_t file;
-    uint32_t n_frames; // frames of this group (<= frames_per_group)
-    uint64_t frame0;   // first frame of the group, local to the file
-};
-
-__device__ __forceinline__ GroupGeom locate_group(const uint64_t *first_group, const FileDesc *files, uint32_t n_files,
-                                                  uint64_t g)
-{
-    uint32_t lo = 0, hi = n_files - 1;
-    while (lo < hi)
-    {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (first_group[mid] <= g)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    GroupGeom gg;
-    gg.file = lo;
-    const uint32_t ch = files[lo].channels;
-    const uint32_t fpg = kFastFcs / ch ? kFastFcs / ch : 1u;
-    gg.frame0 = (g - first_group[lo]) * fpg;
-    const uint64_t left = files[lo].n_frames - gg.frame0;
-    gg.n_frames = (uint32_t)(left < fpg ? left : fpg);
-    return gg;
-}
-
-// ------------------------------------------------------------------ encode
-
-// Persistent CTAs: the perceptual tables and the lane twiddles are loaded once, then the CTA walks
-// frame groups with a grid stride.
-__global__ void __launch_bounds__(kFastThreads, 4) fast_encode_kernel(const FastEncodeLaunch p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const DevPerceptual &pm = *p.perc;
-        for (int k = tid; k < kHop; k += kFastThreads)
-        {
-            sm.inv_w[k] = pm.inv_w[k];
-            sm.band_of[k] = pm.band_of[k];
-        }
-        const int nb = pm.n_edges - 1;
-        if (tid < nb)
-        {
-            sm.band_lo[tid] = (int16_t)pm.band_edges[tid];
-            sm.band_hi[tid] = (int16_t)pm.band_edges[tid + 1];
-            sm.band_fac[tid] = 0.01f * pm.cf * pm.band_pf[tid];
-            sm.band_rcnt[tid] = 1.0f / pm.band_cnt[tid];
-        }
-        if (tid == 0)
-            sm.n_bands = nb;
-    }
-    const float noise_floor_factor = p.perc->noise_floor_factor;
-    LaneTw tw;
-    load_lane_tw(tw, p.twiddles, lane);
-
-    for (uint64_t g = p.group_begin + blockIdx.x; g < p.group_end; g += gridDim.x)
-    {
-        __syncthreads(); // tables ready / previous group done with shared memory
-        if (tid == 0)
-        {
-            const GroupGeom gg0 = locate_group(p.first_group, p.files, p.n_files, g);
-            const FileDesc &fd0 = p.files[gg0.file];
-            sm.g_src = p.pcm_arena + fd0.pcm_off;
-            sm.g_len = (long long)fd0.len;
-            sm.g_first_row = fd0.first_row;
-            sm.g_first_frame = fd0.first_frame;
-            sm.g_frame0 = gg0.frame0;
-            sm.g_ch = fd0.channels;
-            sm.g_n_frames = gg0.n_frames;
-        }
-        if (tid < kFastFcs)
-            sm.frame_nnz[tid] = 0;
-        __syncthreads();
-        struct
-        {
-            uint64_t frame0;
-            uint32_t n_frames;
-        } gg{sm.g_frame0, sm.g_n_frames};
-        struct
-        {
-            uint64_t first_row, first_frame;
-        } fd{sm.g_first_row, sm.g_first_frame};
-        const uint32_t ch = sm.g_ch;
-        const uint32_t n_fc = gg.n_frames * ch; // may exceed kFastFcs only when ch > 8 (then processed in rounds)
-        const float *src = sm.g_src;
-        const long long len = sm.g_len;
-        const int n_bands = sm.n_bands;
-
-        for (uint32_t fc0 = 0; fc0 < n_fc; fc0 += kFastFcs)
-        {
-            const uint32_t fcs_here = min((uint32_t)kFastFcs, n_fc - fc0);
-            __syncthreads();
-            // ---- stage: fold + window, (u[2n], u[N-1-2n]) per n, over the reference's padded signal
-            //      (512 zeros + data + zero tail, src/codec.rs:433-447).  A thread takes the same n of
-            //      every frame-channel of the group: the two window values are loaded once and up to
-            //      32 PCM loads are in flight before the first use. ----
-            if (tid < (int)fcs_here)
-            {
-                const uint32_t lf = (fc0 + tid) / ch, c = (fc0 + tid) - lf * ch;
-                const long long base = (long long)((gg.frame0 + lf) * kHop) - kHop / 2; // sample index of i = 0
-                sm.st_base[tid] = base;
-                sm.st_ptr[tid] = src + base * (long long)ch + c; // only dereferenced in range
-                sm.st_interior[tid] = base >= 0 && base + kFrame <= len; // no padding inside this frame
-                sm.st_row[tid] = fd.first_row + (gg.frame0 + lf) * ch + c;
-                sm.st_lf[tid] = (int)lf;
-                const uint32_t lf0 = fc0 / ch, c0 = fc0 - lf0 * ch; // frame-channel 0 of this round
-                sm.st_off[tid] = (int)(lf - lf0) * (int)(kHop * ch) + ((int)c - (int)c0);
-            }
-            __syncthreads();
-            const int ich = (int)ch;
-            // per-thread copies of the round's descriptors: one base pointer, 32-bit offsets, a validity mask
-            const float *gb = sm.st_ptr[0];
-            int foff[kFastFcs];
-            unsigned interior_mask = 0;
-#pragma unroll
-            for (int fc = 0; fc < kFastFcs; ++fc)
-            {
-                foff[fc] = sm.st_off[fc];
-                if ((uint32_t)fc < fcs_here && sm.st_interior[fc])
-                    interior_mask |= 1u << fc;
-            }
-            // Common case (every frame-channel of a full group lies inside its file): no validity tests,
-            // no per-frame-channel descriptors, 32 independent loads in flight per thread.
-            const bool all_interior = fcs_here == (uint32_t)kFastFcs && interior_mask == (1u << kFastFcs) - 1u;
-            if (all_interior)
-            {
-#pragma unroll 1
-                for (int it = 0; it < (kHop / 2) / kFastThreads; ++it)
-                {
-                    const int n = tid + it * kFastThreads;
-                    const float wa = __ldg(p.window + 512 + 2 * n);
-                    const float wo = __ldg(p.window + (n < 256 ? 511 - 2 * n : 2 * n - 512));
-                    const bool lo_half = n < 256;
-                    // lo_half: u0 = -b[i0] wa - b[i1] wo, u1 =  b[i2] wo - b[i3] wa
-                    // else   : u0 =  b[i0] wo - b[i1] wa, u1 = -b[i2] wa - b[i3] wo
-                    const int i0 = lo_half ? 1535 - 2 * n : 2 * n - 512;
-                    const int i1 = lo_half ? 1536 + 2 * n : 1535 - 2 * n;
-                    const int i2 = lo_half ? 511 - 2 * n : 512 + 2 * n;
-                    const int i3 = lo_half ? 512 + 2 * n : 2559 - 2 * n;
-                    const float *q0 = gb + i0 * ich, *q1 = gb + i1 * ich, *q2 = gb + i2 * ich, *q3 = gb + i3 * ich;
-                    const float c00 = lo_half ? -wa : wo, c01 = lo_half ? -wo : -wa;
-                    const float c10 = lo_half ? wo : -wa, c11 = lo_half ? -wa : -wo;
-                    float x[kFastFcs][4];
-                    if (ich == 2)
-                    {
-                        // stereo: the two channels of a frame sit side by side, one 8-byte load serves both
-#pragma unroll
-                        for (int fc = 0; fc < kFastFcs; fc += 2)
-                        {
-                            const float2 a0 = __ldg(reinterpret_cast<const float2 *>(q0 + foff[fc]));
-                            const float2 a1 = __ldg(reinterpret_cast<const float2 *>(q1 + foff[fc]));
-                            const float2 a2 = __ldg(reinterpret_cast<const float2 *>(q2 + foff[fc]));
-                            const float2 a3 = __ldg(reinterpret_cast<const float2 *>(q3 + foff[fc]));
-                            x[fc][0] = a0.x, x[fc + 1][0] = a0.y;
-                            x[fc][1] = a1.x, x[fc + 1][1] = a1.y;
-                            x[fc][2] = a2.x, x[fc + 1][2] = a2.y;
-                            x[fc][3] = a3.x, x[fc + 1][3] = a3.y;
-                        }
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int fc = 0; fc < kFastFcs; ++fc)
-                        {
-                            x[fc][0] = __ldg(q0 + foff[fc]);
-                            x[fc][1] = __ldg(q1 + foff[fc]);
-                            x[fc][2] = __ldg(q2 + foff[fc]);
-                            x[fc][3] = __ldg(q3 + foff[fc]);
-                        }
-                    }
-#pragma unroll
-                    for (int fc = 0; fc < kFastFcs; ++fc)
-                        sm.u[fc][n] = make_float2(x[fc][0] * c00 + x[fc][1] * c01, x[fc][2] * c10 + x[fc][3] * c11);
-                }
-            }
-            else
-#pragma unroll 1
-            for (int it = 0; it < (kHop / 2) / kFastThreads; ++it)
-            {
-                const int n = tid + it * kFastThreads;
-                // window symmetry w[2047-i] = w[i] leaves two distinct values per n
-                const float wa = __ldg(p.window + 512 + 2 * n);
-                const float wo = __ldg(p.window + (n < 256 ? 511 - 2 * n : 2 * n - 512));
-                int i0, i1, i2, i3;
-                if (n < 256)
-                {
-                    i0 = 1535 - 2 * n; // u0 = -b[i0] - b[i1], u1 = b[i2] - b[i3]
-                    i1 = 1536 + 2 * n;
-                    i2 = 511 - 2 * n;
-                    i3 = 512 + 2 * n;
-                }
-                else
-                {
-                    i0 = 2 * n - 512;  // u0 = b[i0] - b[i1], u1 = -b[i2] - b[i3]
-                    i1 = 1535 - 2 * n;
-                    i2 = 512 + 2 * n;
-                    i3 = 2559 - 2 * n;
-                }
-                const int o0 = i0 * ich, o1 = i1 * ich, o2 = i2 * ich, o3 = i3 * ich;
-                float x[kFastFcs][4];
-#pragma unroll
-                for (int fc = 0; fc < kFastFcs; ++fc)
-                {
-                    x[fc][0] = x[fc][1] = x[fc][2] = x[fc][3] = 0.0f;
-                    if ((interior_mask >> fc) & 1u)
-                    {
-                        x[fc][0] = __ldg(gb + (foff[fc] + o0));
-                        x[fc][1] = __ldg(gb + (foff[fc] + o1));
-                        x[fc][2] = __ldg(gb + (foff[fc] + o2));
-                        x[fc][3] = __ldg(gb + (foff[fc] + o3));
-                    }
-                }
-#pragma unroll
-                for (int fc = 0; fc < kFastFcs; ++fc)
-                    if ((uint32_t)fc < fcs_here)
-                    {
-                        float u0, u1;
-                        if (n < 256)
-                        {
-                            u0 = -x[fc][0] * wa - x[fc][1] * wo; // windows: w[i0] = wa, w[i1] = wo, w[i2] = wo, w[i3] = wa
-                            u1 = x[fc][2] * wo - x[fc][3] * wa;
-                        }
-                        else
-                        {
-                            u0 = x[fc][0] * wo - x[fc][1] * wa;  // windows: w[i0] = wo, w[i1] = wa, w[i2] = wa, w[i3] = wo
-                            u1 = -x[fc][2] * wa - x[fc][3] * wo;
-                        }
-                        sm.u[fc][n] = make_float2(u0, u1);
-                    }
-                // frames that touch the 512-zero lead-in or the zero tail (first / last frames of a file)
-#pragma unroll 1
-                for (uint32_t fc = 0; fc < fcs_here; ++fc)
-                {
-                    if (sm.st_interior[fc])
-                        continue;
-                    const float *fb = sm.st_ptr[fc];
-                    const long long base = sm.st_base[fc];
-                    auto smp = [&](int i) -> float {
-                        const long long pos = base + i;
-                        return (pos >= 0 && pos < len) ? __ldg(fb + (long long)i * ich) : 0.0f;
-                    };
-                    const float y0 = smp(i0), y1 = smp(i1), y2 = smp(i2), y3 = smp(i3);
-                    float u0, u1;
-                    if (n < 256)
-                    {
-                        u0 = -y0 * wa - y1 * wo;
-                        u1 = y2 * wo - y3 * wa;
-                    }
-                    else
-                    {
-                        u0 = y0 * wo - y1 * wa;
-                        u1 = -y2 * wa - y3 * wo;
-                    }
-                    sm.u[fc][n] = make_float2(u0, u1);
-                }
-            }
-            if (fcs_here & 1u) // the transform works on pairs: an odd group gets a silent partner
-                for (uint32_t n = tid; n < kHop / 2; n += kFastThreads)
-                    sm.u[fcs_here][n] = make_float2(0.f, 0.f);
-            __syncthreads();
-
-            for (uint32_t pr = warp; pr * 2 < fcs_here; pr += kFastWarps)
-            {
-                const uint32_t fa = pr * 2;
-                dct4_pair(sm.u[fa], tw, lane);
-                // Both frame-channels of the pair are quantised in lock step: the two instruction streams
-                // are independent, which doubles the work in flight of this latency-bound phase.  (For an
-                // odd group the partner is silence; its results are not stored.)
-                const bool two = pr * 2 + 1 < fcs_here;
-                const float *coef0 = reinterpret_cast<const float *>(sm.u[fa]);
-                const float *coef1 = coef0 + kCoefStride;
-                float m0 = 0.0f, m1 = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                {
-                    const float4 v0 = *reinterpret_cast<const float4 *>(coef0 + j * 128 + lane * 4);
-                    const float4 v1 = *reinterpret_cast<const float4 *>(coef1 + j * 128 + lane * 4);
-                    m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
-                    m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
-                }
-                // scale = max|c| .max(1e-10)                                  src/codec.rs:488-489
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                {
-                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-                }
-                const float gmax0 = fmaxf(m0, 1e-10f), gmax1 = fmaxf(m1, 1e-10f);
-                const float scale0 = gmax0, scale1 = gmax1;
-                // band energies -> per-band base threshold (already times scale, :288)   :205-224
-                float *base0 = sm.band_base[warp], *base1 = sm.band_base2[warp];
-                for (int b0 = 0; b0 < n_bands; b0 += 32)
-                {
-                    const int b = b0 + lane;
-                    int lo = 0, hi = 0;
-                    if (b < n_bands)
-                    {
-                        lo = sm.band_lo[b];
-                        hi = sm.band_hi[b];
-                    }
-                    const bool wide = (hi - lo) > 32;
-                    float acc0 = 0.0f, acc1 = 0.0f;
-                    if (!wide)
-                        for (int k = lo; k < hi; ++k)
-                        {
-                            acc0 = fmaf(coef0[k], coef0[k], acc0);
-                            acc1 = fmaf(coef1[k], coef1[k], acc1);
-                        }
-                    unsigned wide_mask = __ballot_sync(0xffffffffu, wide);
-                    while (wide_mask)
-                    {
-                        const int src_lane = __ffs(wide_mask) - 1;
-                        wide_mask &= wide_mask - 1;
-                        const int wlo = __shfl_sync(0xffffffffu, lo, src_lane), whi = __shfl_sync(0xffffffffu, hi, src_lane);
-                        float p0 = 0.0f, p1 = 0.0f;
-                        for (int k = wlo + lane; k < whi; k += 32)
-                        {
-                            p0 = fmaf(coef0[k], coef0[k], p0);
-                            p1 = fmaf(coef1[k], coef1[k], p1);
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1)
-                        {
-                            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-                            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-                        }
-                        if (lane == src_lane)
-                        {
-                            acc0 = p0;
-                            acc1 = p1;
-                        }
-                    }
-                    if (b < n_bands)
-                    {
-                        const float f = sm.band_fac[b], rc = sm.band_rcnt[b];
-                        base0[b] = sqrtf(acc0 * rc) * f * scale0;
-                        base1[b] = sqrtf(acc1 * rc) * f * scale1;
-                    }
-                }
-                __syncwarp();
-                // thresholds + quantiser + ordered compaction               src/codec.rs:226-235, 277-307
-                const float nf0 = noise_floor_factor * scale0, nf1 = noise_floor_factor * scale1;
-                const float gate0 = 0.3f * gmax0, gate1 = 0.3f * gmax1;
-                const float cap0 = 0.05f * gmax0 * scale0, cap1 = 0.05f * gmax1 * scale1;
-                const float qmul0 = 32768.0f / scale0, qmul1 = 32768.0f / scale1;
-                const uint64_t row0 = sm.st_row[fa], row1 = sm.st_row[two ? fa + 1 : fa];
-                glc_pair *dst0 = p.slots + row0 * kHop, *dst1 = p.slots + row1 * kHop;
-                uint32_t total0 = 0, total1 = 0;
-                auto quant1 = [&](float v, float bs, float iw, float nf, float gate, float cap, float qmul) -> int {
-                    const float a = fabsf(v);
-                    float th = bs * iw;
-                    th = fminf(th, a > gate ? cap : th);
-                    const float x = v * qmul;
-                    // round half away from zero (f32::round) as trunc(x + copysign(0.5, x))
-                    const int q = __float2int_rz(fminf(fmaxf(x + copysignf(0.5f, x), -32768.0f), 32767.0f));
-                    return a > fmaxf(nf, th) ? q : 0;
-                };
-#pragma unroll 1
-                for (int j = 0; j < 8; ++j)
-                {
-                    const float4 c40 = *reinterpret_cast<const float4 *>(coef0 + j * 128 + lane * 4);
-                    const float4 c41 = *reinterpret_cast<const float4 *>(coef1 + j * 128 + lane * 4);
-                    const float4 iw4 = *reinterpret_cast<const float4 *>(sm.inv_w + j * 128 + lane * 4);
-                    const uchar4 bo4 = *reinterpret_cast<const uchar4 *>(sm.band_of + j * 128 + lane * 4);
-                    int q0[4], q1[4];
-                    q0[0] = quant1(c40.x, base0[bo4.x], iw4.x, nf0, gate0, cap0, qmul0);
-                    q1[0] = quant1(c41.x, base1[bo4.x], iw4.x, nf1, gate1, cap1, qmul1);
-                    q0[1] = quant1(c40.y, base0[bo4.y], iw4.y, nf0, gate0, cap0, qmul0);
-                    q1[1] = quant1(c41.y, base1[bo4.y], iw4.y, nf1, gate1, cap1, qmul1);
-                    q0[2] = quant1(c40.z, base0[bo4.z], iw4.z, nf0, gate0, cap0, qmul0);
-                    q1[2] = quant1(c41.z, base1[bo4.z], iw4.z, nf1, gate1, cap1, qmul1);
-                    q0[3] = quant1(c40.w, base0[bo4.w], iw4.w, nf0, gate0, cap0, qmul0);
-                    q1[3] = quant1(c41.w, base1[bo4.w], iw4.w, nf1, gate1, cap1, qmul1);
-                    const uint32_t cnt0 = (q0[0] != 0) + (q0[1] != 0) + (q0[2] != 0) + (q0[3] != 0);
-                    const uint32_t cnt1 = (q1[0] != 0) + (q1[1] != 0) + (q1[2] != 0) + (q1[3] != 0);
-                    // one scan for both: the two counts (<= 4 per lane, <= 128 per warp) share a register
-                    uint32_t incl = cnt0 | (cnt1 << 16);
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1)
-                    {
-                        const uint32_t nn = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o)
-                            incl += nn;
-                    }
-                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-                    uint32_t pos0 = total0 + (incl & 0xffffu) - cnt0, pos1 = total1 + (incl >> 16) - cnt1;
-                    const uint32_t kbase = (uint32_t)(j * 128 + lane * 4);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                    {
-                        if (q0[e] != 0)
-                        {
-                            glc_pair pr2;
-                            pr2.idx = (uint16_t)(kbase + e);
-                            pr2.q = (int16_t)q0[e];
-                            dst0[pos0++] = pr2;
-                        }
-                        if (two && q1[e] != 0)
-                        {
-                            glc_pair pr2;
-                            pr2.idx = (uint16_t)(kbase + e);
-                            pr2.q = (int16_t)q1[e];
-                            dst1[pos1++] = pr2;
-                        }
-                    }
-                    total0 += tot & 0xffffu;
-                    total1 += tot >> 16;
-                }
-                if (lane == 0)
-                {
-                    p.nnz[row0] = total0;
-                    p.scales[row0] = scale0;
-                    atomicAdd(&sm.frame_nnz[sm.st_lf[fa]], total0); // frame index < frames per group <= kFastFcs
-                    if (two)
-                    {
-                        p.nnz[row1] = total1;
-                        p.scales[row1] = scale1;
-                        atomicAdd(&sm.frame_nnz[sm.st_lf[fa + 1]], total1);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        // raw-PCM / sparse decision per frame                                 src/codec.rs:505-540
-        if (tid < gg.n_frames)
-        {
-            const uint64_t frame = fd.first_frame + gg.frame0 + tid;
-            const uint64_t row_f = fd.first_row + (gg.frame0 + tid) * ch;
-            const uint64_t compressed = (uint64_t)ch * 8 + (uint64_t)sm.frame_nnz[tid] * 4 + 8 + (uint64_t)ch * 4 + 64;
-            const float rhs = (float)((uint64_t)kFrame * ch * 2) * 0.85f;
-            const bool raw = (float)compressed >= rhs;
-            p.is_raw[frame] = raw ? 1 : 0;
-            p.raw_len[frame] = raw ? (uint32_t)(kFrame * ch) : 0u;
-            if (raw)
-                for (uint32_t c = 0; c < ch; ++c)
-                {
-                    p.nnz[row_f + c] = 0;
-                    p.scales[row_f + c] = 0.0f;
-                }
-        }
-    }
-}
-
 // ------------------------------------------------------------------ decode
 
 // One CTA per 8 rows: dequantise into the (c[2n], c[N-1-2n]) layout, DCT-IV, unfold, synthesis window.
@@ -736,26 +288,6 @@ void fast_twiddle_table(float norm, float *out /* kFastTwiddleFloats */)
         out[2 * (512 + k2)] = (float)(cos(a) * (double)norm);
         out[2 * (512 + k2) + 1] = (float)(sin(a) * (double)norm);
     }
-}
-
-uint64_t fast_groups_for(uint32_t n_frames, uint32_t channels)
-{
-    const uint32_t fpg = kFastFcs / channels ? kFastFcs / channels : 1u;
-    return ((uint64_t)n_frames + fpg - 1) / fpg;
-}
-
-cudaError_t launch_fast_encode(const FastEncodeLaunch &p, cudaStream_t s)
-{
-    if (p.group_end <= p.group_begin)
-        return cudaSuccess;
-    GLC_SET_MAX_DYN_SMEM_ONCE(fast_encode_kernel, sizeof(FastSmem));
-    // persistent CTAs: 4 resident per SM, grid-stride over the frame groups
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint64_t grid = std::min<uint64_t>(p.group_end - p.group_begin, (uint64_t)sms * 4);
-    fast_encode_kernel<<<(unsigned)grid, kFastThreads, sizeof(FastSmem), s>>>(p);
-    return cudaGetLastError();
 }
 
 cudaError_t launch_fast_decode(const FastDecodeLaunch &p, cudaStream_t s)

@@ -239,12 +239,23 @@ struct FastEncodeLaunch
     const float2 *twiddles; // fast_twiddle_table
     float norm;
     const DevPerceptual *perc;
-    glc_pair *slots;   // [n_rows][1024]
-    uint32_t *nnz;     // [n_rows]
-    float *scales;     // [n_rows]
-    uint8_t *is_raw;   // [n_frames_total]
-    uint32_t *raw_len; // [n_frames_total]
+    // fast_encode_kernel: per-row / per-frame results + every group's compact block in its slot
+    uint32_t *nnz;       // [n_rows]
+    float *scales;       // [n_rows]
+    uint8_t *is_raw;     // [n_frames_total]
+    glc_pair *slots;     // [n_rows][1024]: a group's rows are its slot (pairs to the front, raw bodies to the back)
+    uint32_t *grp_pairs; // [n_groups] pairs of the group's sparse frames
+    uint32_t *grp_raw;   // [n_groups] frame-channels of the group's raw frames (units of 2048 i16)
+    unsigned int *ticket; // group counter of THIS launch, zero at launch
+    // fast_place_kernel: exclusive scans of the two totals -> final positions
+    const uint64_t *grp_pair_off; // [n_groups + 1]
+    const uint64_t *grp_raw_off;  // [n_groups + 1]
+    uint64_t *pair_off;  // [n_rows + 1]
+    uint64_t *raw_off;   // [n_frames_total + 1]
+    glc_pair *pairs;
+    int16_t *raw;
 };
+cudaError_t launch_fast_place(const FastEncodeLaunch &p, cudaStream_t s);
 constexpr int kFastTwiddleFloats = 2 * (32 * 16 + 16);
 void fast_twiddle_table(float norm, float *out); // host, double precision
 uint64_t fast_groups_for(uint32_t n_frames, uint32_t channels);

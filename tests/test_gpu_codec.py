@@ -397,10 +397,14 @@ def test_sharded_batch_over_several_contexts(gpu_ctx):
         fl, _ = shard.flac_encode_batch_devices(ctxs, files[:6], [44100] * 6, chans[:6], 5)
         for i in range(6):
             assert fl[i] == flac.encode_flac_with_level(files[i], 44100, chans[i], 5, gpu_ctx), f"sharded flac, file {i}"
-        # a failing shard fails the call with that shard's message
+        # every file is validated before anything is planned (a too-short file must not reach the planner's weights)
         with pytest.raises(Exception) as e:
             shard.encode_batch_devices(encs, [files[0], np.zeros(100, np.float32)], [2, 1])
-        assert "shard" in str(e.value)
+        assert "file 1" in str(e.value) and e.value.status == 2
+        # a failing shard fails the call with that shard's message; the other shards' outputs are released
+        with pytest.raises(Exception) as e:
+            shard.flac_encode_batch_devices(ctxs, [files[0], files[1], np.zeros(10, np.float32)], [44100] * 3, [2, 2, 1], 5)
+        assert "shard" in str(e.value) and e.value.status == 4
     finally:
         del encs
         for c in ctxs:
