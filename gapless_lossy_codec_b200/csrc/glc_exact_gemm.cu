@@ -279,7 +279,11 @@ cudaError_t launch_gemm(const GemmParams &p, uint64_t m_tiles, cudaStream_t s)
 // 20.1, 4-row warps 15.7, 2-row warps with 16-index stages 14.8).  What is left is the per-step bookkeeping (12 of 44 instructions) and warps of
 // one CTA waiting for each other at the ring; with every mask forced to all-ones the same kernel runs
 // at the full issue rate, i.e. the pipeline itself is not the limit.
-constexpr int kImdctRing = 2;
+#ifndef GLC_IMDCT_RING
+#define GLC_IMDCT_RING 2
+#endif
+constexpr int kImdctRing = GLC_IMDCT_RING;
+constexpr int kImdctNQ = kImdctBN / 128; // float4 chunks of outputs per thread (lane*4 + 128 q)
 struct ImdctSmem
 {
     float a[kImdctRing][kImdctAStageFloats];
@@ -290,8 +294,12 @@ struct ImdctSmem
     uint8_t stage_list[kImdctStages]; // the tile's stages
 };
 static_assert((kImdctAStageFloats * 4) % 16 == 0, "bulk copies need 16-byte granularity");
+static_assert(kImdctRowsPerWarp == 1 || kImdctRowsPerWarp == 2, "a warp owns one row or a pair of rows");
 
-__global__ void __launch_bounds__(kImdctThreads, kImdctRowsPerWarp == 2 ? 3 : 4) imdct_sparse_kernel(const __grid_constant__ GemmParams p)
+#ifndef GLC_IMDCT_MINB
+#define GLC_IMDCT_MINB (GLC_IMDCT_RW == 2 && GLC_IMDCT_BN == 256 ? 3 : 1)
+#endif
+__global__ void __launch_bounds__(kImdctThreads, GLC_IMDCT_MINB) imdct_sparse_kernel(const __grid_constant__ GemmParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ImdctSmem &sm = *reinterpret_cast<ImdctSmem *>(smem_raw);
@@ -347,11 +355,12 @@ __global__ void __launch_bounds__(kImdctThreads, kImdctRowsPerWarp == 2 ? 3 : 4)
             issue(s);
 
     constexpr int RW = kImdctRowsPerWarp;
-    float acc[RW][8];
+    constexpr int NO = 4 * kImdctNQ; // outputs per thread and row
+    float acc[RW][NO];
 #pragma unroll
     for (int r = 0; r < RW; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < NO; ++c)
             acc[r][c] = 0.0f;
 
     for (int s = 0; s < n_stages; ++s)
@@ -370,28 +379,23 @@ __global__ void __launch_bounds__(kImdctThreads, kImdctRowsPerWarp == 2 ? 3 : 4)
             rm ^= 0x80000000u >> ii; // the bit is known to be set
             float a[RW];
             if constexpr (RW == 2)
-            {
                 asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[0]), "=f"(a[1]) : "r"(a_base + ii * (kImdctBM * 4)));
-            }
             else
-            {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[0]) : "r"(a_base + ii * (kImdctBM * 4)));
+            float t[NO];
 #pragma unroll
-                for (int r4 = 0; r4 < RW / 4; ++r4)
-                {
-                    const float4 v = lds128(a_base + ii * (kImdctBM * 4) + r4 * 16);
-                    a[r4 * 4 + 0] = v.x;
-                    a[r4 * 4 + 1] = v.y;
-                    a[r4 * 4 + 2] = v.z;
-                    a[r4 * 4 + 3] = v.w;
-                }
+            for (int q = 0; q < kImdctNQ; ++q)
+            {
+                const float4 v = lds128(t_base + ii * (kImdctBN * 4) + q * 512);
+                t[4 * q + 0] = v.x;
+                t[4 * q + 1] = v.y;
+                t[4 * q + 2] = v.z;
+                t[4 * q + 3] = v.w;
             }
-            const float4 t_lo = lds128(t_base + ii * (kImdctBN * 4));
-            const float4 t_hi = lds128(t_base + ii * (kImdctBN * 4) + 512);
-            const float t[8] = {t_lo.x, t_lo.y, t_lo.z, t_lo.w, t_hi.x, t_hi.y, t_hi.z, t_hi.w};
 #pragma unroll
             for (int r = 0; r < RW; ++r)
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
+                for (int c = 0; c < NO; ++c)
                     acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
         }
         __syncwarp();
@@ -411,33 +415,26 @@ __global__ void __launch_bounds__(kImdctThreads, kImdctRowsPerWarp == 2 ? 3 : 4)
         }
     }
 
-    // ---- epilogue: * norm, * window, 2 x float4 per row (a warp writes 2 x 512 contiguous bytes) ----
-    const int n_lo = n_block * kImdctBN + lane * 4;
-    const int n_hi = n_lo + 128;
-    const float4 w_lo = __ldg(reinterpret_cast<const float4 *>(p.window + n_lo));
-    const float4 w_hi = __ldg(reinterpret_cast<const float4 *>(p.window + n_hi));
+    // ---- epilogue: * norm, * window, float4 per 128 outputs (a warp writes contiguous 512-byte runs) ----
     const uint64_t row0 = m_tile * kImdctBM + warp * RW;
 #pragma unroll
-    for (int r = 0; r < RW; ++r)
+    for (int q = 0; q < kImdctNQ; ++q)
     {
-        const uint64_t row = row0 + r;
-        if (row >= p.n_rows)
-            continue;
-        float v[8];
+        const int n0 = n_block * kImdctBN + lane * 4 + 128 * q;
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(p.window + n0));
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            v[c] = __fmul_rn(acc[r][c], p.norm);
-        v[0] = __fmul_rn(v[0], w_lo.x);
-        v[1] = __fmul_rn(v[1], w_lo.y);
-        v[2] = __fmul_rn(v[2], w_lo.z);
-        v[3] = __fmul_rn(v[3], w_lo.w);
-        v[4] = __fmul_rn(v[4], w_hi.x);
-        v[5] = __fmul_rn(v[5], w_hi.y);
-        v[6] = __fmul_rn(v[6], w_hi.z);
-        v[7] = __fmul_rn(v[7], w_hi.w);
-        float *orow = p.out + row * kFrame;
-        *reinterpret_cast<float4 *>(orow + n_lo) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(orow + n_hi) = make_float4(v[4], v[5], v[6], v[7]);
+        for (int r = 0; r < RW; ++r)
+        {
+            const uint64_t row = row0 + r;
+            if (row >= p.n_rows)
+                continue;
+            float4 v;
+            v.x = __fmul_rn(__fmul_rn(acc[r][4 * q + 0], p.norm), w.x);
+            v.y = __fmul_rn(__fmul_rn(acc[r][4 * q + 1], p.norm), w.y);
+            v.z = __fmul_rn(__fmul_rn(acc[r][4 * q + 2], p.norm), w.z);
+            v.w = __fmul_rn(__fmul_rn(acc[r][4 * q + 3], p.norm), w.w);
+            *reinterpret_cast<float4 *>(p.out + row * kFrame + n0) = v;
+        }
     }
 }
 

@@ -25,11 +25,26 @@ constexpr int kGemmThreads = 256;
 // IMDCT (warp-sparse variant): tiles of kImdctBM compacted rows; a warp owns kImdctRowsPerWarp rows of
 // the tile and all kImdctBN outputs of the CTA; a pipeline stage is kImdctKC consecutive coefficient
 // indices and one A stage carries, after its [kImdctKC][kImdctBM] values, one step mask per warp.
+// The shape is a compile-time choice (tools/imdct_sweep.sh builds and times variants on the GPU box).
+// Measured on the hour-long bench signal: 2 rows x 256 outputs per warp, 32-index
+// stages, 2-slot ring, 3 CTAs/SM = 13.85 ms; 1 row x 512 outputs (no union of index sets, 16 accumulators
+// per thread, 1 CTA of 32 warps) = 15.6 ms; 2 rows x 512 outputs = 15.2 ms -- a thread's table operand is
+// used by `rows per warp` rows only, and below two rows per warp the kernel is bound by shared-memory
+// wavefronts (17 per 32 arithmetic instructions) instead of by issue slots.
+#ifndef GLC_IMDCT_BN
+#define GLC_IMDCT_BN 256
+#endif
+#ifndef GLC_IMDCT_KC
+#define GLC_IMDCT_KC 32
+#endif
+#ifndef GLC_IMDCT_RW
+#define GLC_IMDCT_RW 2
+#endif
 constexpr int kImdctBM = 32;
-constexpr int kImdctBN = 256;
-constexpr int kImdctKC = 32;
+constexpr int kImdctBN = GLC_IMDCT_BN;
+constexpr int kImdctKC = GLC_IMDCT_KC;
 constexpr int kImdctStages = kHop / kImdctKC;                          // 32
-constexpr int kImdctRowsPerWarp = 2;
+constexpr int kImdctRowsPerWarp = GLC_IMDCT_RW;
 constexpr int kImdctWarps = kImdctBM / kImdctRowsPerWarp;              // 16
 constexpr int kImdctThreads = kImdctWarps * 32;                        // 512
 constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctWarps;  // 1024 values + 16 masks = 4 160 B
