@@ -288,9 +288,17 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         L.glc_dev_encoded_free(de)
         return ms_e.value, ms_d.value
 
-    def host_step():
+    def host_step(src=None, probe=False):
+        """Encoder::encode then Decoder::decode through the C ABI with host buffers.  src: the PCM (default: the
+        library-pinned copy).  probe=True additionally records per-call DMA bytes and workload statistics."""
+        src = xp if src is None else src
         out = C.POINTER(_ffi.Encoded)()
-        chk(L.glc_encode(enc_h, xp.ctypes.data, xp.size, CH, C.byref(out)))
+        if probe:
+            ctx.stats_reset()
+        chk(L.glc_encode(enc_h, src.ctypes.data, src.size, CH, C.byref(out)))
+        if probe:
+            s_e = ctx.stats()
+            ctx.stats_reset()
         p, n = C.POINTER(C.c_float)(), C.c_uint64()
         chk(L.glc_decode(dec_h, out, C.byref(p), C.byref(n)))
         got = n.value
@@ -298,6 +306,27 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         e = out.contents
         host_step.pairs = int(e.pair_offset[int(e.n_frames) * int(e.channels)]) if e.n_frames else 0
         host_step.raw = int(e.raw_offset[int(e.n_frames)]) if e.n_frames else 0
+        if probe:
+            s_d = ctx.stats()
+            host_step.bytes = {"enc_h2d": s_e["h2d_bytes"], "enc_d2h": s_e["d2h_bytes"],
+                               "dec_h2d": s_d["h2d_bytes"], "dec_d2h": s_d["d2h_bytes"]}
+            # measured workload statistics: raw-frame share, kept coefficients per sparse
+            # frame-channel, and the size of the index-set union of the two channels of a frame (what a 2-row
+            # warp of the IMDCT kernel executes) over a sample of frames
+            nf, ch = int(e.n_frames), int(e.channels)
+            raw = np.ctypeslib.as_array(e.frame_is_raw, (nf,))
+            n_raw = int(raw.sum())
+            nnz = np.ctypeslib.as_array(e.nnz, (nf * ch,))
+            po = np.ctypeslib.as_array(e.pair_offset, (nf * ch + 1,))
+            sparse_rows = max(1, (nf - n_raw) * ch)
+            unions = []
+            idx = np.ctypeslib.as_array(C.cast(e.pairs, C.POINTER(C.c_uint16)), (2 * max(host_step.pairs, 1),))[0::2]
+            for f in np.flatnonzero(raw == 0)[:: max(1, (nf - n_raw) // 2000)][:2000]:
+                a, b, c2 = int(po[f * ch]), int(po[f * ch + 1]), int(po[f * ch + 2]) if ch > 1 else int(po[f * ch + 1])
+                unions.append(len(np.union1d(idx[a:b], idx[b:c2])))
+            host_step.workload = {"raw_frame_fraction": n_raw / max(nf, 1), "mean_nnz_per_sparse_row": float(nnz.sum()) / sparse_rows,
+                                  "mean_union_of_2_rows": float(np.mean(unions)) if unions else None,
+                                  "union_sample_frames": len(unions)}
         L.glc_free(ctx.handle, p)
         L.glc_encoded_free(ctx.handle, out)
         return got, first
@@ -349,6 +378,40 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     st2 = ctx.stats()
     e2e_ms = max_over_ranks(e2e_s / args.steps * 1e3)
     launches += sum(st2["launches"].values())
+
+    # ---- timed region 2b: the same round trip with the PCM in ORDINARY (pageable) memory, what a caller of
+    #      Encoder::encode(&[f32]) hands over (src/codec.rs:421); the library stages it through pinned chunks ----
+    x_pageable = np.array(xp, copy=True)  # numpy heap memory: not pinned
+    host_step(x_pageable, probe=True)     # warm-up + per-call DMA bytes + workload statistics
+    host_step(x_pageable)
+    barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    n_pg = max(2, min(args.steps, 5))
+    for _ in range(n_pg):
+        got, _first = host_step(x_pageable)
+        assert got == xp.size
+    ctx.sync()
+    e2e_pg_ms = max_over_ranks((time.perf_counter() - t0) / n_pg * 1e3)
+    barrier()
+    del x_pageable
+
+    # ---- pure-DMA floor: the bytes of one encode call and of one decode call, up and down at once, pinned host
+    #      memory <-> HBM, no kernel, every rank at the same time ----
+    def dma(h2d, d2h, concurrent):
+        ms = C.c_float()
+        best = 1e30
+        for _ in range(3):
+            barrier()
+            chk(L.glc_dma_probe(ctx.handle, int(h2d), int(d2h), int(concurrent), C.byref(ms)))
+            best = min(best, max_over_ranks(ms.value))
+        return best
+    hb = host_step.bytes
+    dma_enc = dma(hb["enc_h2d"], hb["enc_d2h"], 1)
+    dma_dec = dma(hb["dec_h2d"], hb["dec_d2h"], 1)
+    dma_h2d_only = dma(hb["enc_h2d"], 0, 0)
+    dma_d2h_only = dma(0, hb["dec_d2h"], 0)
+    t_region1 = time.perf_counter()
 
     # ---- timed region 3: the same round trip with 16-bit integer ingest (glc_encode_i16: the WAV
     #      loader's division runs on the device, half the H2D bytes) ----
@@ -450,6 +513,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "kernel": "exact_gemm_kernel<MDCT> (direct-form MDCT contraction, EXACT mode; operands by TMA bulk copy)",
         "bound": "fp32_issue", "achieved": achieved_tops, "peak": fp32_roof, "unit": "TFLOP/s",
         "frac": achieved_tops / fp32_roof if fp32_roof else None,
+        # nominal: 148 SMs x 128 FP32 lanes x the maximum SM clock, one non-FMA operation per lane and cycle
+        "peak_nominal": 148 * 128 * (clocks["sm_max_mhz"] if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e6 / 1e12,
+        "frac_of_nominal": achieved_tops / (148 * 128 * (clocks["sm_max_mhz"] if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e6 / 1e12),
         "peak_source": "FMUL+FADD issue micro-benchmark on this GPU in this run (glc_measure_fp32_issue); "
                        "non-FMA FP32 lane-ops: tensor cores / FMA / reordering break bit-exact parity",
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
@@ -471,14 +537,30 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"batched encode+decode of {secs:.0f} s synthetic 44.1 kHz stereo PCM per GPU "
-                               f"({n_frames} frames, {rows} frame-channels; ~30 % raw-PCM frames)",
+                               f"({n_frames} frames, {rows} frame-channels)",
+                   "measured": host_step.workload,
                    "mode": ("FAST (FFT-based true MDCT, tolerance class -- NOT bit-exact with the reference)" if fast
                             else "EXACT (bit-exact with the reference arithmetic)"), "sharding": f"by file, {world} rank(s), no collective",
                    "l2": f"inputs larger than L2 ({xp.size * 4 / 1e6:.0f} MB PCM per step vs 126 MB)"},
         "encode_value": total_secs / (enc_ms_max * 1e-3), "decode_value": total_secs / (dec_ms_max * 1e-3),
         "e2e": {"value": total_secs / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps,
-                "ms_per_step": e2e_ms, "api": "glc_encode + glc_decode (C ABI, pinned host buffers)"},
+                "ms_per_step": e2e_ms, "api": "glc_encode + glc_decode (C ABI, pinned host buffers)",
+                # the same bytes as pure DMA (no kernels), every rank at once: encode call (PCM up || stream down)
+                # + decode call (stream up || PCM down).  e2e cannot be faster than this on this box.
+                "dma_floor_ms": dma_enc + dma_dec, "dma_floor_encode_ms": dma_enc, "dma_floor_decode_ms": dma_dec,
+                "dma_floor_frac": (dma_enc + dma_dec) / e2e_ms,
+                # each call can hide its kernels behind its transfers or the other way round, never both: the
+                # floor of two separate calls is max(device time, DMA time) per call
+                "floor_ms": max(enc_ms_max, dma_enc) + max(dec_ms_max, dma_dec),
+                "floor_frac": (max(enc_ms_max, dma_enc) + max(dec_ms_max, dma_dec)) / e2e_ms,
+                "dma_h2d_gbs_per_gpu": hb["enc_h2d"] / (dma_h2d_only * 1e-3) / 1e9,
+                "dma_d2h_gbs_per_gpu": hb["dec_d2h"] / (dma_d2h_only * 1e-3) / 1e9,
+                "bytes_per_call": hb},
+        "e2e_pageable": {"value": total_secs / (e2e_pg_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_pg_ms,
+                         "vs_pinned": e2e_ms / e2e_pg_ms,
+                         "api": "glc_encode + glc_decode with the PCM in ordinary pageable memory (staged through a "
+                                "ring of pinned chunks by host threads)"},
         "e2e_int16_ingest": {"value": total_secs / (e2e16_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e16_ms,
                              "h2d_bytes_per_step": st3["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st3["d2h_bytes"] // args.steps,
                              "api": "glc_encode_i16 + glc_decode (16-bit PCM in, f32 PCM out)"},

@@ -81,7 +81,7 @@ EXPORTS = [
     "glc_stats_reset", "glc_stats_get", "glc_stats_enable_kernel_timing",
     "glc_dev_upload", "glc_dev_pcm_free", "glc_dev_encode", "glc_dev_decode",
     "glc_dev_encoded_download", "glc_dev_pcm_download", "glc_dev_encoded_free",
-    "glc_timer_begin", "glc_timer_end", "glc_ctx_sync", "glc_flush_l2", "glc_measure_fp32_issue",
+    "glc_timer_begin", "glc_timer_end", "glc_ctx_sync", "glc_flush_l2", "glc_measure_fp32_issue", "glc_dma_probe",
 ]
 
 _lib = None
@@ -154,6 +154,7 @@ def load() -> C.CDLL:
         "glc_ctx_sync": (C.c_int, [vp]),
         "glc_flush_l2": (C.c_int, [vp]),
         "glc_measure_fp32_issue": (C.c_int, [vp, C.c_int, pp(C.c_double)]),
+        "glc_dma_probe": (C.c_int, [vp, u64, u64, C.c_int, pp(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

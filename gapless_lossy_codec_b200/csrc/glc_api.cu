@@ -16,9 +16,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -29,6 +31,13 @@ using namespace glc;
 // ------------------------------------------------------------------ errors
 
 static thread_local std::string g_last_error;
+
+static double PhaseTraceNow()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 static glc_status fail(glc_status st, const char *fmt, ...)
 {
@@ -140,6 +149,14 @@ struct PinnedPool
             }
         return false;
     }
+    bool owns(const void *p) // p points into one of the pool's blocks
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &b : blocks)
+            if ((const char *)p >= (const char *)b.p && (const char *)p < (const char *)b.p + b.cap)
+                return true;
+        return false;
+    }
     void destroy()
     {
         for (auto &b : blocks)
@@ -247,6 +264,105 @@ struct DevicePool
     }
 };
 
+// ------------------------------------------------ pageable host memory -> device
+//
+// The reference's entry points take borrowed slices (`Encoder::encode(&mut self, samples: &[f32], ..)`,
+// src/codec.rs:421; `Decoder::decode(&EncodedAudio)`, :744): ordinary pageable memory.  cudaMemcpyAsync from
+// pageable memory is staged by the driver through one internal buffer, synchronously, at a fraction of the
+// PCIe rate.  Here a few host threads copy the caller's bytes into a ring of pinned chunks while the DMA
+// engine drains the chunks filled before: the transfer then runs at min(host memcpy rate, PCIe rate) and
+// overlaps the kernels of the previous wave like a pinned transfer does.
+class ParallelMemcpy
+{
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    const char *src = nullptr;
+    char *dst = nullptr;
+    size_t bytes = 0;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    static void part(const char *s, char *d, size_t n, int i, int k)
+    {
+        const size_t a = (n * (size_t)i / (size_t)k) & ~(size_t)63, b = i + 1 == k ? n : ((n * (size_t)(i + 1) / (size_t)k) & ~(size_t)63);
+        if (b > a)
+            memcpy(d + a, s + a, b - a);
+    }
+    void run(int idx)
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return stop || generation != seen; });
+            if (stop)
+                return;
+            seen = generation;
+            const char *s = src;
+            char *d = dst;
+            const size_t n = bytes;
+            const int k = (int)workers.size() + 1;
+            lk.unlock();
+            part(s, d, n, idx + 1, k);
+            lk.lock();
+            if (--pending == 0)
+                cv_done.notify_one();
+        }
+    }
+
+  public:
+    void start(int n_workers)
+    {
+        for (int i = 0; i < n_workers; ++i)
+            workers.emplace_back([this, i] { run(i); });
+    }
+    // copies on the calling thread plus the workers; returns when every byte is in place
+    void copy(void *d, const void *s, size_t n)
+    {
+        if (workers.empty() || n < ((size_t)1 << 20))
+        {
+            memcpy(d, s, n);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            src = (const char *)s;
+            dst = (char *)d;
+            bytes = n;
+            pending = (int)workers.size();
+            ++generation;
+        }
+        cv.notify_all();
+        part((const char *)s, (char *)d, n, 0, (int)workers.size() + 1);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~ParallelMemcpy()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : workers)
+            t.join();
+    }
+};
+
+struct HostStager
+{
+    static constexpr size_t kChunk = (size_t)8 << 20; // bytes per pinned chunk
+    static constexpr int kSlots = 4;
+    void *slot[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done[kSlots];
+    bool busy[kSlots] = {false, false, false, false};
+    int next = 0;
+    bool ready = false;
+    ParallelMemcpy pm;
+};
+
 // ------------------------------------------------------------------ context
 
 struct TimedLaunch
@@ -279,6 +395,8 @@ struct glc_ctx
     uint64_t wave_frames;
     float *d_flush;
     size_t flush_floats;
+    HostStager *stager = nullptr; // created on the first transfer from pageable memory
+    uint64_t staged_bytes = 0;    // bytes that went through the stager (statistics)
 };
 
 struct glc_encoder
@@ -425,6 +543,16 @@ extern "C" void glc_ctx_destroy(glc_ctx *c)
     cudaFree(c->d_fast_tw);
     if (c->d_flush)
         cudaFree(c->d_flush);
+    if (c->stager)
+    {
+        for (int i = 0; i < HostStager::kSlots; ++i)
+            if (c->stager->slot[i])
+            {
+                cudaEventDestroy(c->stager->done[i]);
+                cudaFreeHost(c->stager->slot[i]);
+            }
+        delete c->stager;
+    }
     c->pool.destroy();
     c->dpool.destroy();
     free_host_tables(&c->host);
@@ -634,6 +762,7 @@ glc_ctx *decoder_ctx(glc_decoder *dec) { return dec->ctx; }
 cudaStream_t ctx_compute_stream(glc_ctx *ctx) { return ctx->compute; }
 cudaStream_t ctx_d2h_stream(glc_ctx *ctx) { return ctx->d2h; }
 void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n) { ctx->stats.launches[kernel_id] += n; }
+cudaError_t ctx_h2d(glc_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t s);
 void ctx_count_bytes(glc_ctx *ctx, uint64_t h2d, uint64_t d2h)
 {
     ctx->stats.h2d_bytes += h2d;
@@ -660,6 +789,87 @@ void ctx_time_end(glc_ctx *ctx, void *token)
     cudaEventRecord(t->b, ctx->compute);
     ctx->timed.push_back(*t);
     delete t;
+}
+} // namespace glc
+
+
+// true when the DMA engine can read `p` directly: the library's own pinned pool, or memory the caller pinned
+static bool host_ptr_is_pinned(glc_ctx *c, const void *p)
+{
+    if (c->pool.owns(p))
+        return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// Host -> device on `stream`.  Pinned sources go to the DMA engine as they are; pageable ones above 256 KiB
+// pass through the stager's ring (see HostStager).  Returns after the LAST byte has been handed to a pinned
+// chunk, i.e. the caller's buffer is no longer needed once the function returns... for pageable sources; for
+// pinned ones it must stay valid until the stream reaches the copy, as with cudaMemcpyAsync.
+static cudaError_t h2d_async(glc_ctx *c, void *dst, const void *src, size_t bytes, bool pinned, cudaStream_t stream)
+{
+    if (bytes == 0)
+        return cudaSuccess;
+    if (pinned || bytes < ((size_t)256 << 10))
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    if (!c->stager)
+        c->stager = new HostStager();
+    HostStager &st = *c->stager;
+    if (!st.ready)
+    {
+        for (int i = 0; i < HostStager::kSlots; ++i)
+        {
+            cudaError_t e = cudaHostAlloc(&st.slot[i], HostStager::kChunk, cudaHostAllocDefault);
+            if (e != cudaSuccess)
+                return e;
+            e = cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming);
+            if (e != cudaSuccess)
+                return e;
+        }
+        int n = 3; // + the calling thread
+        if (const char *v = getenv("GLC_COPY_THREADS"))
+            n = std::max(0, atoi(v) - 1);
+        st.pm.start(n);
+        st.ready = true;
+    }
+    const char *s = (const char *)src;
+    char *d = (char *)dst;
+    while (bytes)
+    {
+        const size_t n = std::min(bytes, HostStager::kChunk);
+        const int i = st.next;
+        st.next = (st.next + 1) % HostStager::kSlots;
+        if (st.busy[i])
+        {
+            cudaError_t e = cudaEventSynchronize(st.done[i]); // the DMA engine is done with this chunk
+            if (e != cudaSuccess)
+                return e;
+        }
+        st.pm.copy(st.slot[i], s, n);
+        cudaError_t e = cudaMemcpyAsync(d, st.slot[i], n, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(st.done[i], stream);
+        if (e != cudaSuccess)
+            return e;
+        st.busy[i] = true;
+        c->staged_bytes += n;
+        s += n;
+        d += n;
+        bytes -= n;
+    }
+    return cudaSuccess;
+}
+
+namespace glc
+{
+cudaError_t ctx_h2d(glc_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t s)
+{
+    return h2d_async(ctx, dst, src, bytes, host_ptr_is_pinned(ctx, src), s);
 }
 } // namespace glc
 
@@ -868,6 +1078,47 @@ static std::vector<Wave> plan_waves(const std::vector<Desc> &files, uint64_t tot
 }
 
 static const uint64_t kRowQuantum = 37ull * kBM;
+
+extern "C" glc_status glc_dma_probe(glc_ctx *c, uint64_t h2d_bytes, uint64_t d2h_bytes, int concurrent, float *elapsed_ms)
+{
+    if (!c || !elapsed_ms)
+        return fail(GLC_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    DevScope ds(c, c->compute);
+    char *d_up = nullptr, *d_down = nullptr;
+    CUDA_TRY(ds.alloc(&d_up, (size_t)std::max<uint64_t>(h2d_bytes, 16)));
+    CUDA_TRY(ds.alloc(&d_down, (size_t)std::max<uint64_t>(d2h_bytes, 16)));
+    void *h_up = c->pool.alloc(std::max<uint64_t>(h2d_bytes, 16)), *h_down = c->pool.alloc(std::max<uint64_t>(d2h_bytes, 16));
+    if (!h_up || !h_down)
+    {
+        if (h_up)
+            c->pool.release(h_up);
+        if (h_down)
+            c->pool.release(h_down);
+        return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
+    }
+    memset(h_up, 1, (size_t)std::max<uint64_t>(h2d_bytes, 16)); // touch: the pages exist before the clock starts
+    memset(h_down, 1, (size_t)std::max<uint64_t>(d2h_bytes, 16));
+    cudaError_t e = cudaStreamSynchronize(c->compute);
+    const double t0 = PhaseTraceNow();
+    if (e == cudaSuccess && h2d_bytes)
+        e = cudaMemcpyAsync(d_up, h_up, h2d_bytes, cudaMemcpyHostToDevice, c->copy);
+    if (e == cudaSuccess && !concurrent)
+        e = cudaStreamSynchronize(c->copy);
+    if (e == cudaSuccess && d2h_bytes)
+        e = cudaMemcpyAsync(h_down, d_down, d2h_bytes, cudaMemcpyDeviceToHost, c->d2h);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->copy);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->d2h);
+    const double t1 = PhaseTraceNow();
+    c->pool.release(h_up);
+    c->pool.release(h_down);
+    if (e != cudaSuccess)
+        return fail(GLC_ERR_CUDA, "DMA probe failed: %s", cudaGetErrorString(e));
+    *elapsed_ms = (float)(t1 - t0);
+    return GLC_OK;
+}
 
 // ------------------------------------------------- device-resident objects
 
@@ -1199,6 +1450,13 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         c->stats.d2h_bytes += (p1 - p0) * sizeof(glc_pair) + (q1 - q0) * sizeof(int16_t);
         return GLC_OK;
     };
+    std::vector<char> file_pinned; // per file: can the DMA engine read the caller's buffer directly?
+    if (host_pcm)
+    {
+        file_pinned.resize(n_files);
+        for (uint32_t i = 0; i < n_files; ++i)
+            file_pinned[i] = host_ptr_is_pinned(c, host_pcm->ptr[i]) ? 1 : 0;
+    }
     std::vector<std::pair<uint64_t, uint64_t>> pending_convert; // (arena offset, count) of integer samples to convert
     uint32_t copy_file = 0;      // next file with bytes left to copy
     uint64_t copy_done = 0;      // interleaved samples of copy_file already enqueued
@@ -1223,9 +1481,9 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
                 {
                     const size_t eb = (size_t)host_pcm->elem_bytes;
                     char *dst_h2d = host_pcm->is_int ? (char *)host_pcm->d_stage : (char *)d_arena;
-                    CUDA_TRY(cudaMemcpyAsync(dst_h2d + (fd.pcm_off + copy_done) * eb,
-                                             (const char *)host_pcm->ptr[copy_file] + copy_done * eb,
-                                             (need - copy_done) * eb, cudaMemcpyHostToDevice, c->copy));
+                    CUDA_TRY(h2d_async(c, dst_h2d + (fd.pcm_off + copy_done) * eb,
+                                       (const char *)host_pcm->ptr[copy_file] + copy_done * eb, (need - copy_done) * eb,
+                                       file_pinned[copy_file] != 0, c->copy));
                     c->stats.h2d_bytes += (need - copy_done) * eb;
                     if (host_pcm->is_int)
                         pending_convert.push_back({fd.pcm_off + copy_done, need - copy_done});
@@ -1741,6 +1999,7 @@ struct DecodeHostIO
     const uint64_t *win_len;        // [n_files] number of values kept
     glc_pair *d_pairs;              // device arrays being filled wave by wave
     int16_t *d_raw;
+    const char *pinned;             // [n_files] the stream's pairs AND raw arrays can be read by the DMA engine
 };
 
 // Device part of a batched decode.  With io == nullptr the stream arrays are already on the device
@@ -1851,8 +2110,8 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
                     const uint64_t p0 = io->h_pair_off[a], p1 = io->h_pair_off[b], pf = io->h_pair_off[f.first_row];
                     if (p1 > p0)
                     {
-                        CUDA_TRY(cudaMemcpyAsync(io->d_pairs + p0, io->enc[i]->pairs + (p0 - pf), (p1 - p0) * 4,
-                                                 cudaMemcpyHostToDevice, c->copy));
+                        CUDA_TRY(h2d_async(c, io->d_pairs + p0, io->enc[i]->pairs + (p0 - pf), (p1 - p0) * 4,
+                                           io->pinned[i] != 0, c->copy));
                         c->stats.h2d_bytes += (p1 - p0) * 4;
                         any = true;
                     }
@@ -1863,8 +2122,8 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
                     const uint64_t q0 = io->h_raw_off[fa], q1 = io->h_raw_off[fb], qf = io->h_raw_off[f.first_frame];
                     if (q1 > q0)
                     {
-                        CUDA_TRY(cudaMemcpyAsync(io->d_raw + q0, io->enc[i]->raw + (q0 - qf), (q1 - q0) * 2,
-                                                 cudaMemcpyHostToDevice, c->copy));
+                        CUDA_TRY(h2d_async(c, io->d_raw + q0, io->enc[i]->raw + (q0 - qf), (q1 - q0) * 2,
+                                           io->pinned[i] != 0, c->copy));
                         c->stats.h2d_bytes += (q1 - q0) * 2;
                         any = true;
                     }
@@ -2185,6 +2444,13 @@ static glc_status decode_batch_impl(glc_decoder *dec, uint32_t n_files, const gl
     io.win_len = win_len.data();
     io.d_pairs = d_pairs;
     io.d_raw = d_raw;
+    std::vector<char> enc_pinned(n_files);
+    for (uint32_t i = 0; i < n_files; ++i)
+        enc_pinned[i] = (enc[i]->n_frames == 0 || ((!enc[i]->pairs || host_ptr_is_pinned(c, enc[i]->pairs)) &&
+                                                    (!enc[i]->raw || host_ptr_is_pinned(c, enc[i]->raw))))
+                            ? 1
+                            : 0;
+    io.pinned = enc_pinned.data();
     float *d_out = nullptr;
     glc_status st = decode_core(c, files, rows, frames, outv, d_is_raw, d_pair_off, d_pairs, d_scales, d_raw_off,
                                 d_raw, &io, &d_out);

@@ -36,6 +36,16 @@ __device__ __forceinline__ const FileDesc &find_file_by_frame(const FileDesc *fi
     return files[lo];
 }
 
+// `(v).clamp(-32768.0, 32767.0) as i16` of the reference (src/codec.rs:498-502, src/audio.rs:11-16): ONE conversion
+// instruction -- cvt.rzi.s16.f32 truncates toward zero, saturates to the i16 range and maps NaN to 0, which is
+// exactly Rust's clamp followed by `as i16` (clamp passes NaN through, `as` turns it into 0)
+__device__ __forceinline__ short f32_to_i16_rz_sat(float v)
+{
+    short q;
+    asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q) : "f"(v));
+    return q;
+}
+
 __device__ __forceinline__ float warp_max(float v)
 {
 #pragma unroll
@@ -300,10 +310,7 @@ __global__ void __launch_bounds__(256) gather_raw_kernel(const GatherLaunch p)
     int16_t *dst = p.raw + p.raw_off[frame];
     const float *src = p.pcm_arena + fd.pcm_off;
     const long long base = (long long)(f * kHop) - kHop / 2; // sample index of i = 0
-    auto conv = [](float x, float w) -> short {
-        const float sc = __fmul_rn(__fmul_rn(x, w), 32767.0f);
-        return (sc == sc) ? (short)__float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f)) : (short)0; // NaN -> 0
-    };
+    auto conv = [](float x, float w) -> short { return f32_to_i16_rz_sat(__fmul_rn(__fmul_rn(x, w), 32767.0f)); };
     if (ch <= 2 && base >= 0 && base + kFrame <= (long long)fd.len && (fd.pcm_off & 3) == 0)
     {
         // mono / stereo frame without padding inside: four sample frames per thread, 16-byte loads,
@@ -336,12 +343,7 @@ __global__ void __launch_bounds__(256) gather_raw_kernel(const GatherLaunch p)
         float x = 0.0f;
         if (pos >= 0 && pos < (long long)fd.len)
             x = __ldg(src + pos * ch + c);
-        const float wv = __fmul_rn(x, __ldg(p.window + i));
-        const float sc = __fmul_rn(wv, 32767.0f);
-        int q = 0;
-        if (sc == sc) // NaN -> 0 (Rust `as i16`)
-            q = __float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f));
-        dst[(size_t)c * kFrame + i] = (int16_t)q;
+        dst[(size_t)c * kFrame + i] = conv(x, __ldg(p.window + i));
     }
 }
 
@@ -771,8 +773,7 @@ __global__ void pcm_to_i16_kernel(const float *in, int16_t *out, uint64_t n)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-        const float v = __fmul_rn(in[i], 32767.0f);
-        out[i] = (v != v) ? (int16_t)0 : (int16_t)__float2int_rz(fminf(fmaxf(v, -32768.0f), 32767.0f));
+        out[i] = f32_to_i16_rz_sat(__fmul_rn(in[i], 32767.0f));
     }
 }
 

@@ -288,7 +288,7 @@ glc_status glc::flac_encode_impl(glc_ctx *ctx, uint32_t n_files, const float *co
         FL_STEP(cudaMemcpyAsync(d_files, files.data(), sizeof(FlacFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
         bool bad = false;
         for (uint32_t i = 0; pcm && i < n_files && !bad; ++i)
-            if (cudaMemcpyAsync(d_pcm + files[i].pcm_off, pcm[i], n_samples[i] * 4, cudaMemcpyHostToDevice, cs) !=
+            if (ctx_h2d(ctx, d_pcm + files[i].pcm_off, pcm[i], n_samples[i] * 4, cs) !=
                 cudaSuccess)
                 bad = true;
         if (bad)

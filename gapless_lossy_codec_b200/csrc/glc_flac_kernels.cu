@@ -98,10 +98,10 @@ __device__ __forceinline__ int partition_order(int level, uint32_t bs, int order
 // (s * 32767.0).clamp(-32768.0, 32767.0) as i16          src/flac.rs:955-958
 __device__ __forceinline__ int f32_to_i16(float s)
 {
-    const float v = __fmul_rn(s, 32767.0f);
-    if (v != v)
-        return 0;
-    return __float2int_rz(fminf(fmaxf(v, -32768.0f), 32767.0f));
+    // one instruction: truncate toward zero, saturate to i16, NaN -> 0 (= Rust's clamp then `as i16`)
+    short q;
+    asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q) : "f"(__fmul_rn(s, 32767.0f)));
+    return (int)q;
 }
 
 // residual of the fixed predictors, src/flac.rs:498-507 (no overflow for 16-bit input)

@@ -347,6 +347,8 @@ cudaStream_t ctx_compute_stream(glc_ctx *ctx);
 cudaStream_t ctx_d2h_stream(glc_ctx *ctx);
 void ctx_count_launch(glc_ctx *ctx, int kernel_id, uint64_t n);
 void ctx_count_bytes(glc_ctx *ctx, uint64_t h2d, uint64_t d2h);
+// host -> device; pageable sources are staged through a ring of pinned chunks filled by a few host threads
+cudaError_t ctx_h2d(glc_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t s);
 void ctx_time_begin(glc_ctx *ctx, int kernel_id, void **token);
 void ctx_time_end(glc_ctx *ctx, void *token);
 

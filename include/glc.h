@@ -17,6 +17,10 @@
  *   - outputs are allocated by the library (pinned host memory from a per-context pool) and are
  *     released with glc_encoded_free / glc_free;
  *   - PCM is interleaved f32 in [-1, 1], exactly what the reference's functions take.
+ *   - input buffers may live in ordinary pageable memory (the reference's entry points borrow slices);
+ *     they are then staged through a ring of pinned chunks filled by a few host threads
+ *     (GLC_COPY_THREADS, default 4).  Buffers from glc_host_alloc, or pinned by the caller, go to the DMA
+ *     engine directly.
  *   - a context and the objects made from it may be used by one thread at a time.
  */
 #ifndef GLC_H
@@ -32,7 +36,7 @@ extern "C" {
 #define GLC_FRAME_SIZE 2048u      /* src/codec.rs:15 */
 #define GLC_HOP_SIZE 1024u        /* src/codec.rs:16 */
 #define GLC_FRAMES_PER_CHUNK 500u /* src/codec.rs:18 */
-#define GLC_ABI_VERSION 6u
+#define GLC_ABI_VERSION 7u
 
 typedef enum glc_status
 {
@@ -282,6 +286,11 @@ glc_status glc_timer_end(glc_ctx *ctx, float *elapsed_ms);
 glc_status glc_ctx_sync(glc_ctx *ctx);
 /* Writes `bytes` of HBM with a fill kernel (L2 flush helper for benchmarks, > 126 MB). */
 glc_status glc_flush_l2(glc_ctx *ctx);
+/* Pure-DMA probe: moves h2d_bytes host -> device and d2h_bytes device -> host between pinned host memory and
+ * HBM, both directions at once (on two streams) when `concurrent` is non-zero, one after the other otherwise,
+ * with no kernel in between; *elapsed_ms is the host-clock time until both are done.  The floor any end-to-end
+ * figure of this path can reach on this box: bench.py runs it on every rank at the same time. */
+glc_status glc_dma_probe(glc_ctx *ctx, uint64_t h2d_bytes, uint64_t d2h_bytes, int concurrent, float *elapsed_ms);
 /* FP32 non-FMA issue micro-benchmark (FMUL+FADD chains on every SM): returns achieved
  * 1e12 lane-operations per second; the measured roof for the EXACT transform kernels. */
 glc_status glc_measure_fp32_issue(glc_ctx *ctx, int packed, double *tera_ops_per_s);

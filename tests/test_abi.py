@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"declared in include/glc.h but not exported: {missing}"
     assert sorted(_ffi.EXPORTS) == declared, "the ctypes binding must cover exactly the declared ABI"
-    assert lib.glc_abi_version() == 6
+    assert lib.glc_abi_version() == 7
 
 
 def test_struct_layout_matches_header():

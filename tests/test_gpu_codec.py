@@ -409,3 +409,16 @@ def test_sharded_batch_over_several_contexts(gpu_ctx):
         del encs
         for c in ctxs:
             c.close()
+
+
+def test_raw_frames_saturate_out_of_range_samples(gpu_ctx):
+    """raw-PCM frames store ((x * w) * 32767).clamp(-32768, 32767) as i16 (src/codec.rs:498-502): loud noise
+    (|x| up to 4) takes the raw path and saturates; 16-bit PCM output (src/audio.rs:11-16) saturates too."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    for ch in (1, 2, 3):
+        x = signals.white_noise(44100, ch, 0.4, 31 + ch) * np.float32(13.0)
+        enc, pcm = _roundtrip_case(gpu_ctx, x, ch, 44100, f"loud noise {ch} ch")
+        assert enc.frame_is_raw.all() and (np.abs(enc.raw.astype(np.int32)) >= 32767).any()
+        want16 = np.trunc(np.clip(pcm * np.float32(32767.0), -32768.0, 32767.0)).astype(np.int16)
+        assert np.array_equal(Decoder(ch, 44100, gpu_ctx).decode_pcm16(enc), want16)

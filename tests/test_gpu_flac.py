@@ -142,3 +142,20 @@ def test_batch_and_large_lossless(gpu_ctx):
     assert info["md5_ok"] and info["total_samples"] == n and info["n_frames"] == (n + 4095) // 4096
     assert np.array_equal(info["samples"], _to_i16(x).astype(np.int32))
     assert hashlib.md5(_to_i16(x).tobytes()).digest() == info["md5"]
+
+
+def test_non_finite_and_out_of_range_samples(gpu_ctx):
+    """`(s * 32767.0).clamp(-32768.0, 32767.0) as i16` (src/flac.rs:955-958): NaN -> 0, +-inf and anything outside
+    [-1, 1] saturate, everything else truncates toward zero.  One saturating conversion instruction on the
+    device; bytes must equal the oracle's."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(20000) * 0.7).astype(np.float32)
+    x[::97] = np.nan
+    x[5::211] = np.inf
+    x[9::223] = -np.inf
+    x[11::131] = 3.5
+    x[13::137] = -1.0000001
+    x[17::139] = np.float32(32767.4 / 32767.0)
+    x[19::149] = -0.0
+    _check(gpu_ctx, x, 44100, 1, 5, "non-finite mono")
+    _check(gpu_ctx, x[:19998], 48000, 2, 8, "non-finite stereo")
