@@ -8,15 +8,17 @@
 //   pass A  "measure": f32 -> i16 (:955-958), residuals, per-partition Rice parameters, exact frame
 //           size in bytes.  Output: i16 arena, parameters, frame_bytes[].
 //   (scan of frame_bytes on the device gives every frame its final byte offset)
-//   pass B  "emit":    per-sample code lengths -> block-wide exclusive scan -> every thread writes its
-//           own contiguous run of codes into a zeroed shared-memory bit buffer (atomicOr on the
-//           words it shares with neighbours), CRC-8 of the header, parallel CRC-16 of the frame
-//           (per-thread partial CRCs combined with x^(8n) mod P multiplications), coalesced copy
-//           to the frame's final position.
+//   pass B  "emit":    every thread owns a RUN of 16 consecutive samples of a channel: code lengths, run
+//           totals, block-wide exclusive scan of the 256 run totals, then the thread assembles its run's
+//           bits word by word in a register and stores whole words into a zeroed shared-memory bit buffer
+//           (plain stores; atomicOr only for the first and last word of the run, which neighbours share),
+//           CRC-8 of the header, parallel CRC-16 of the frame (per-thread partial CRCs combined with
+//           x^(8n) mod P multiplications), word-wise copy to the frame's final position.
 //
 // Integer work only: bit-exact against the oracle is the bar.  HBM-bound: 4 B/sample read in pass
 // A, 2 B/sample written, 2 B/sample + bitstream in pass B.
 #include <algorithm>
+#include <type_traits>
 
 #include "glc_internal.cuh"
 
@@ -34,6 +36,7 @@ struct BlockGeom
     uint32_t file;       // index into the file table
     uint32_t frame_no;   // frame number inside the file
     uint32_t bs;         // samples per channel in this block
+    uint32_t bs_pad;     // channel stride of the planar shared-memory copy: bs rounded up to 8 samples (16 bytes)
     uint32_t ch;
     uint32_t rate;
     uint64_t smp_off;    // interleaved sample offset of the block inside the file
@@ -60,6 +63,7 @@ __device__ __forceinline__ BlockGeom locate_block(const FlacFileDesc *files, uin
     const uint64_t remaining = fd.n_samples - g.smp_off;
     const uint64_t per_ch = remaining / fd.channels; // src/flac.rs:1026-1027
     g.bs = (uint32_t)(per_ch < fd.block_size ? per_ch : fd.block_size);
+    g.bs_pad = (g.bs + 7u) & ~7u;
     return g;
 }
 
@@ -105,6 +109,9 @@ __device__ __forceinline__ int f32_to_i16(float s)
 }
 
 // residual of the fixed predictors, src/flac.rs:498-507 (no overflow for 16-bit input)
+
+// residual of the fixed predictors, src/flac.rs:498-507 (no overflow for 16-bit input); used by the compact
+// (not unrolled) paths of ragged tail blocks, which read the planar copy directly
 __device__ __forceinline__ int residual_at(const int16_t *s, uint32_t i, int order)
 {
     switch (order)
@@ -149,7 +156,7 @@ __device__ __forceinline__ uint32_t header_bytes(uint32_t bs, uint32_t frame_no)
     return n + 1; // + CRC-8
 }
 
-// loads the block's samples as planar i16 into shared memory: s[c*bs + i].  Four samples per load
+// loads the block's samples as planar i16 into shared memory: s[c*bs_pad + i].  Four samples per load
 // (float4 from the PCM arena / 8-byte loads from the i16 arena), all of a thread's loads issued before
 // the first use so that several are in flight.  File starts are 4-sample aligned in both arenas and
 // every block before a file's last one holds a multiple of 4 samples, so the vector path applies
@@ -172,7 +179,7 @@ __device__ __forceinline__ void scatter_sample(int16_t *s_smp, const BlockGeom &
         i = e / g.ch;
         c = e - i * g.ch;
     }
-    s_smp[c * g.bs + i] = (int16_t)q;
+    s_smp[c * g.bs_pad + i] = (int16_t)q;
 }
 
 template <bool FROM_F32>
@@ -265,7 +272,8 @@ __device__ __forceinline__ void load_block(const FlacLaunch &p, const FlacFileDe
     }
 }
 
-constexpr int kMaxRun = 16; // samples per thread and channel: block sizes never exceed 4096 (src/flac.rs:983-995)
+constexpr int kRunLen = 16; // consecutive samples per thread and channel: 256 x 16 = the largest block (src/flac.rs:983-995)
+static_assert(kFlacThreads * kRunLen == 4096, "a thread run times the CTA size must cover the largest block");
 
 __device__ __forceinline__ uint32_t rice_param32(uint32_t sum_abs, uint32_t n) // src/flac.rs:515-552
 {
@@ -278,15 +286,12 @@ __device__ __forceinline__ uint32_t rice_param32(uint32_t sum_abs, uint32_t n) /
     return lg < 14 ? (uint32_t)lg : 14u;
 }
 
-// Thread t owns samples i = t + 256 j (j < kMaxRun) of the channel: consecutive threads read
-// consecutive shared-memory words, and when the partition size is a multiple of 32 a whole warp
-// lies in one partition, so per-partition sums are one hardware warp reduction + one atomic.
 struct ChannelPlan
 {
     int order, po;
     uint32_t dps, nparts;
-    bool warp_uniform; // every warp's 32 samples share a partition
-    int dps_shift;     // log2(dps) when dps is a power of two, else -1
+    bool run_uniform; // every thread's run of kRunLen samples lies inside one partition
+    int dps_shift;    // log2(dps) when dps is a power of two, else -1
     __device__ __forceinline__ uint32_t part_of(uint32_t i) const { return dps_shift >= 0 ? i >> dps_shift : i / dps; }
 };
 
@@ -297,15 +302,65 @@ __device__ __forceinline__ ChannelPlan plan_channel(int level, uint32_t bs)
     cp.po = cp.order ? partition_order(level, bs, cp.order) : 0;
     cp.dps = bs >> cp.po;
     cp.nparts = 1u << cp.po;
-    cp.warp_uniform = (cp.dps & 31u) == 0;
+    cp.run_uniform = (cp.dps % kRunLen) == 0;
     cp.dps_shift = (cp.dps & (cp.dps - 1u)) == 0 ? (__ffs(cp.dps) - 1) : -1;
     return cp;
 }
 
+// The thread's run of kRunLen samples plus the four before it (the predictor's history), as ints.
+// s = channel base in the planar copy (16-byte aligned, stride bs_pad), i0 = first sample of the run (a
+// multiple of 16).  Samples outside the block read as 0 and are never used.
+__device__ __forceinline__ void load_run(const int16_t *s, uint32_t i0, uint32_t bs_pad, int (&v)[kRunLen + 4])
+{
+    // history: samples i0-4 .. i0-1 (8 bytes, aligned)
+    if (i0 >= 4)
+    {
+        const uint2 h = *reinterpret_cast<const uint2 *>(s + i0 - 4);
+        v[0] = (int)(short)(h.x & 0xffffu);
+        v[1] = (int)(short)(h.x >> 16);
+        v[2] = (int)(short)(h.y & 0xffffu);
+        v[3] = (int)(short)(h.y >> 16);
+    }
+    else
+        v[0] = v[1] = v[2] = v[3] = 0;
+#pragma unroll
+    for (int q = 0; q < kRunLen / 8; ++q)
+    {
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + 8 * q < bs_pad)
+            w = *reinterpret_cast<const uint4 *>(s + i0 + 8 * q);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+        {
+            v[4 + 8 * q + 2 * e] = (int)(short)(ww[e] & 0xffffu);
+            v[4 + 8 * q + 2 * e + 1] = (int)(short)(ww[e] >> 16);
+        }
+    }
+}
+
+// residual of the fixed predictors at run position j (sample i0 + j), src/flac.rs:498-507; ORDER known at compile
+// time (the hot paths are instantiated per predictor order: no per-sample switch, and one launch runs ONE
+// instantiation, which is what keeps its loop inside the instruction cache)
+template <int ORDER>
+__device__ __forceinline__ int run_residual_t(const int (&v)[kRunLen + 4], int j)
+{
+    const int x0 = v[4 + j], x1 = v[3 + j], x2 = v[2 + j], x3 = v[1 + j], x4 = v[j];
+    if (ORDER == 1)
+        return x0 - x1;
+    if (ORDER == 2)
+        return x0 - (2 * x1 - x2);
+    if (ORDER == 3)
+        return x0 - (3 * x1 - 3 * x2 + x3);
+    if (ORDER == 4)
+        return x0 - (4 * x1 - 6 * x2 + 4 * x3 - x4);
+    return x0;
+}
+
 // ------------------------------------------------------------------ pass A
 
-__global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLaunch p, uint8_t *rice_k /* [blocks][ch][64] */,
-                                                                    uint32_t max_ch)
+__global__ void __launch_bounds__(kFlacThreads, 4) flac_measure_kernel(const FlacLaunch p, uint8_t *rice_k /* [blocks][ch][64] */,
+                                                                       uint32_t max_ch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int16_t *s_smp = reinterpret_cast<int16_t *>(smem_raw);
@@ -322,6 +377,7 @@ __global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLa
     load_block<true>(p, fd, g, s_smp);
     const int tid = threadIdx.x, lane = tid & 31;
     const ChannelPlan cp = plan_channel(p.level, g.bs);
+    const uint32_t i0 = (uint32_t)tid * kRunLen;
     if (tid == 0)
         s_total_bits = 0;
 
@@ -339,31 +395,43 @@ __global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLa
         if (tid == 0)
             s_bits = 0;
         __syncthreads();
-        const int16_t *s = s_smp + c * g.bs;
-        uint32_t zz[kMaxRun];
-        // ---- residuals and per-partition sums of |r| ----
-#pragma unroll
-        for (int j = 0; j < kMaxRun; ++j)
+        // ---- residuals of the thread's run and per-partition sums of |r| ----
+        // fast path (every block but a ragged tail): the whole run lies inside the block and inside one
+        // partition; unrolled, everything in registers.  Otherwise a compact loop over the planar copy.
+        const int16_t *s = s_smp + c * g.bs_pad;
+        const bool fastp = cp.run_uniform && i0 + kRunLen <= g.bs;
+        uint32_t zz[kRunLen];
+        if (fastp)
         {
-            const uint32_t i = tid + kFlacThreads * j;
-            const bool valid = i < g.bs && i >= (uint32_t)cp.order;
-            int r = 0;
-            if (valid)
-                r = residual_at(s, i, cp.order);
-            zz[j] = valid ? zigzag(r) : 0xffffffffu;
-            const uint32_t a = (uint32_t)(r < 0 ? -r : r);
-            if (kFlacThreads * j >= g.bs)
-                continue; // uniform: nothing left in this block
-            if (cp.warp_uniform)
+            int v[kRunLen + 4];
+            load_run(s, i0, g.bs_pad, v);
+            uint32_t run_abs = 0;
+            auto body = [&](auto order_tag) {
+                constexpr int ORDER = decltype(order_tag)::value;
+#pragma unroll
+                for (int j = 0; j < kRunLen; ++j)
+                {
+                    const int r = run_residual_t<ORDER>(v, j);
+                    const bool valid = i0 != 0 || j >= ORDER; // only thread 0 holds warm-up samples
+                    zz[j] = zigzag(r);
+                    run_abs += valid ? (uint32_t)(r < 0 ? -r : r) : 0u;
+                }
+            };
+            switch (cp.order)
             {
-                const uint32_t sum = __reduce_add_sync(0xffffffffu, a);
-                const uint32_t i0 = i - lane; // first sample of this warp
-                if (lane == 0 && i0 < g.bs)
-                    atomicAdd(&s_psum[cp.part_of(i0)], sum);
+            case 1: body(std::integral_constant<int, 1>()); break;
+            case 2: body(std::integral_constant<int, 2>()); break;
+            case 3: body(std::integral_constant<int, 3>()); break;
+            default: body(std::integral_constant<int, 4>()); break;
             }
-            else if (valid)
-                atomicAdd(&s_psum[cp.part_of(i)], a);
+            atomicAdd(&s_psum[cp.part_of(i0)], run_abs);
         }
+        else
+            for (uint32_t i = max(i0, (uint32_t)cp.order); i < min(i0 + kRunLen, g.bs); ++i)
+            {
+                const int r = residual_at(s, i, cp.order);
+                atomicAdd(&s_psum[cp.part_of(i)], (uint32_t)(r < 0 ? -r : r));
+            }
         __syncthreads();
         uint8_t *kout = rice_k + (b * max_ch + c) * kMaxParts;
         if ((uint32_t)tid < cp.nparts)
@@ -378,18 +446,22 @@ __global__ void __launch_bounds__(kFlacThreads) flac_measure_kernel(const FlacLa
         __syncthreads();
         // ---- code lengths ----
         uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < kMaxRun; ++j)
+        if (fastp)
         {
-            const uint32_t i = tid + kFlacThreads * j;
-            if (zz[j] != 0xffffffffu)
+            const uint32_t k = s_k[cp.part_of(i0)];
+            const int first_valid = i0 == 0 ? cp.order : 0;
+#pragma unroll
+            for (int j = 0; j < kRunLen; ++j)
+                mine += j >= first_valid ? (zz[j] >> k) + 1u + k : 0u;
+        }
+        else
+            for (uint32_t i = max(i0, (uint32_t)cp.order); i < min(i0 + kRunLen, g.bs); ++i)
             {
                 const uint32_t k = s_k[cp.part_of(i)];
-                mine += (zz[j] >> k) + 1u + k;
+                mine += (zigzag(residual_at(s, i, cp.order)) >> k) + 1u + k;
             }
-        }
         mine = __reduce_add_sync(0xffffffffu, mine);
-        if (lane == 0)
+        if (lane == 0 && mine)
             atomicAdd(&s_bits, mine);
         __syncthreads();
         if (tid == 0)
@@ -417,6 +489,71 @@ __device__ __forceinline__ void put_bits(uint32_t *buf, unsigned long long pos, 
     if (lo)
         atomicOr(buf + word + 1, lo);
 }
+
+// A thread's contiguous bit range of the frame, written front to back through a 64-bit accumulator: codes
+// are appended below the bits already collected and every time 32 of them are complete the word goes to the
+// (zeroed) buffer.  Only the first word of the range (its leading bits belong to the previous range) and the
+// final partial word (its trailing bits belong to the next range) are merged with atomicOr; every word in
+// between belongs to this thread alone and is a plain store.
+struct RunWriter
+{
+    uint32_t *buf;
+    unsigned long long acc;
+    uint32_t wi, nb;
+    bool first;
+    __device__ __forceinline__ void begin(uint32_t *b, uint32_t first_bit)
+    {
+        buf = b;
+        wi = first_bit >> 5;
+        nb = first_bit & 31u; // the leading bits of the first word stay zero in this thread's copy
+        acc = 0;
+        first = true;
+    }
+    __device__ __forceinline__ void emit(uint32_t word)
+    {
+        if (first)
+        {
+            atomicOr(buf + wi, word);
+            first = false;
+        }
+        else
+            buf[wi] = word;
+        ++wi;
+    }
+    // n (1..32) bits; `code` has no bits set at or above bit n
+    __device__ __forceinline__ void append(uint32_t code, uint32_t n)
+    {
+        acc = (acc << n) | code;
+        nb += n;
+        if (nb >= 32u)
+        {
+            emit((uint32_t)(acc >> (nb - 32u)));
+            nb -= 32u;
+        }
+    }
+    // a Rice code: q zeros, the stop bit and the k low bits (code = stop | low, k + 1 bits)
+    __device__ __forceinline__ void append_rice(uint32_t q, uint32_t code, uint32_t k1)
+    {
+        if (q + k1 <= 32u)
+        {
+            append(code, q + k1); // the common case: the zeros ride in front of the code
+            return;
+        }
+        while (q >= 32u) // long unary run: whole words of zeros
+        {
+            append(0u, 32u);
+            q -= 32u;
+        }
+        if (q)
+            append(0u, q);
+        append(code, k1);
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (nb)
+            atomicOr(buf + wi, (uint32_t)(acc << (32u - nb)));
+    }
+};
 
 __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b) // mod x^16+x^15+x^2+1
 {
@@ -549,7 +686,7 @@ __device__ void write_frame_header(uint32_t *bitbuf, const BlockGeom &g)
         put_bits(bitbuf, 8ull * j, h[j], 8);
 }
 
-__global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLaunch p, const uint8_t *rice_k, uint32_t max_ch,
+__global__ void __launch_bounds__(kFlacThreads, 4) flac_emit_kernel(const FlacLaunch p, const uint8_t *rice_k, uint32_t max_ch,
                                                                  const uint64_t *frame_off, uint8_t *out_arena,
                                                                  uint32_t smp_bytes, uint32_t buf_words,
                                                                  uint32_t *g_scratch /* null = bit buffer in smem */)
@@ -559,12 +696,15 @@ __global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLa
     uint32_t *bitbuf = g_scratch ? g_scratch + (size_t)blockIdx.x * buf_words
                                  : reinterpret_cast<uint32_t *>(smem_raw + smp_bytes);
     constexpr int kWarps = kFlacThreads / 32;
-    __shared__ uint32_t s_wtot[kMaxRun * kWarps]; // code bits per (run step j, warp), in sample order
-    __shared__ uint32_t s_chan_total;
-    __shared__ uint16_t s_crc_tab[256];
+    __shared__ uint32_t s_wsum[2][kWarps]; // code bits per warp (runs in sample order), double-buffered by channel parity
+    __shared__ uint16_t s_crc_tab[4][256]; // [k][x] = CRC-16 of byte x followed by k zero bytes (slicing by 4)
     __shared__ uint16_t s_xpow[32];
     __shared__ uint32_t s_crc_part[kWarps];
-    __shared__ unsigned long long s_bitpos;
+    // multiplication by x^(8 * chunk * 2^L) mod P as two byte-indexed tables per merge level L (the CRC is linear:
+    // a * b = low byte of a times b XOR high byte of a times b); rebuilt only when the chunk size changes
+    __shared__ uint16_t s_mul[6][2][256];
+    __shared__ uint16_t s_bitmul[6][16];
+    int cur_m = -1;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -573,7 +713,17 @@ __global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLa
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x8005u) : (crc << 1);
-        s_crc_tab[tid] = (uint16_t)crc;
+        s_crc_tab[0][tid] = (uint16_t)crc;
+        // one more zero byte per table: crc <- (crc << 8) ^ tab0[crc >> 8]; tab0[y] is recomputed bitwise here
+        for (int t = 1; t < 4; ++t)
+        {
+            uint32_t hi = crc & 0xff00u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                hi = (hi & 0x8000u) ? ((hi << 1) ^ 0x8005u) : (hi << 1);
+            crc = ((crc << 8) & 0xffffu) ^ (hi & 0xffffu);
+            s_crc_tab[t][tid] = (uint16_t)crc;
+        }
         if (tid == 0)
         {
             uint32_t x = 0x0100u; // x^8
@@ -585,6 +735,7 @@ __global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLa
         }
     }
     __syncthreads();
+    const uint32_t i0 = (uint32_t)tid * kRunLen;
 
     for (uint64_t b = blockIdx.x; b < p.n_blocks_total; b += gridDim.x)
     {
@@ -599,132 +750,134 @@ __global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLa
 
         const uint32_t hbytes = header_bytes(g.bs, g.frame_no);
         if (tid == 0)
-        {
             write_frame_header(bitbuf, g);
-            s_bitpos = (unsigned long long)hbytes * 8ull;
-        }
-        __syncthreads();
 
         const ChannelPlan cp = plan_channel(p.level, g.bs);
         const int order = cp.order;
-        const uint32_t n_steps = (g.bs + kFlacThreads - 1) / kFlacThreads;
+        uint32_t sub0 = hbytes * 8u; // first bit of the current subframe (the same value in every thread)
 
         for (uint32_t c = 0; c < g.ch; ++c)
         {
-            const int16_t *s = s_smp + c * g.bs;
+            const int16_t *s = s_smp + c * g.bs_pad;
             const uint8_t *kin = rice_k + (b * max_ch + c) * kMaxParts;
-            const unsigned long long sub0 = s_bitpos; // first bit of this subframe
-            if (order == 0)
+            const bool have = i0 < g.bs;
+            // ---- bits of the thread's run ----
+            // fast path: the whole run lies inside the block and inside one partition (every block but a ragged
+            // tail): unrolled, samples and codes in registers, one Rice parameter per run, and a partition can
+            // only start at the run's first sample (or at sample `order` of the block, in thread 0's run).
+            // Everything else (tail blocks, verbatim subframes) goes through compact loops over the planar copy.
+            const bool fastp = order != 0 && cp.run_uniform && i0 + kRunLen <= g.bs;
+            const uint32_t fixed = order == 0 ? 8u : 8u + 16u * (uint32_t)order + 6u; // bits before the first run
+            uint32_t zz[kRunLen];
+            uint32_t run_bits = 0;
+            uint32_t k_run = 0;
+            int pj = -1; // run position at which a partition starts (its 4-bit parameter goes in front), or -1
+            if (fastp)
             {
-                // verbatim subframe: 0 | 000001 | 0, then the samples (src/flac.rs:704-729)
-                if (tid == 0)
-                    put_bits(bitbuf, sub0, 0x02u, 8);
-                for (uint32_t i = tid; i < g.bs; i += kFlacThreads)
-                    put_bits(bitbuf, sub0 + 8ull + 16ull * i, (uint32_t)(uint16_t)s[i], 16);
-                __syncthreads();
-                if (tid == 0)
-                    s_bitpos = sub0 + 8ull + 16ull * g.bs;
-                __syncthreads();
-                continue;
-            }
-            // ---- code lengths in sample order: (step j, warp, lane) ----
-            uint32_t zz[kMaxRun], len[kMaxRun];
+                int v[kRunLen + 4];
+                load_run(s, i0, g.bs_pad, v);
+                k_run = (uint32_t)kin[cp.part_of(i0)];
+                const bool starts = cp.dps_shift >= 0 ? (i0 & (cp.dps - 1u)) == 0 : (i0 % cp.dps) == 0;
+                pj = i0 == 0 ? order : (starts ? 0 : -1);
+                auto body = [&](auto order_tag) {
+                    constexpr int ORDER = decltype(order_tag)::value;
 #pragma unroll
-            for (int j = 0; j < kMaxRun; ++j)
-            {
-                const uint32_t i = tid + kFlacThreads * j;
-                zz[j] = 0;
-                len[j] = 0;
-                if ((uint32_t)j >= n_steps)
-                    continue;
-                if (i < g.bs && i >= (uint32_t)order)
-                {
-                    const uint32_t part = cp.part_of(i);
-                    const uint32_t k = kin[part];
-                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * cp.dps;
-                    zz[j] = zigzag(residual_at(s, i, order));
-                    len[j] = (zz[j] >> k) + 1u + k + (i == pstart ? 4u : 0u);
-                }
-                const uint32_t wsum = __reduce_add_sync(0xffffffffu, len[j]);
-                if (lane == 0)
-                    s_wtot[j * kWarps + warp] = wsum;
-            }
-            __syncthreads();
-            if (warp == 0)
-            {
-                // exclusive scan of the n_steps * 8 warp totals (<= 128 values, 4 per lane)
-                uint32_t v[4], sum = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                {
-                    const uint32_t idx = lane * 4 + q;
-                    v[q] = idx < n_steps * kWarps ? s_wtot[idx] : 0u;
-                    sum += v[q];
-                }
-                uint32_t incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o)
-                        incl += t;
-                }
-                uint32_t run = incl - sum;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                {
-                    const uint32_t idx = lane * 4 + q;
-                    if (idx < n_steps * kWarps)
-                        s_wtot[idx] = run;
-                    run += v[q];
-                }
-                if (lane == 31)
-                    s_chan_total = incl;
-            }
-            __syncthreads();
-            const unsigned long long fixed = 8ull + 16ull * order + 6ull;
-            if (tid == 0)
-            {
-                // subframe header + warm-up + residual header, src/flac.rs:704-720, 733-736, 611-614
-                put_bits(bitbuf, sub0, (0x08u | (uint32_t)order) << 1, 8); // 0 | 001ooo | 0
-                for (int i = 0; i < order; ++i)
-                    put_bits(bitbuf, sub0 + 8ull + 16ull * i, (uint32_t)(uint16_t)s[i], 16);
-                put_bits(bitbuf, sub0 + 8ull + 16ull * order, (uint32_t)cp.po, 6); // method 00 + partition order
-            }
-#pragma unroll
-            for (int j = 0; j < kMaxRun; ++j)
-            {
-                if ((uint32_t)j >= n_steps)
-                    continue;
-                uint32_t incl = len[j];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o)
-                        incl += t;
-                }
-                if (len[j])
-                {
-                    const uint32_t i = tid + kFlacThreads * j;
-                    const uint32_t part = cp.part_of(i);
-                    const uint32_t k = kin[part];
-                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * cp.dps;
-                    unsigned long long pos = sub0 + fixed + s_wtot[j * kWarps + warp] + (incl - len[j]);
-                    if (i == pstart)
+                    for (int j = 0; j < kRunLen; ++j)
                     {
-                        put_bits(bitbuf, pos, k, 4);
-                        pos += 4;
+                        const bool valid = i0 != 0 || j >= ORDER;
+                        zz[j] = zigzag(run_residual_t<ORDER>(v, j));
+                        run_bits += valid ? (zz[j] >> k_run) + 1u + k_run : 0u;
                     }
-                    // unary zeros (the buffer is zeroed), then the stop bit and the k low bits
-                    put_bits(bitbuf, pos + (zz[j] >> k), (1u << k) | (zz[j] & ((1u << k) - 1u)), (int)k + 1);
+                };
+                switch (order)
+                {
+                case 1: body(std::integral_constant<int, 1>()); break;
+                case 2: body(std::integral_constant<int, 2>()); break;
+                case 3: body(std::integral_constant<int, 3>()); break;
+                default: body(std::integral_constant<int, 4>()); break;
+                }
+                run_bits += pj >= 0 ? 4u : 0u;
+            }
+            else if (order == 0)
+                run_bits = have ? 16u * min((uint32_t)kRunLen, g.bs - i0) : 0u; // verbatim samples (src/flac.rs:722-729)
+            else
+                for (uint32_t i = max(i0, (uint32_t)order); i < min(i0 + kRunLen, g.bs); ++i)
+                {
+                    const uint32_t part = cp.part_of(i);
+                    const uint32_t k = (uint32_t)kin[part];
+                    const uint32_t pstart = part == 0 ? (uint32_t)order : part * cp.dps;
+                    run_bits += (zigzag(residual_at(s, i, order)) >> k) + 1u + k + (i == pstart ? 4u : 0u);
+                }
+            // ---- exclusive scan of the 256 run totals ----
+            uint32_t incl = run_bits;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            if (lane == 31)
+                s_wsum[c & 1][warp] = incl;
+            __syncthreads(); // the only barrier per channel (s_wsum alternates between two copies)
+            uint32_t before = 0, chan_bits = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w)
+            {
+                const uint32_t t = s_wsum[c & 1][w];
+                before += w < warp ? t : 0u;
+                chan_bits += t;
+            }
+            const uint32_t first_bit = sub0 + fixed + before + (incl - run_bits);
+            if (tid == 0)
+            {
+                if (order == 0)
+                    put_bits(bitbuf, sub0, 0x02u, 8); // verbatim subframe: 0 | 000001 | 0 (src/flac.rs:704-720)
+                else
+                {
+                    // subframe header + warm-up + residual header, src/flac.rs:704-720, 733-736, 611-614
+                    put_bits(bitbuf, sub0, (0x08u | (uint32_t)order) << 1, 8); // 0 | 001ooo | 0
+                    for (int i = 0; i < order; ++i)
+                        put_bits(bitbuf, sub0 + 8ull + 16ull * i, (uint32_t)(uint16_t)s[i], 16);
+                    put_bits(bitbuf, sub0 + 8ull + 16ull * order, (uint32_t)cp.po, 6); // method 00 + partition order
                 }
             }
-            __syncthreads();
-            if (tid == 0)
-                s_bitpos = sub0 + fixed + s_chan_total;
-            __syncthreads();
+            if (run_bits)
+            {
+                RunWriter rw;
+                rw.begin(bitbuf, first_bit);
+                if (fastp)
+                {
+                    const uint32_t kmask = (1u << k_run) - 1u, stop = 1u << k_run, nb_code = k_run + 1u;
+                    const int first_valid = i0 == 0 ? order : 0;
+#pragma unroll
+                    for (int j = 0; j < kRunLen; ++j)
+                    {
+                        if (j == pj)
+                            rw.append(k_run, 4u); // Rice parameter of the partition (src/flac.rs:676)
+                        if (j >= first_valid)
+                            rw.append_rice(zz[j] >> k_run, stop | (zz[j] & kmask), nb_code); // unary zeros, stop bit, k low bits
+                    }
+                }
+                else if (order == 0)
+                    for (uint32_t i = i0; i < min(i0 + kRunLen, g.bs); ++i)
+                        rw.append((uint32_t)(uint16_t)s[i], 16u);
+                else
+                    for (uint32_t i = max(i0, (uint32_t)order); i < min(i0 + kRunLen, g.bs); ++i)
+                    {
+                        const uint32_t part = cp.part_of(i);
+                        const uint32_t k = (uint32_t)kin[part];
+                        const uint32_t pstart = part == 0 ? (uint32_t)order : part * cp.dps;
+                        if (i == pstart)
+                            rw.append(k, 4u);
+                        const uint32_t z = zigzag(residual_at(s, i, order));
+                        rw.append_rice(z >> k, (1u << k) | (z & ((1u << k) - 1u)), k + 1u);
+                    }
+                rw.finish();
+            }
+            sub0 += fixed + chan_bits;
         }
+        __syncthreads();
 
         // ---- CRC-16 over bytes [0, nb): the frame is right-aligned in a virtual buffer of 256 chunks of
         //      2^m bytes (leading zero bytes do not change a CRC with init 0), every thread hashes its
@@ -735,22 +888,46 @@ __global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLa
             uint32_t m = 0;
             while (((uint32_t)kFlacThreads << m) < nb)
                 ++m;
+            if ((int)m != cur_m) // uniform over the CTA
+            {
+                cur_m = (int)m;
+                if (tid < 6)
+                {
+                    uint32_t bm = s_xpow[m + tid]; // x^(8 * 2^(m + L)); times x^i for i = 0..15
+                    for (int i = 0; i < 16; ++i)
+                    {
+                        s_bitmul[tid][i] = (uint16_t)bm;
+                        bm = ((bm << 1) ^ ((bm & 0x8000u) ? 0x18005u : 0u)) & 0xffffu;
+                    }
+                }
+                __syncthreads();
+                for (uint32_t e = tid; e < 6u * 512u; e += kFlacThreads)
+                {
+                    const uint32_t L = e >> 9, hi = (e >> 8) & 1u, x = e & 255u;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int jb = 0; jb < 8; ++jb)
+                        acc ^= ((x >> jb) & 1u) ? (uint32_t)s_bitmul[L][jb + 8 * hi] : 0u;
+                    s_mul[L][hi][x] = (uint16_t)acc;
+                }
+                __syncthreads();
+            }
             const uint32_t chunk = 1u << m;
             const uint32_t pad = kFlacThreads * chunk - nb;
             const uint32_t v0 = (uint32_t)tid * chunk, v1 = v0 + chunk;
             const uint32_t b0 = v0 > pad ? v0 - pad : 0u, b1 = v1 > pad ? v1 - pad : 0u;
             uint32_t crc = 0;
             uint32_t j = b0;
-            auto step = [&](uint32_t byte) { crc = ((crc << 8) & 0xffffu) ^ s_crc_tab[((crc >> 8) ^ byte) & 0xffu]; };
+            auto step = [&](uint32_t byte) { crc = ((crc << 8) & 0xffffu) ^ s_crc_tab[0][((crc >> 8) ^ byte) & 0xffu]; };
             for (; j < b1 && (j & 3u); ++j)
                 step(buf_byte(bitbuf, j));
             for (; j + 4 <= b1; j += 4)
             {
-                const uint32_t w = bitbuf[j >> 2];
-                step(w >> 24);
-                step((w >> 16) & 0xffu);
-                step((w >> 8) & 0xffu);
-                step(w & 0xffu);
+                // four bytes at once: the running CRC is folded into the first two, every byte looks up the table
+                // for its distance from the end of the word
+                const uint32_t w = bitbuf[j >> 2] ^ (crc << 16);
+                crc = (uint32_t)s_crc_tab[3][w >> 24] ^ s_crc_tab[2][(w >> 16) & 0xffu] ^ s_crc_tab[1][(w >> 8) & 0xffu] ^
+                      s_crc_tab[0][w & 0xffu];
             }
             for (; j < b1; ++j)
                 step(buf_byte(bitbuf, j));
@@ -758,7 +935,7 @@ __global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLa
             for (int l = 0; l < 5; ++l)
             {
                 const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << l);
-                crc = gf16_mul(crc, s_xpow[m + l]) ^ other;
+                crc = (uint32_t)s_mul[l][0][crc & 0xffu] ^ s_mul[l][1][(crc >> 8) & 0xffu] ^ other;
             }
             if (lane == 0)
                 s_crc_part[warp] = crc;
@@ -767,13 +944,27 @@ __global__ void __launch_bounds__(kFlacThreads, 3) flac_emit_kernel(const FlacLa
             {
                 uint32_t acc = 0;
                 for (int w = 0; w < kWarps; ++w)
-                    acc = gf16_mul(acc, s_xpow[m + 5]) ^ s_crc_part[w];
+                    acc = ((uint32_t)s_mul[5][0][acc & 0xffu] ^ s_mul[5][1][(acc >> 8) & 0xffu]) ^ s_crc_part[w];
                 put_bits(bitbuf, (unsigned long long)nb * 8ull, acc & 0xffffu, 16);
             }
         }
         __syncthreads();
+        // ---- copy out: bytes up to the first 4-byte boundary of the destination, then whole words (two
+        //      big-endian buffer words funnel-shifted and byte-swapped per store), then the tail ----
         uint8_t *dst = out_arena + frame_off[b];
-        for (uint32_t j = tid; j < fbytes; j += kFlacThreads)
+        const uint32_t head = min(fbytes, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+        const uint32_t n_words = (fbytes - head) >> 2;
+        if ((uint32_t)tid < head)
+            dst[tid] = (uint8_t)buf_byte(bitbuf, tid);
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+        for (uint32_t k = tid; k < n_words; k += kFlacThreads)
+        {
+            const uint32_t j = head + 4u * k; // first source byte of this word
+            const uint32_t w0 = bitbuf[j >> 2], w1 = bitbuf[(j >> 2) + 1];
+            const uint32_t be = __funnelshift_l(w1, w0, 8u * (j & 3u)); // bytes j..j+3, most significant first
+            dw[k] = __byte_perm(be, 0u, 0x0123);
+        }
+        for (uint32_t j = head + 4u * n_words + tid; j < fbytes; j += kFlacThreads)
             dst[j] = (uint8_t)buf_byte(bitbuf, j);
         __syncthreads();
     }
@@ -791,7 +982,7 @@ cudaError_t launch_flac_measure(const FlacLaunch &p, uint8_t *rice_k, uint32_t m
 {
     if (p.n_blocks_total == 0)
         return cudaSuccess;
-    const size_t smem = (size_t)max_bs * max_ch * sizeof(int16_t);
+    const size_t smem = (size_t)((max_bs + 7u) & ~7u) * max_ch * sizeof(int16_t) + 16;
     cudaError_t e = cudaFuncSetAttribute(flac_measure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
@@ -812,8 +1003,8 @@ struct EmitPlan
 EmitPlan plan_emit(uint64_t n_blocks, uint32_t max_ch, uint32_t max_bs, uint32_t max_frame_bytes, int sm_count)
 {
     EmitPlan pl;
-    pl.smp_bytes = (uint32_t)(((size_t)max_bs * max_ch * sizeof(int16_t) + 15) & ~(size_t)15);
-    pl.buf_words = ((max_frame_bytes + 3) >> 2) + 2;
+    pl.smp_bytes = (uint32_t)(((size_t)((max_bs + 7u) & ~7u) * max_ch * sizeof(int16_t) + 31) & ~(size_t)15);
+    pl.buf_words = ((max_frame_bytes + 3) >> 2) + 4;
     pl.smem = (size_t)pl.smp_bytes + (size_t)pl.buf_words * 4;
     pl.global_scratch = pl.smem > kEmitSmemLimit;
     if (pl.global_scratch)
@@ -825,9 +1016,17 @@ EmitPlan plan_emit(uint64_t n_blocks, uint32_t max_ch, uint32_t max_bs, uint32_t
     }
     else
     {
-        // as many CTAs as fit; each loops over blocks with a grid stride
-        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (pl.smem + 1024)));
-        pl.grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)sm_count * per_sm);
+        // exactly one resident set of CTAs (each loops over blocks with a grid stride): more would queue behind
+        // the first set and run the tail of the launch at partial occupancy
+        int per_sm = 0;
+        (void)cudaFuncSetAttribute(flac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flac_emit_kernel, kFlacThreads, pl.smem) != cudaSuccess ||
+            per_sm < 1)
+        {
+            (void)cudaGetLastError();
+            per_sm = 1;
+        }
+        pl.grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)sm_count * (unsigned)per_sm);
     }
     return pl;
 }
