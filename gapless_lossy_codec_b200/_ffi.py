@@ -63,6 +63,11 @@ class Stats(C.Structure):
         ("kernel_ms", C.c_double * K_COUNT),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("staged_bytes", C.c_uint64),
+        ("pinned_allocs", C.c_uint64),
+        ("pinned_alloc_bytes", C.c_uint64),
+        ("dev_allocs", C.c_uint64),
+        ("dev_alloc_bytes", C.c_uint64),
     ]
 
 

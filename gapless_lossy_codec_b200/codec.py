@@ -57,7 +57,9 @@ class Context:
         return dict(
             launches={n: int(st.launches[i]) for i, n in enumerate(_ffi.K_NAMES)},
             kernel_ms={n: float(st.kernel_ms[i]) for i, n in enumerate(_ffi.K_NAMES)},
-            h2d_bytes=int(st.h2d_bytes), d2h_bytes=int(st.d2h_bytes))
+            h2d_bytes=int(st.h2d_bytes), d2h_bytes=int(st.d2h_bytes), staged_bytes=int(st.staged_bytes),
+            pinned_allocs=int(st.pinned_allocs), pinned_alloc_bytes=int(st.pinned_alloc_bytes),
+            dev_allocs=int(st.dev_allocs), dev_alloc_bytes=int(st.dev_alloc_bytes))
 
     def stats_reset(self):
         self._lib.glc_stats_reset(self.handle)

@@ -112,6 +112,7 @@ struct PinnedPool
 {
     std::vector<PinnedBlock> blocks;
     std::mutex mu;
+    uint64_t n_grow = 0, grow_bytes = 0; // cudaHostAlloc calls (statistics)
 
     void *alloc(size_t bytes)
     {
@@ -136,6 +137,8 @@ struct PinnedPool
             return nullptr;
         }
         blocks.push_back({p, cap, true});
+        ++n_grow;
+        grow_bytes += cap;
         return p;
     }
     bool release(void *p)
@@ -187,6 +190,7 @@ struct DevicePool
     std::vector<DevBlock> blocks;
     std::mutex mu;
     size_t total = 0;
+    uint64_t n_grow = 0, grow_bytes = 0; // cudaMalloc calls (statistics)
 
     cudaError_t alloc(void **out, size_t bytes, cudaStream_t s)
     {
@@ -239,6 +243,8 @@ struct DevicePool
         }
         blocks.push_back({p, cap, true, s});
         total += cap;
+        ++n_grow;
+        grow_bytes += cap;
         *out = p;
         return cudaSuccess;
     }
@@ -397,6 +403,7 @@ struct glc_ctx
     size_t flush_floats;
     HostStager *stager = nullptr; // created on the first transfer from pageable memory
     uint64_t staged_bytes = 0;    // bytes that went through the stager (statistics)
+    uint64_t staged_base = 0, pool_base[4] = {0, 0, 0, 0}; // counters at the last glc_stats_reset
 };
 
 struct glc_encoder
@@ -643,6 +650,11 @@ extern "C" void glc_stats_reset(glc_ctx *c)
         return;
     drain_timed(c);
     memset(&c->stats, 0, sizeof c->stats);
+    c->staged_base = c->staged_bytes;
+    c->pool_base[0] = c->pool.n_grow;
+    c->pool_base[1] = c->pool.grow_bytes;
+    c->pool_base[2] = c->dpool.n_grow;
+    c->pool_base[3] = c->dpool.grow_bytes;
 }
 
 extern "C" void glc_stats_get(glc_ctx *c, glc_stats *out)
@@ -652,6 +664,11 @@ extern "C" void glc_stats_get(glc_ctx *c, glc_stats *out)
     cudaSetDevice(c->device);
     drain_timed(c);
     *out = c->stats;
+    out->staged_bytes = c->staged_bytes - c->staged_base;
+    out->pinned_allocs = c->pool.n_grow - c->pool_base[0];
+    out->pinned_alloc_bytes = c->pool.grow_bytes - c->pool_base[1];
+    out->dev_allocs = c->dpool.n_grow - c->pool_base[2];
+    out->dev_alloc_bytes = c->dpool.grow_bytes - c->pool_base[3];
 }
 
 extern "C" void glc_stats_enable_kernel_timing(glc_ctx *c, int on)

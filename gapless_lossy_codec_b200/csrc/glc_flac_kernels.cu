@@ -570,7 +570,7 @@ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b) // mod x^16
     return r & 0xffffu;
 }
 
-__device__ __forceinline__ uint32_t buf_byte(const volatile uint32_t *buf, uint32_t j)
+__device__ __forceinline__ uint32_t buf_byte(const uint32_t *buf, uint32_t j)
 {
     return (buf[j >> 2] >> (24 - 8 * (j & 3))) & 0xffu;
 }
@@ -686,6 +686,9 @@ __device__ void write_frame_header(uint32_t *bitbuf, const BlockGeom &g)
         put_bits(bitbuf, 8ull * j, h[j], 8);
 }
 
+// GLOBAL_SCRATCH: the bit buffer lives in global memory (frames too large for shared memory); the common
+// instantiation addresses it as shared memory outright instead of through generic pointers
+template <bool GLOBAL_SCRATCH>
 __global__ void __launch_bounds__(kFlacThreads, 4) flac_emit_kernel(const FlacLaunch p, const uint8_t *rice_k, uint32_t max_ch,
                                                                  const uint64_t *frame_off, uint8_t *out_arena,
                                                                  uint32_t smp_bytes, uint32_t buf_words,
@@ -693,8 +696,8 @@ __global__ void __launch_bounds__(kFlacThreads, 4) flac_emit_kernel(const FlacLa
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int16_t *s_smp = reinterpret_cast<int16_t *>(smem_raw);
-    uint32_t *bitbuf = g_scratch ? g_scratch + (size_t)blockIdx.x * buf_words
-                                 : reinterpret_cast<uint32_t *>(smem_raw + smp_bytes);
+    uint32_t *bitbuf = GLOBAL_SCRATCH ? g_scratch + (size_t)blockIdx.x * buf_words
+                                      : reinterpret_cast<uint32_t *>(smem_raw + smp_bytes);
     constexpr int kWarps = kFlacThreads / 32;
     __shared__ uint32_t s_wsum[2][kWarps]; // code bits per warp (runs in sample order), double-buffered by channel parity
     __shared__ uint16_t s_crc_tab[4][256]; // [k][x] = CRC-16 of byte x followed by k zero bytes (slicing by 4)
@@ -885,10 +888,12 @@ __global__ void __launch_bounds__(kFlacThreads, 4) flac_emit_kernel(const FlacLa
         //      with x^(8 * 2^j) mod P tabulated ----
         const uint32_t nb = fbytes - 2;
         {
+            // one chunk size for the whole launch (from the largest frame): smaller frames simply have more
+            // leading zero padding, and the merge tables are built once per CTA
             uint32_t m = 0;
-            while (((uint32_t)kFlacThreads << m) < nb)
+            while (((uint32_t)kFlacThreads << m) < (buf_words - 4u) * 4u)
                 ++m;
-            if ((int)m != cur_m) // uniform over the CTA
+            if ((int)m != cur_m) // first block of this CTA
             {
                 cur_m = (int)m;
                 if (tid < 6)
@@ -1019,8 +1024,8 @@ EmitPlan plan_emit(uint64_t n_blocks, uint32_t max_ch, uint32_t max_bs, uint32_t
         // exactly one resident set of CTAs (each loops over blocks with a grid stride): more would queue behind
         // the first set and run the tail of the launch at partial occupancy
         int per_sm = 0;
-        (void)cudaFuncSetAttribute(flac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flac_emit_kernel, kFlacThreads, pl.smem) != cudaSuccess ||
+        (void)cudaFuncSetAttribute(flac_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flac_emit_kernel<false>, kFlacThreads, pl.smem) != cudaSuccess ||
             per_sm < 1)
         {
             (void)cudaGetLastError();
@@ -1050,11 +1055,22 @@ cudaError_t launch_flac_emit(const FlacLaunch &p, const uint8_t *rice_k, uint32_
     const EmitPlan pl = plan_emit(p.n_blocks_total, max_ch, max_bs, max_frame_bytes, sm_count);
     if (pl.global_scratch && !scratch)
         return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(flac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess)
-        return e;
-    flac_emit_kernel<<<pl.grid, kFlacThreads, pl.smem, s>>>(p, rice_k, max_ch, frame_off, out_arena, pl.smp_bytes,
-                                                            pl.buf_words, pl.global_scratch ? scratch : nullptr);
+    if (pl.global_scratch)
+    {
+        cudaError_t e = cudaFuncSetAttribute(flac_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e != cudaSuccess)
+            return e;
+        flac_emit_kernel<true><<<pl.grid, kFlacThreads, pl.smem, s>>>(p, rice_k, max_ch, frame_off, out_arena, pl.smp_bytes,
+                                                                      pl.buf_words, scratch);
+    }
+    else
+    {
+        cudaError_t e = cudaFuncSetAttribute(flac_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e != cudaSuccess)
+            return e;
+        flac_emit_kernel<false><<<pl.grid, kFlacThreads, pl.smem, s>>>(p, rice_k, max_ch, frame_off, out_arena, pl.smp_bytes,
+                                                                       pl.buf_words, nullptr);
+    }
     return cudaGetLastError();
 }
 

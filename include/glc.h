@@ -259,6 +259,9 @@ typedef struct glc_stats
     uint64_t launches[GLC_K_COUNT]; /* kernels launched since the last reset */
     double kernel_ms[GLC_K_COUNT];  /* CUDA-event time per kernel id; filled only while timing is on */
     uint64_t h2d_bytes, d2h_bytes;  /* bytes moved by cudaMemcpyAsync since the last reset */
+    uint64_t staged_bytes;          /* of h2d_bytes: came from pageable memory through the pinned staging ring */
+    uint64_t pinned_allocs, pinned_alloc_bytes; /* cudaHostAlloc calls made by the pinned pool (growth, not reuse) */
+    uint64_t dev_allocs, dev_alloc_bytes;       /* cudaMalloc calls made by the device pool */
 } glc_stats;
 
 void glc_stats_reset(glc_ctx *ctx);

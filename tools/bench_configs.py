@@ -57,7 +57,14 @@ def config3(ctx, scale):
     out = C.POINTER(_ffi.Encoded)()
     t0 = time.perf_counter()
     _ffi.check(L.glc_encode(enc_h, xp.ctypes.data, xp.size, ch, C.byref(out)))
-    t_enc = time.perf_counter() - t0
+    t_enc_first = time.perf_counter() - t0  # includes pool growth (pinned + device allocations)
+    t_enc = 1e9
+    for rep in range(2):  # steady state: every buffer comes from the pools
+        L.glc_encoded_free(ctx.handle, out)
+        out = C.POINTER(_ffi.Encoded)()
+        t0 = time.perf_counter()
+        _ffi.check(L.glc_encode(enc_h, xp.ctypes.data, xp.size, ch, C.byref(out)))
+        t_enc = min(t_enc, time.perf_counter() - t0)
     best = 1e9
     ctx.enable_kernel_timing(True)
     for rep in range(3):
@@ -75,7 +82,8 @@ def config3(ctx, scale):
     res = {"config": "3: 48 kHz 5.1, decode path", "audio_s": secs, "frames": int(e.n_frames),
            "frame_channels": int(e.n_frames) * ch, "raw_frames": int(np.ctypeslib.as_array(e.frame_is_raw, (int(e.n_frames),)).sum()),
            "decode_e2e_audio_s_per_s": secs / best, "decode_e2e_ms": best * 1e3,
-           "encode_e2e_audio_s_per_s_first_call": secs / t_enc,
+           "encode_e2e_audio_s_per_s": secs / t_enc, "encode_e2e_ms": t_enc * 1e3,
+           "encode_e2e_audio_s_per_s_first_call": secs / t_enc_first,
            "decode_kernel_ms": {k: v for k, v in st["kernel_ms"].items() if v},
            "prefix_parity": "20 s prefix bit-exact vs oracle", "gapless": "decoded count == input count"}
     L.glc_encoded_free(ctx.handle, out)
@@ -107,11 +115,16 @@ def config4(ctx, scale, rank, world, dist):
     _ffi.check(L.glc_decoder_new(ctx.handle, ch, sr, C.byref(dec_h)))
     t_enc = t_dec = 0.0
     total_in = total_out = 0
+    per_batch = []
+    grow = {"pinned_allocs": 0, "pinned_alloc_bytes": 0, "dev_allocs": 0, "dev_alloc_bytes": 0}
     n_batches = max(1, (len(mine) + 999) // 1000)
     B = (len(mine) + n_batches - 1) // n_batches  # equal batches of <= 1000 tracks (same pool size classes)
     starts = list(range(0, len(mine), B))
-    for it, b0 in enumerate([starts[0]] + starts):  # the first batch runs once untimed (pools, tables warm)
-        warm = it == 0
+    # the first batch runs twice untimed: the first call builds the pools, the second re-sizes the output arenas
+    # from the density the context has now seen (one more pinned allocation, 0.2 s per GB and serialised
+    # between the processes of a box); after that steady-state calls allocate nothing
+    for it, b0 in enumerate([starts[0], starts[0]] + starts):
+        warm = it < 2
         idx = mine[b0:b0 + B]
         n = len(idx)
         sizes = [int(lens[i]) * ch for i in idx]
@@ -127,20 +140,37 @@ def config4(ctx, scale, rank, world, dist):
         outs = (C.POINTER(_ffi.Encoded) * n)()
         if dist:
             dist.barrier()
+        ctx.stats_reset()
         t0 = time.perf_counter()
         _ffi.check(L.glc_encode_batch(enc_h, n, pp, ns, chs, outs))
         t1 = time.perf_counter()
+        if dist:
+            dist.barrier()  # every rank decodes while every other rank decodes (not while it refills its arena)
+        t1b = time.perf_counter()
         pcm = (C.POINTER(C.c_float) * n)()
         cnt = (C.c_uint64 * n)()
         _ffi.check(L.glc_decode_batch(dec_h, n, outs, pcm, cnt))
         t2 = time.perf_counter()
+        st = ctx.stats()
+        if dist:
+            dist.barrier()
         for j in range(n):
             assert cnt[j] == sizes[j], f"track {idx[j]}: decoded {cnt[j]} != {sizes[j]}"  # per-track gapless count
             L.glc_free(ctx.handle, pcm[j])
             L.glc_encoded_free(ctx.handle, outs[j])
         if not warm:
             t_enc += t1 - t0
-            t_dec += t2 - t1
+            t_dec += t2 - t1b
+            tb = [t1 - t0, t2 - t1b]
+            if dist:
+                import torch
+
+                tt = torch.tensor(tb, dtype=torch.float64, device=f"cuda:{ctx.device}")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                tb = [float(tt[0]), float(tt[1])]
+            per_batch.append((round(tb[0] * 1e3, 1), round(tb[1] * 1e3, 1)))
+            for k in grow:
+                grow[k] += st[k]
             total_out += sum(cnt[j] for j in range(n))
             total_in += sum(sizes)
         L.glc_host_free(ctx.handle, C.c_void_p(arena.ctypes.data))
@@ -159,7 +189,43 @@ def config4(ctx, scale, rank, world, dist):
     return {"config": "4: 10 000 short tracks sharded by file", "tracks": n_tracks, "n_gpus": world, "audio_s": audio,
             "encode_e2e_audio_s_per_s": audio / t_enc, "decode_e2e_audio_s_per_s": audio / t_dec,
             "roundtrip_e2e_audio_s_per_s": audio / (t_enc + t_dec),
-            "gapless": "per-track decoded count == input count; sum == sum", "batch": f"{B} tracks per call, {n_batches} calls per rank (+1 untimed warm-up call)"}
+            "max_over_ranks_ms_per_batch_encode_decode": per_batch, "rank0_pool_growth_inside_timed_calls": grow,
+            "gapless": "per-track decoded count == input count; sum == sum", "batch": f"{B} tracks per call, {n_batches} calls per rank (+2 untimed warm-up calls)"}
+
+
+def _utf8_len(v):
+    return 1 if v < 0x80 else 2 if v < 0x800 else 3 if v < 0x10000 else 4 if v < 0x200000 else 5
+
+
+def _verify_config5(blob, x, sr, ch, n_ranges=8, n=12):
+    """The whole stream under the independent RFC 9639 decoder (frame-number sequence, CRC-8, CRC-16 of every
+    frame, MD5 of STREAMINFO, every sample equal to the reference's f32 -> i16 conversion), then sampled
+    frame ranges byte for byte against the oracle's encode of the same blocks (frames are independent given
+    the frame number: everything but the coded number, the header CRC-8 and the frame CRC-16 must be equal;
+    those three were just verified by the decoder)."""
+    import oracle
+
+    bs = 4096
+    info = oracle.flac_decode(blob, frame_offsets=True)
+    total = x.size // ch
+    assert info["md5_ok"] and info["total_samples"] == total and info["n_frames"] == (total + bs - 1) // bs
+    want = np.trunc(np.clip(x * np.float32(32767.0), -32768.0, 32767.0)).astype(np.int16)
+    assert np.array_equal(info["samples"].astype(np.int16), want) and int(np.abs(info["samples"]).max()) <= 32768
+    off = info["frame_off"]
+    rng = np.random.default_rng(5)
+    starts = sorted({0, 120, 2040, 65530, info["n_frames"] - n - 1} | {int(v) for v in rng.integers(0, info["n_frames"] - n - 1, n_ranges)})
+    starts = [f for f in starts if 0 <= f < info["n_frames"] - n]
+    for f0 in starts:
+        ref = oracle.flac_encode(np.asarray(x[f0 * bs * ch:(f0 + n) * bs * ch]), sr, ch, 8)
+        roff = oracle.flac_decode(ref, frame_offsets=True)["frame_off"]
+        for j in range(n):
+            a = blob[int(off[f0 + j]) + 4 + _utf8_len(f0 + j) + 1:int(off[f0 + j + 1]) - 2]
+            r = ref[int(roff[j]) + 4 + _utf8_len(j) + 1:int(roff[j + 1]) - 2]
+            assert a == r, f"frame {f0 + j}: subframe bytes differ from the oracle's"
+            assert blob[int(off[f0 + j]):int(off[f0 + j]) + 4] == ref[int(roff[j]):int(roff[j]) + 4]
+    return {"decoded_frames": int(info["n_frames"]), "md5_ok": True, "samples_equal_reference_conversion": True,
+            "frame_ranges_byte_equal_to_oracle": [[f, f + n] for f in starts],
+            "longest_coded_frame_number_bytes": _utf8_len(int(info["n_frames"]) - 1)}
 
 
 def config5(ctx, scale):
@@ -183,11 +249,7 @@ def config5(ctx, scale):
         dt = time.perf_counter() - t0
         nbytes = ln.value
         if rep == 0:
-            import oracle
-
-            blob = C.string_at(b, min(nbytes, 42 + 3_000_000))
-            # lossless check on the first frames with the independent decoder is done in tests; here: header only
-            assert blob[:4] == b"fLaC"
+            verify = _verify_config5(C.string_at(b, nbytes), xp, sr, ch)
         L.glc_free(ctx.handle, b)
         best = min(best, dt)
         st = ctx.stats()
@@ -196,6 +258,7 @@ def config5(ctx, scale):
     return {"config": "5: FLAC level 8, 96 kHz stereo", "audio_s": secs, "bytes_in": int(xp.size * 4), "bytes_out": int(nbytes),
             "e2e_audio_s_per_s": secs / best, "e2e_ms": best * 1e3, "kernel_ms": k_ms,
             "kernel_audio_s_per_s": secs / (k_ms * 1e-3), "kernel_hbm_gbs": (xp.size * 4 + nbytes) / (k_ms * 1e-3) / 1e9,
+            "verified": verify,
             "note": "e2e is bound by the serial MD5 of the file's samples on one host core (src/flac.rs:305-318)"}
 
 
