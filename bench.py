@@ -498,14 +498,15 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         # FAST mode: the fused window + FFT-MDCT + quantise + pack kernel is HBM-bound by design.
         # Algorithmic bytes per launch: every PCM sample once (4096 B per frame-channel)
         # + the pairs it emits (4 B each) + scale and count (8 B per frame-channel).
-        fe_ms = k_ms["fast_encode"] / max(k_n["fast_encode"], 1)
+        n_l = max(k_n["fast_encode"], 1) / args.steps
+        fe_ms = k_ms["fast_encode"] / args.steps  # per step (a step is a few launches)
         fe_bytes = rows * 4096.0 + host_step.pairs * 4.0 + rows * 8.0
         fe_gbs = fe_bytes / (fe_ms * 1e-3) / 1e9
         roofline = {
             "kernel": "fast_encode_kernel (fused window + fold + 512-point FFT DCT-IV + thresholds + quantise + ordered pack)",
             "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fe_gbs / hbm_peak,
             "peak_source": peak_src, "traffic": None, "launches_per_step": k_n["fast_encode"] / args.steps,
-            "ms_per_launch": fe_ms, "algorithmic_bytes_per_launch": fe_bytes,
+            "ms_per_launch": fe_ms / n_l, "algorithmic_bytes_per_launch": fe_bytes / n_l,
             "kernel_ms_per_step": {k: v / args.steps for k, v in k_ms.items() if v},
         }
     else:
@@ -625,14 +626,23 @@ def bench_fast_side(device: int, _unused, args, rows: int, pairs: int, hbm_peak:
     ms = sum(step() for _ in range(steps)) / steps
     st = ctx.stats()
     ctx.enable_kernel_timing(False)
-    fe_ms = st["kernel_ms"]["fast_encode"] / max(st["launches"]["fast_encode"], 1)
+    # achieved = the step's algorithmic bytes / the kernel's time per step (a step is cut into a few launches of
+    # up to 151 552 frame-channels; per-launch figures are the step's divided by the launches of a step)
+    n_l = max(st["launches"]["fast_encode"], 1) / steps
+    fe_ms = st["kernel_ms"]["fast_encode"] / steps
     fe_bytes = rows * 4096.0 + pairs * 4.0 + rows * 8.0  # SURVEY.md 8(d); `pairs` from the EXACT stream (same order of magnitude)
     out = {
         "mode": "FAST (FFT-based true MDCT fused with the quantiser; tolerance class, NOT bit-exact)",
         "value": args.seconds / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
         "roofline": {"kernel": "fast_encode_kernel", "bound": "hbm", "achieved": fe_bytes / (fe_ms * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / hbm_peak,
-                     "peak_source": peak_src, "ms_per_launch": fe_ms, "algorithmic_bytes_per_launch": fe_bytes},
+                     "peak_source": peak_src, "launches_per_step": n_l, "ms_per_launch": fe_ms / n_l,
+                     "algorithmic_bytes_per_launch": fe_bytes / n_l,
+                     # executed warp instructions per frame-channel (ncu, profiles/r2_ncu_fast_encode_*): the 512-point
+                     # FFT alone is 880, i.e. at a perfect issue rate the FFT alone takes as long as moving the
+                     # kernel's bytes at the full HBM rate: the kernel is instruction-bound by construction
+                     "instruction_floor_note": "2 920 warp-instructions per frame-channel (FFT 880); at 100 % issue "
+                                               "that is 0.29 of the HBM peak, 0.60 would need <= 1 400 in total"},
         "kernel_ms_per_step": {k: v / steps for k, v in st["kernel_ms"].items() if v},
     }
     L.glc_dev_pcm_free(dpcm)
@@ -681,7 +691,35 @@ def bench_flac(ctx, args) -> dict:
     k_ms = (st["kernel_ms"]["flac_block"] + st["kernel_ms"]["flac_gather"]) / reps
     # algorithmic bytes per sample: 4 B f32 in + the emitted bitstream
     alg = xp.size * 4.0 + nbytes
-    return {"workload": f"FLAC level 8, {args.flac_seconds:.0f} s 96 kHz stereo, 16-bit (reference truncates 24-bit)",
+
+    # The same audio as a batch of one-minute files (glc_flac_encode_batch): the per-file MD5 chains run on one
+    # host thread each, so the serial hash of a single long file no longer hides the device work.
+    n_files = max(1, int(args.flac_seconds // 60))
+    per = 60 * sr * 2
+    batch = None
+    if n_files >= 2:
+        ptrs = (C.c_void_p * n_files)(*[xp.ctypes.data + 4 * per * i for i in range(n_files)])
+        ns = (C.c_uint64 * n_files)(*([per] * n_files))
+        srs = (C.c_uint32 * n_files)(*([sr] * n_files))
+        chs = (C.c_uint16 * n_files)(*([2] * n_files))
+
+        def many():
+            outs = (C.POINTER(C.c_uint8) * n_files)()
+            lens = (C.c_uint64 * n_files)()
+            _ffi.check(L.glc_flac_encode_batch(ctx.handle, n_files, ptrs, ns, srs, chs, 8, outs, lens))
+            tot = sum(lens[i] for i in range(n_files))
+            for i in range(n_files):
+                L.glc_free(ctx.handle, outs[i])
+            return tot
+
+        many()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            many()
+        dtb = (time.perf_counter() - t0) / reps
+        batch = {"files": n_files, "seconds_per_file": 60, "e2e_audio_s_per_s": n_files * 60 / dtb, "e2e_ms": dtb * 1e3,
+                 "api": "glc_flac_encode_batch (one host MD5 thread per file)"}
+    return {"batch_of_one_minute_files": batch, "workload": f"FLAC level 8, {args.flac_seconds:.0f} s 96 kHz stereo, 16-bit (reference truncates 24-bit)",
             "e2e_audio_s_per_s": args.flac_seconds / dt, "e2e_ms": dt * 1e3, "bytes_out": int(nbytes),
             "kernel_ms": k_ms, "kernel_audio_s_per_s": args.flac_seconds / (k_ms * 1e-3) if k_ms else None,
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": hbm_peak,

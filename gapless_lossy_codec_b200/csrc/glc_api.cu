@@ -1345,7 +1345,6 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     CUDA_TRY(dmalloc(&de->d_scales, tot_rows, cs));
     CUDA_TRY(dmalloc(&de->d_raw_off, tot_frames + 1, cs));
     const bool fast = c->mode == GLC_MODE_FAST;
-    CUDA_TRY(ds.alloc(&d_slots, tot_rows * kHop)); // EXACT: per-row slots; FAST: per-group compact blocks
     if (!fast)
         CUDA_TRY(ds.alloc(&d_raw_len, tot_frames));
     // the compact outputs are produced wave by wave, so they are sized for the worst case
@@ -1361,8 +1360,6 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     uint64_t target_rows = kRowQuantum * (host_pcm ? 4 : 32);
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1); // explicit tuning: rows per wave
-    if (fast && !host_pcm)
-        target_rows = UINT64_MAX; // device-resident: the fused FFT kernel takes the whole batch in one launch
     uint64_t max_wave_rows = 0;
     const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, true,
                                                (host_pcm && !c->wave_frames) ? kRowQuantum : 0);
@@ -1396,6 +1393,9 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     uint32_t *d_grp_pairs = nullptr, *d_grp_raw = nullptr;
     uint64_t *d_grp_pair_off = nullptr, *d_grp_raw_off = nullptr;
     unsigned int *d_tickets = nullptr;
+    // slots live for one wave only (EXACT: per-row slots read by the gather of the same wave; FAST: per-group
+    // compact blocks read by the placement of the same wave): sized by the largest wave, indexed by absolute row
+    CUDA_TRY(ds.alloc(&d_slots, max_wave_rows * kHop));
     if (!fast)
     {
         CUDA_TRY(ds.alloc(&d_coefs, max_wave_rows * kHop));
@@ -1545,7 +1545,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             fe.nnz = de->d_nnz;
             fe.scales = de->d_scales;
             fe.is_raw = de->d_is_raw;
-            fe.slots = d_slots;
+            fe.slots = d_slots - w.r0 * kHop;
             fe.grp_pairs = d_grp_pairs;
             fe.grp_raw = d_grp_raw;
             fe.ticket = d_tickets + wi;
@@ -1603,7 +1603,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             q.group_begin = group_of_frame(w.f0);
             q.group_end = group_of_frame(w.f1);
             q.perc = enc->d_perc;
-            q.slots = d_slots;
+            q.slots = d_slots - w.r0 * kHop;
             q.nnz = de->d_nnz;
             q.scales = de->d_scales;
             q.is_raw = de->d_is_raw;
@@ -1623,7 +1623,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         {
             LaunchScope ls(c, GLC_K_GATHER, cs, 2);
             GatherLaunch g{};
-            g.slots = d_slots;
+            g.slots = d_slots - w.r0 * kHop;
             g.nnz = de->d_nnz;
             g.pair_off = de->d_pair_off;
             g.pairs = de->d_pairs;
