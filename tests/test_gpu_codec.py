@@ -422,3 +422,35 @@ def test_raw_frames_saturate_out_of_range_samples(gpu_ctx):
         assert enc.frame_is_raw.all() and (np.abs(enc.raw.astype(np.int32)) >= 32767).any()
         want16 = np.trunc(np.clip(pcm * np.float32(32767.0), -32768.0, 32767.0)).astype(np.int16)
         assert np.array_equal(Decoder(ch, 44100, gpu_ctx).decode_pcm16(enc), want16)
+
+
+def test_pageable_and_pinned_inputs_give_the_same_stream_and_dma_probe(gpu_ctx):
+    """Encoder::encode borrows a slice (src/codec.rs:421): ordinary pageable memory.  Inputs above 256 KiB are
+    staged through the library's ring of pinned chunks by host threads; buffers from glc_host_alloc go to the DMA
+    engine directly.  Both must give the oracle's stream; the statistics say which path carried the bytes."""
+    import ctypes as C
+
+    from gapless_lossy_codec_b200 import Decoder, Encoder, _ffi
+
+    x = np.tile(signals.music_like(44100, 2, 5.0), 8)  # 14 MB: several 8 MiB chunks, ragged last one
+    ref = oracle.encode(x, 2, 44100)
+    enc = Encoder(44100, gpu_ctx)
+    gpu_ctx.stats_reset()
+    assert_encoded_equal(enc.encode(x, 2), ref, "pageable input")
+    st = gpu_ctx.stats()
+    assert st["staged_bytes"] == x.nbytes and st["h2d_bytes"] >= x.nbytes
+    xp = gpu_ctx.pinned_array(x.size)
+    xp[:] = x
+    gpu_ctx.stats_reset()
+    assert_encoded_equal(enc.encode(xp, 2), ref, "pinned input")
+    assert gpu_ctx.stats()["staged_bytes"] == 0
+    # decode from a stream held in pageable numpy arrays (what the Rust shim's Flat::new builds)
+    gpu_ctx.stats_reset()
+    assert_pcm_bits_equal(Decoder(2, 44100, gpu_ctx).decode(to_product(ref)), oracle.decode(ref), "pageable stream")
+    assert gpu_ctx.stats()["staged_bytes"] > 0
+    # the pure-DMA probe moves the bytes it is asked to move and reports a positive time
+    ms = C.c_float()
+    _ffi.check(gpu_ctx._lib.glc_dma_probe(gpu_ctx.handle, 64 << 20, 32 << 20, 1, C.byref(ms)))
+    assert 0.0 < ms.value < 1000.0
+    _ffi.check(gpu_ctx._lib.glc_dma_probe(gpu_ctx.handle, 0, 1 << 20, 0, C.byref(ms)))
+    assert ms.value > 0.0
