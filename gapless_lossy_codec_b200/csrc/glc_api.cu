@@ -2051,11 +2051,13 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     CUDA_TRY(ds.alloc(&d_files, n_files));
     CUDA_TRY(cudaMemcpyAsync(d_files, files.data(), sizeof(DecFileDesc) * n_files, cudaMemcpyHostToDevice, cs));
     c->stats.h2d_bytes += sizeof(DecFileDesc) * n_files;
-    // Worst-case sizes (every row transformed, every k present); the live counts stay on the device,
-    // so the decode needs no host round trip.  `blocks` holds every row of the batch (+1 tile of
-    // slack for the clipped last tile of a wave) because hop h needs frames h-1 and h.
+    // Worst-case sizes per WAVE (every row transformed, every k present); the live counts stay on the device,
+    // so the decode needs no host round trip.  `blocks` is a ring of two waves: hop h needs frames h-1 and h,
+    // i.e. the overlap-add of a wave reads its own blocks and the last frame of the wave before it, never
+    // anything older (8 KiB per row of two waves instead of 8 KiB per row of the whole batch).
+    const uint64_t ring_cap = (max_wave_rows + kImdctBM - 1) / kImdctBM * kImdctBM + kBM; // slots per ring half
     CUDA_TRY(ds.alloc(&d_atiles, wave_tiles * kImdctATileFloats));
-    CUDA_TRY(ds.alloc(&d_blocks, (tot_rows + kBM) * kFrame));
+    CUDA_TRY(ds.alloc(&d_blocks, 2 * ring_cap * kFrame));
     CUDA_TRY(ds.alloc(&d_flags, max_wave_rows));
     CUDA_TRY(ds.alloc(&d_slot_off, max_wave_rows + 1));
     CUDA_TRY(ds.alloc(&d_row_slot, tot_rows));
@@ -2113,6 +2115,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     for (size_t wi = 0; wi < waves.size(); ++wi)
     {
         const Wave &w = waves[wi];
+        const uint64_t slot_base = (wi & 1) * ring_cap; // this wave's half of the block ring
         if (io)
         {
             // H2D of this wave's pairs and raw frames, file segment by file segment
@@ -2170,6 +2173,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             fdl.twiddles = reinterpret_cast<const float2 *>(c->d_fast_tw);
             fdl.norm = c->host.norm;
             fdl.row_slot = d_row_slot;
+            fdl.slot_base = slot_base;
             fdl.blocks = d_blocks;
             CUDA_TRY(launch_fast_decode(fdl, cs));
         }
@@ -2185,7 +2189,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             q.n_files = n_files;
             q.row_begin = w.r0;
             q.row_end = w.r1;
-            q.slot_base = w.r0; // slots <= rows, so a wave's slots fit behind its first row index
+            q.slot_base = slot_base; // slots <= rows of the wave: they fit its half of the ring
             q.row_slot = d_row_slot;
             q.flags = d_flags;
             q.slot_off = d_slot_off;
@@ -2208,7 +2212,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             m.tab = c->d_tab_imdct;
             m.window = c->d_window;
             m.norm = c->host.norm;
-            m.blocks = d_blocks + w.r0 * kFrame;
+            m.blocks = d_blocks + slot_base * kFrame;
             CUDA_TRY(launch_imdct_exact(m, cs));
         }
         const uint64_t o0 = wi ? out_index(w.f0) : 0, o1 = out_index(w.f1);

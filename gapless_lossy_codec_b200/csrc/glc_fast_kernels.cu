@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kFastThreads, 5) fast_decode_kernel(const Fast
             const DecFileDesc &fd = p.files[lo];
             const uint64_t frame = fd.first_frame + (row - fd.first_row) / fd.channels;
             live = (!p.is_raw[frame] && p.pair_off[row + 1] > p.pair_off[row]) ? 1 : 0;
-            p.row_slot[row] = live ? (int32_t)row : -1;
+            p.row_slot[row] = live ? (int32_t)(p.slot_base + (row - p.row_begin)) : -1;
         }
         s_live[tid] = live;
     }
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kFastThreads, 5) fast_decode_kernel(const Fast
             if (!s_live[fa + h])
                 continue;
             const float *v = reinterpret_cast<const float *>(sm.u[fa]) + h * kCoefStride;
-            float *out = p.blocks + (row0 + fa + h) * kFrame;
+            float *out = p.blocks + (p.slot_base + (row0 - p.row_begin) + fa + h) * kFrame;
             // unfold (transpose of the fold) + synthesis window           src/codec.rs:672-675
             // four consecutive outputs per lane: [0,512) = v[512+i], [512,1536) = -v[1535-i] (read reversed),
             // [1536,2048) = -v[i-1536]; the segment is uniform over the warp in every iteration

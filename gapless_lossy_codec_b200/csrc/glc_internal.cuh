@@ -288,8 +288,9 @@ struct FastDecodeLaunch
     const float *window;
     const float2 *twiddles;
     float norm;
-    int32_t *row_slot; // [batch rows] row itself when transformed, -1 otherwise
-    float *blocks;     // [batch rows][2048]
+    uint64_t slot_base; // first slot of this wave in `blocks` (a ring of two waves)
+    int32_t *row_slot;  // [batch rows] slot_base + (row - row_begin) when transformed, -1 otherwise
+    float *blocks;      // [2 waves of slots][2048]
 };
 cudaError_t launch_fast_decode(const FastDecodeLaunch &p, cudaStream_t s);
 
