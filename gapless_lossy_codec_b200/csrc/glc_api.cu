@@ -1358,6 +1358,8 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     // Host input: small waves so that the H2D of wave w+1 hides behind the MDCT of wave w.
     // Device-resident input: large waves (fewer launches, scratch still bounded).
     uint64_t target_rows = kRowQuantum * (host_pcm ? 4 : 32);
+    if (fast && !host_pcm)
+        target_rows = kRowQuantum * 110; // device-resident FAST: one launch per ~521 000 rows (2 GiB of slots at most)
     if (c->wave_frames)
         target_rows = std::max<uint64_t>(c->wave_frames, 1); // explicit tuning: rows per wave
     uint64_t max_wave_rows = 0;

@@ -113,84 +113,94 @@ def config4(ctx, scale, rank, world, dist):
     enc_h, dec_h = C.c_void_p(), C.c_void_p()
     _ffi.check(L.glc_encoder_new(ctx.handle, sr, C.byref(enc_h)))
     _ffi.check(L.glc_decoder_new(ctx.handle, ch, sr, C.byref(dec_h)))
-    t_enc = t_dec = 0.0
-    total_in = total_out = 0
-    per_batch = []
-    grow = {"pinned_allocs": 0, "pinned_alloc_bytes": 0, "dev_allocs": 0, "dev_alloc_bytes": 0}
     n_batches = max(1, (len(mine) + 999) // 1000)
     B = (len(mine) + n_batches - 1) // n_batches  # equal batches of <= 1000 tracks (same pool size classes)
     starts = list(range(0, len(mine), B))
-    # the first batch runs twice untimed: the first call builds the pools, the second re-sizes the output arenas
-    # from the density the context has now seen (one more pinned allocation, 0.2 s per GB and serialised
-    # between the processes of a box); after that steady-state calls allocate nothing
-    for it, b0 in enumerate([starts[0], starts[0]] + starts):
-        warm = it < 2
-        idx = mine[b0:b0 + B]
-        n = len(idx)
-        sizes = [int(lens[i]) * ch for i in idx]
-        arena = ctx.pinned_array(sum(sizes))
-        ptrs, off = [], 0
-        for i, sz in zip(idx, sizes):
-            arena[off:off + sz] = bases[i % len(bases)][:sz]
-            ptrs.append(arena.ctypes.data + off * 4)
-            off += sz
-        pp = (C.c_void_p * n)(*ptrs)
-        ns = (C.c_uint64 * n)(*sizes)
-        chs = (C.c_uint16 * n)(*([ch] * n))
-        outs = (C.POINTER(_ffi.Encoded) * n)()
-        if dist:
-            dist.barrier()
-        ctx.stats_reset()
-        t0 = time.perf_counter()
-        _ffi.check(L.glc_encode_batch(enc_h, n, pp, ns, chs, outs))
-        t1 = time.perf_counter()
-        if dist:
-            dist.barrier()  # every rank decodes while every other rank decodes (not while it refills its arena)
-        t1b = time.perf_counter()
-        pcm = (C.POINTER(C.c_float) * n)()
-        cnt = (C.c_uint64 * n)()
-        _ffi.check(L.glc_decode_batch(dec_h, n, outs, pcm, cnt))
-        t2 = time.perf_counter()
-        st = ctx.stats()
-        if dist:
-            dist.barrier()
-        for j in range(n):
-            assert cnt[j] == sizes[j], f"track {idx[j]}: decoded {cnt[j]} != {sizes[j]}"  # per-track gapless count
-            L.glc_free(ctx.handle, pcm[j])
-            L.glc_encoded_free(ctx.handle, outs[j])
-        if not warm:
-            t_enc += t1 - t0
-            t_dec += t2 - t1b
-            tb = [t1 - t0, t2 - t1b]
+
+    def run(io16):
+        """io16: 16-bit PCM in and out (glc_encode_batch_i16 + glc_decode_batch_i16: what `glc` moves between two
+        16-bit WAV files, src/audio.rs:11-16, 51-59) instead of f32 in and out: half the PCIe bytes."""
+        t_enc = t_dec = 0.0
+        total_in = total_out = 0
+        per_batch = []
+        grow = {"pinned_allocs": 0, "pinned_alloc_bytes": 0, "dev_allocs": 0, "dev_alloc_bytes": 0}
+        # the first batch runs twice untimed: the first call builds the pools, the second re-sizes the output arenas
+        # from the density the context has now seen (one more pinned allocation, 0.2 s per GB and serialised
+        # between the processes of a box); after that steady-state calls allocate nothing
+        for it, b0 in enumerate([starts[0], starts[0]] + starts):
+            warm = it < 2
+            idx = mine[b0:b0 + B]
+            n = len(idx)
+            sizes = [int(lens[i]) * ch for i in idx]
+            arena = ctx.pinned_array(sum(sizes), np.int16 if io16 else np.float32)
+            ptrs, off = [], 0
+            for i, sz in zip(idx, sizes):
+                src = bases[i % len(bases)][:sz]
+                arena[off:off + sz] = np.rint(src * 16384.0).astype(np.int16) if io16 else src
+                ptrs.append(arena.ctypes.data + off * arena.itemsize)
+                off += sz
+            pp = (C.c_void_p * n)(*ptrs)
+            ns = (C.c_uint64 * n)(*sizes)
+            chs = (C.c_uint16 * n)(*([ch] * n))
+            outs = (C.POINTER(_ffi.Encoded) * n)()
             if dist:
-                import torch
+                dist.barrier()
+            ctx.stats_reset()
+            t0 = time.perf_counter()
+            _ffi.check((L.glc_encode_batch_i16 if io16 else L.glc_encode_batch)(enc_h, n, pp, ns, chs, outs))
+            t1 = time.perf_counter()
+            if dist:
+                dist.barrier()  # every rank decodes while every other rank decodes (not while it refills its arena)
+            t1b = time.perf_counter()
+            pcm = ((C.POINTER(C.c_int16) if io16 else C.POINTER(C.c_float)) * n)()
+            cnt = (C.c_uint64 * n)()
+            _ffi.check((L.glc_decode_batch_i16 if io16 else L.glc_decode_batch)(dec_h, n, outs, pcm, cnt))
+            t2 = time.perf_counter()
+            st = ctx.stats()
+            if dist:
+                dist.barrier()
+            for j in range(n):
+                assert cnt[j] == sizes[j], f"track {idx[j]}: decoded {cnt[j]} != {sizes[j]}"  # per-track gapless count
+                L.glc_free(ctx.handle, pcm[j])
+                L.glc_encoded_free(ctx.handle, outs[j])
+            if not warm:
+                t_enc += t1 - t0
+                t_dec += t2 - t1b
+                tb = [t1 - t0, t2 - t1b]
+                if dist:
+                    import torch
 
-                tt = torch.tensor(tb, dtype=torch.float64, device=f"cuda:{ctx.device}")
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                tb = [float(tt[0]), float(tt[1])]
-            per_batch.append((round(tb[0] * 1e3, 1), round(tb[1] * 1e3, 1)))
-            for k in grow:
-                grow[k] += st[k]
-            total_out += sum(cnt[j] for j in range(n))
-            total_in += sum(sizes)
-        L.glc_host_free(ctx.handle, C.c_void_p(arena.ctypes.data))
-    assert total_in == total_out  # gapless: sum of decoded lengths == sum of original lengths
-    audio = total_in / ch / sr
-    if dist:
-        import torch
+                    tt = torch.tensor(tb, dtype=torch.float64, device=f"cuda:{ctx.device}")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    tb = [float(tt[0]), float(tt[1])]
+                per_batch.append((round(tb[0] * 1e3, 1), round(tb[1] * 1e3, 1)))
+                for k in grow:
+                    grow[k] += st[k]
+                total_out += sum(cnt[j] for j in range(n))
+                total_in += sum(sizes)
+            L.glc_host_free(ctx.handle, C.c_void_p(arena.ctypes.data))
+        assert total_in == total_out  # gapless: sum of decoded lengths == sum of original lengths
+        audio = total_in / ch / sr
+        if dist:
+            import torch
 
-        t = torch.tensor([t_enc, t_dec], dtype=torch.float64, device=f"cuda:{ctx.device}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        a = torch.tensor([audio], dtype=torch.float64, device=f"cuda:{ctx.device}")
-        dist.all_reduce(a, op=dist.ReduceOp.SUM)
-        t_enc, t_dec, audio = float(t[0]), float(t[1]), float(a[0])
+            t = torch.tensor([t_enc, t_dec], dtype=torch.float64, device=f"cuda:{ctx.device}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            a = torch.tensor([audio], dtype=torch.float64, device=f"cuda:{ctx.device}")
+            dist.all_reduce(a, op=dist.ReduceOp.SUM)
+            t_enc, t_dec, audio = float(t[0]), float(t[1]), float(a[0])
+        return {"audio_s": audio, "encode_e2e_audio_s_per_s": audio / t_enc, "decode_e2e_audio_s_per_s": audio / t_dec,
+                "roundtrip_e2e_audio_s_per_s": audio / (t_enc + t_dec),
+                "max_over_ranks_ms_per_batch_encode_decode": per_batch, "rank0_pool_growth_inside_timed_calls": grow}
+
+    res = {"config": "4: 10 000 short tracks sharded by file", "tracks": n_tracks, "n_gpus": world}
+    res.update(run(False))
+    res["pcm16_in_and_out"] = run(True)
+    res["gapless"] = "per-track decoded count == input count; sum == sum"
+    res["batch"] = f"{B} tracks per call, {n_batches} calls per rank (+2 untimed warm-up calls)"
     L.glc_encoder_free(enc_h)
     L.glc_decoder_free(dec_h)
-    return {"config": "4: 10 000 short tracks sharded by file", "tracks": n_tracks, "n_gpus": world, "audio_s": audio,
-            "encode_e2e_audio_s_per_s": audio / t_enc, "decode_e2e_audio_s_per_s": audio / t_dec,
-            "roundtrip_e2e_audio_s_per_s": audio / (t_enc + t_dec),
-            "max_over_ranks_ms_per_batch_encode_decode": per_batch, "rank0_pool_growth_inside_timed_calls": grow,
-            "gapless": "per-track decoded count == input count; sum == sum", "batch": f"{B} tracks per call, {n_batches} calls per rank (+2 untimed warm-up calls)"}
+    return res
 
 
 def _utf8_len(v):
