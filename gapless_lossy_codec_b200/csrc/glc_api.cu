@@ -129,9 +129,19 @@ struct PinnedPool
             blocks[best].used = true;
             return blocks[best].p;
         }
-        size_t cap = pool_size_class(bytes);
+        // Growth is expensive (cudaHostAlloc: about 0.2 s per GB, and serialised between the processes of a box),
+        // and the batches of a workload differ by a few per cent: large blocks get 25 % headroom so that the
+        // next, slightly larger request still fits (a block serves requests down to half its size)
+        size_t cap = pool_size_class(bytes >= ((size_t)16 << 20) ? bytes + bytes / 4 : bytes);
         void *p = nullptr;
-        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess)
+        cudaError_t e = cudaHostAlloc(&p, cap, cudaHostAllocDefault);
+        if (e != cudaSuccess && cap > pool_size_class(bytes))
+        {
+            (void)cudaGetLastError();
+            cap = pool_size_class(bytes); // no room for the headroom: the exact class
+            e = cudaHostAlloc(&p, cap, cudaHostAllocDefault);
+        }
+        if (e != cudaSuccess)
         {
             (void)cudaGetLastError();
             return nullptr;
@@ -203,7 +213,7 @@ struct DevicePool
             for (size_t i = 0; i < blocks.size(); ++i)
             {
                 const DevBlock &b = blocks[i];
-                if (b.used || b.cap < bytes || b.cap > bytes + bytes / 4 + ((size_t)4 << 20))
+                if (b.used || b.cap < bytes || b.cap > bytes + bytes / 2 + ((size_t)4 << 20))
                     continue;
                 if (pass == 0 && b.last != s)
                     continue; // prefer a block whose previous user ran on the same stream
@@ -220,9 +230,19 @@ struct DevicePool
             *out = b.p;
             return cudaSuccess;
         }
-        const size_t cap = bytes >= ((size_t)1 << 20) ? pool_size_class(bytes) : ((bytes + 511) & ~(size_t)511);
+        // large blocks get 12.5 % headroom: batches of a workload differ by a few per cent (a block serves
+        // requests down to two thirds of its size, see above)
+        size_t cap = bytes >= ((size_t)16 << 20)  ? pool_size_class(bytes + bytes / 8)
+                     : bytes >= ((size_t)1 << 20) ? pool_size_class(bytes)
+                                                  : ((bytes + 511) & ~(size_t)511);
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, cap);
+        if (e != cudaSuccess && cap > pool_size_class(bytes))
+        {
+            (void)cudaGetLastError();
+            cap = pool_size_class(bytes); // no room for the headroom: the exact class
+            e = cudaMalloc(&p, cap);
+        }
         if (e != cudaSuccess)
         {
             // out of memory: give every idle block back to the driver and retry once
@@ -1505,7 +1525,16 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
                                        file_pinned[copy_file] != 0, c->copy));
                     c->stats.h2d_bytes += (need - copy_done) * eb;
                     if (host_pcm->is_int)
-                        pending_convert.push_back({fd.pcm_off + copy_done, need - copy_done});
+                    {
+                        // one conversion launch per run of files: a file's PCM starts at most 3 elements (the
+                        // 16-byte alignment) after the previous one ends, and nobody reads the gap
+                        const uint64_t a = fd.pcm_off + copy_done, n = need - copy_done;
+                        if (!pending_convert.empty() &&
+                            a - (pending_convert.back().first + pending_convert.back().second) <= 4)
+                            pending_convert.back().second = a + n - pending_convert.back().first;
+                        else
+                            pending_convert.push_back({a, n});
+                    }
                     copy_done = need;
                     issued = true;
                 }
