@@ -641,7 +641,7 @@ def bench_fast_side(device: int, _unused, args, rows: int, pairs: int, hbm_peak:
                      # executed warp instructions per frame-channel (ncu, profiles/r2_ncu_fast_encode_*): the 512-point
                      # FFT alone is 880, i.e. at a perfect issue rate the FFT alone takes as long as moving the
                      # kernel's bytes at the full HBM rate: the kernel is instruction-bound by construction
-                     "instruction_floor_note": "2 920 warp-instructions per frame-channel (FFT 880); at 100 % issue "
+                     "instruction_floor_note": "2 884 warp-instructions per frame-channel (ncu; FFT 867); at 100 % issue "
                                                "that is 0.29 of the HBM peak, 0.60 would need <= 1 400 in total"},
         "kernel_ms_per_step": {k: v / steps for k, v in st["kernel_ms"].items() if v},
     }
