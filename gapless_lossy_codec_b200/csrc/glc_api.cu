@@ -1367,10 +1367,6 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     const bool fast = c->mode == GLC_MODE_FAST;
     if (!fast)
         CUDA_TRY(ds.alloc(&d_raw_len, tot_frames));
-    // the compact outputs are produced wave by wave, so they are sized for the worst case
-    // (every coefficient kept / every frame raw); the live totals stay on the device
-    CUDA_TRY(dmalloc(&de->d_pairs, tot_rows * kHop, cs));
-    CUDA_TRY(dmalloc(&de->d_raw, tot_rows * kFrame, cs));
 
     // Wave plan: contiguous frame ranges.  A wave's MDCT grid is (rows/128) x 8 CTAs and 2 x 148 CTAs
     // are resident at a time, so waves are sized in multiples of 37 row tiles (4 736 rows): every
@@ -1385,6 +1381,24 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     uint64_t max_wave_rows = 0;
     const std::vector<Wave> waves = plan_waves(files, tot_frames, tot_rows, target_rows, &max_wave_rows, true,
                                                (host_pcm && !c->wave_frames) ? kRowQuantum : 0);
+    // The compact outputs are produced wave by wave and their totals are only known on the device, so a wave's
+    // share is sized for the worst case (every coefficient kept / every frame raw).  Device-resident results keep
+    // all of it; a host-bound encode drains every wave over PCIe one wave behind, so it holds a ring of TWO waves
+    // (the gathers subtract the wave's first offsets, GatherLaunch::pair_bias) instead of 8 KiB per row of the batch.
+    glc_pair *d_ring_pairs = nullptr;
+    int16_t *d_ring_raw = nullptr;
+    const uint64_t ring_pairs = max_wave_rows * kHop, ring_raw = max_wave_rows * kFrame; // elements per half
+    cudaEvent_t ev_ring[2] = {nullptr, nullptr}; // the D2H copies out of each half have been queued up to here
+    if (ho)
+    {
+        CUDA_TRY(ds.alloc(&d_ring_pairs, 2 * std::max<uint64_t>(ring_pairs, 1)));
+        CUDA_TRY(ds.alloc(&d_ring_raw, 2 * std::max<uint64_t>(ring_raw, 1)));
+    }
+    else
+    {
+        CUDA_TRY(dmalloc(&de->d_pairs, tot_rows * kHop, cs));
+        CUDA_TRY(dmalloc(&de->d_raw, tot_rows * kFrame, cs));
+    }
     float *d_atiles = nullptr;
     uint64_t *d_first_group = nullptr;
     // frame groups (max(1, 8/ch) frames of one file): the unit of work of quant_pack and of the FAST kernel
@@ -1481,12 +1495,16 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
         CUDA_TRY(cudaStreamWaitEvent(c->d2h, wave_done[w], 0));
         if (p1 > p0)
-            CUDA_TRY(cudaMemcpyAsync(ho->h_pairs + p0, de->d_pairs + p0, (p1 - p0) * sizeof(glc_pair),
+            CUDA_TRY(cudaMemcpyAsync(ho->h_pairs + p0, d_ring_pairs + (w & 1) * ring_pairs, (p1 - p0) * sizeof(glc_pair),
                                      cudaMemcpyDeviceToHost, c->d2h));
         if (q1 > q0)
-            CUDA_TRY(cudaMemcpyAsync(ho->h_raw + q0, de->d_raw + q0, (q1 - q0) * sizeof(int16_t), cudaMemcpyDeviceToHost,
-                                     c->d2h));
+            CUDA_TRY(cudaMemcpyAsync(ho->h_raw + q0, d_ring_raw + (w & 1) * ring_raw, (q1 - q0) * sizeof(int16_t),
+                                     cudaMemcpyDeviceToHost, c->d2h));
         c->stats.d2h_bytes += (p1 - p0) * sizeof(glc_pair) + (q1 - q0) * sizeof(int16_t);
+        // wave w + 2 writes the same half of the ring: it waits for these copies
+        if (!ev_ring[w & 1])
+            ev_ring[w & 1] = get_event(c);
+        CUDA_TRY(cudaEventRecord(ev_ring[w & 1], c->d2h));
         return GLC_OK;
     };
     std::vector<char> file_pinned; // per file: can the DMA engine read the caller's buffer directly?
@@ -1502,6 +1520,8 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
     for (size_t wi = 0; wi < waves.size(); ++wi)
     {
         const Wave &w = waves[wi];
+        if (ho && wi >= 2) // this wave's half of the output ring is free once wave wi - 2 has left for the host
+            CUDA_TRY(cudaStreamWaitEvent(cs, ev_ring[wi & 1], 0));
         if (host_pcm)
         {
             // everything up to the last sample any frame < w.f1 can touch
@@ -1584,8 +1604,9 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             fe.grp_raw_off = d_grp_raw_off;
             fe.pair_off = de->d_pair_off;
             fe.raw_off = de->d_raw_off;
-            fe.pairs = de->d_pairs;
-            fe.raw = de->d_raw;
+            fe.pairs = ho ? d_ring_pairs + (wi & 1) * ring_pairs : de->d_pairs;
+            fe.raw = ho ? d_ring_raw + (wi & 1) * ring_raw : de->d_raw;
+            fe.ring = ho != nullptr;
             {
                 LaunchScope ls(c, GLC_K_FAST_ENCODE, cs);
                 CUDA_TRY(launch_fast_encode(fe, cs));
@@ -1657,10 +1678,12 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
             g.slots = d_slots - w.r0 * kHop;
             g.nnz = de->d_nnz;
             g.pair_off = de->d_pair_off;
-            g.pairs = de->d_pairs;
+            g.pairs = ho ? d_ring_pairs + (wi & 1) * ring_pairs : de->d_pairs;
             g.is_raw = de->d_is_raw;
             g.raw_off = de->d_raw_off;
-            g.raw = de->d_raw;
+            g.raw = ho ? d_ring_raw + (wi & 1) * ring_raw : de->d_raw;
+            g.pair_bias = ho ? de->d_pair_off + w.r0 : nullptr;
+            g.raw_bias = ho ? de->d_raw_off + w.f0 : nullptr;
             g.pcm_arena = d_arena;
             g.files = d_files;
             g.n_files = n_files;
@@ -1696,6 +1719,13 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         c->pool.release(h_tot);
         for (cudaEvent_t e : wave_done)
             c->ev_free.push_back(e);
+        // the ring goes back to the pool in compute-stream order: the last copies out of it come first
+        for (cudaEvent_t e : ev_ring)
+            if (e)
+            {
+                CUDA_TRY(cudaStreamWaitEvent(cs, e, 0));
+                c->ev_free.push_back(e);
+            }
     }
     if (ev_copy)
         c->ev_free.push_back(ev_copy);
@@ -1776,18 +1806,23 @@ static glc_status download_encoded(glc_dev_encoded *de, EncodeHostOut *ho, glc_e
     // the two big arrays may already have come down wave by wave (host-input encode)
     glc_pair *h_pairs = nullptr;
     int16_t *h_raw = nullptr;
-    if (ho && ho->h_pairs && ho->h_raw)
+    if (ho)
     {
-        h_pairs = ho->h_pairs;
-        h_raw = ho->h_raw;
-        blk->pinned.push_back(h_pairs);
-        blk->pinned.push_back(h_raw);
+        // an array that never grew is empty (no pairs / no raw frame in the whole batch): the device side of a
+        // host-bound encode is a ring of two waves, there is nothing left to fetch from it
+        if (ho->h_pairs)
+            blk->pinned.push_back(h_pairs = ho->h_pairs);
+        else
+            h_pairs = (glc_pair *)pin(0);
+        if (ho->h_raw)
+            blk->pinned.push_back(h_raw = ho->h_raw);
+        else
+            h_raw = (int16_t *)pin(0);
         ho->h_pairs = nullptr;
         ho->h_raw = nullptr;
     }
     else
     {
-        ho = nullptr;
         h_pairs = (glc_pair *)pin(de->n_pairs * 4);
         h_raw = (int16_t *)pin(de->n_raw * 2);
     }

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) gather_pairs_kernel(const GatherLaunch p)
     const int lane = threadIdx.x & 31;
     const uint32_t n = p.nnz[row];
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.slots + row * kHop);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(p.pairs + p.pair_off[row]);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(p.pairs + (p.pair_off[row] - (p.pair_bias ? *p.pair_bias : 0ull)));
     for (uint32_t j = lane; j < n; j += 32)
         dst[j] = src[j];
 }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) gather_raw_kernel(const GatherLaunch p)
     const FileDesc &fd = find_file_by_frame(p.files, p.n_files, frame, nullptr);
     const uint32_t ch = fd.channels;
     const uint64_t f = frame - fd.first_frame;
-    int16_t *dst = p.raw + p.raw_off[frame];
+    int16_t *dst = p.raw + (p.raw_off[frame] - (p.raw_bias ? *p.raw_bias : 0ull));
     const float *src = p.pcm_arena + fd.pcm_off;
     const long long base = (long long)(f * kHop) - kHop / 2; // sample index of i = 0
     auto conv = [](float x, float w) -> short { return f32_to_i16_rz_sat(__fmul_rn(__fmul_rn(x, w), 32767.0f)); };

@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(kThreads) fast_place_kernel(const FastEncodeLa
     }
     // pairs: one contiguous block (the destination is only 4-byte aligned)
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.slots + row0 * kHop);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(p.pairs + pair_base);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(p.pairs + (pair_base - (p.ring ? p.grp_pair_off[p.group_begin] : 0ull)));
     {
         // eight independent loads in flight per lane: the copy is latency-bound otherwise
         uint32_t k = lane;
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(kThreads) fast_place_kernel(const FastEncodeLa
     {
         const int4 *rs = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(p.slots + row0 * kHop) +
                                                         (size_t)(n_fc - n_raw_units) * kFrame);
-        int4 *rd = reinterpret_cast<int4 *>(p.raw + raw_base * (u64)kFrame);
+        int4 *rd = reinterpret_cast<int4 *>(p.raw + (raw_base - (p.ring ? p.grp_raw_off[p.group_begin] : 0ull)) * (u64)kFrame);
         const uint32_t n16 = n_raw_units * (kFrame * 2 / 16); // a multiple of 256
         for (uint32_t k = lane; k < n16; k += 8 * 32)
         {

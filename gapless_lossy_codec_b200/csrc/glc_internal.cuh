@@ -189,6 +189,11 @@ struct GatherLaunch
     const float *window;
     uint64_t row_begin, row_end;     // rows whose pairs are compacted by this launch
     uint64_t frame_begin, frame_end; // frames whose raw bodies are produced by this launch
+    // Host-bound encodes keep only two waves of compact output on the device (a ring): `pairs` / `raw` then point
+    // at this wave's half and the wave's first offsets (read on the device: pair_off[row_begin],
+    // raw_off[frame_begin]) are subtracted from every destination.  Null = absolute offsets.
+    const uint64_t *pair_bias;
+    const uint64_t *raw_bias;
 };
 cudaError_t launch_gather(const GatherLaunch &p, cudaStream_t s);
 
@@ -269,6 +274,9 @@ struct FastEncodeLaunch
     uint64_t *raw_off;   // [n_frames_total + 1]
     glc_pair *pairs;
     int16_t *raw;
+    // ring of two waves for host-bound encodes (see GatherLaunch): the placement subtracts
+    // grp_pair_off[group_begin] / grp_raw_off[group_begin] from its destinations when set
+    bool ring;
 };
 cudaError_t launch_fast_place(const FastEncodeLaunch &p, cudaStream_t s);
 constexpr int kFastTwiddleFloats = 2 * (32 * 16 + 16);
