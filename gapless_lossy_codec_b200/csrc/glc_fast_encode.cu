@@ -662,9 +662,11 @@ __global__ void __launch_bounds__(kThreads, 4) fast_encode_kernel(const FastEnco
                 sm.g_next = p.group_begin + atomicAdd(p.ticket, 1u); // this is the group's last step
             if (multi_round && last_count && tid == 0)
                 sm.frame_raw[0] = raw_units_total ? 1u : 0u; // read by the EMIT steps after their first barrier
-            if (multi_round && count_step && active && lane == 0)
+            if (multi_round && count_step && active && lane == 0 && !group_raw0)
             {
-                p.nnz[row0 + fc0 + warp] = sm.fc_nnz[warp]; // parked: final unless the frame turns out raw
+                // parked: final unless the frame turns out raw (then the last COUNT step has just zeroed every row
+                // of the frame, this round's included: it must not park on top of that)
+                p.nnz[row0 + fc0 + warp] = sm.fc_nnz[warp];
                 p.scales[row0 + fc0 + warp] = sm.fc_scale[warp];
             }
             if (emit_step && active)

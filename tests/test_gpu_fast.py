@@ -46,6 +46,10 @@ CASES = [
     ("ragged_len", lambda: signals.sine(300, 44100, 1, 0.3)[:4097], 1, 44100),
     ("three_channels", lambda: signals.music_like(44100, 3, 0.5), 3, 44100),
     ("ten_channels", lambda: signals.music_like(44100, 10, 0.4, seed=77), 10, 44100),
+    # wider than one round of 8 channels AND with raw frames: the COUNT rounds park per-row tables that the
+    # raw decision must clear (a race here left nnz of the last channels set; found by the wave-cut test below)
+    ("ten_channels_raw_frames", lambda: signals.music_like(44100, 10, 1.2, seed=5), 10, 44100),
+    ("seventeen_channels_raw_frames", lambda: signals.music_like(44100, 17, 0.9, seed=3), 17, 44100),
 ]
 
 
@@ -131,3 +135,31 @@ def test_flac_and_container_are_mode_independent(fast_ctx):
     assert blob == oracle.bincode_serialize(to_oracle(enc))
     back = encoded_from_bytes(blob, fast_ctx)
     assert np.array_equal(back.pair_q, enc.pair_q) and np.array_equal(back.raw, enc.raw)
+
+
+@pytest.mark.parametrize("wave_rows", [8, 48, 640])
+def test_fast_wave_size_does_not_change_bits(fast_ctx, wave_rows):
+    """The FAST encode pipeline is cut into waves too (host-bound encodes keep two waves of compact output in a
+    device ring and place each wave relative to its first offset): any cut gives the same stream, bit for bit,
+    as the automatic one -- pairs, raw bodies, offsets -- on a signal with raw and sparse frames, and the decode
+    of many small waves equals the decode of one."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder
+
+    cases = [(signals.music_like(44100, 2, 3.0), 2, 44100), (signals.music_like(48000, 6, 1.2, seed=9), 6, 48000),
+             (signals.music_like(44100, 10, 1.2, seed=5), 10, 44100)]
+    for x, ch, sr in cases:
+        auto = Encoder(sr, fast_ctx).encode(x, ch)
+        pcm_auto = Decoder(ch, sr, fast_ctx).decode(auto)
+        try:
+            fast_ctx.set_tuning(0, wave_rows)
+            cut = Encoder(sr, fast_ctx).encode(x, ch)
+            pcm_cut = Decoder(ch, sr, fast_ctx).decode(cut)
+        finally:
+            fast_ctx.set_tuning(0, 0)
+        a, b = to_oracle(auto), to_oracle(cut)
+        assert a.n_frames == b.n_frames and np.array_equal(a.frame_is_raw, b.frame_is_raw)
+        assert a.frame_is_raw.any() and not a.frame_is_raw.all(), "the case must mix raw and sparse frames"
+        assert np.array_equal(a.nnz, b.nnz) and np.array_equal(a.pair_idx, b.pair_idx) and np.array_equal(a.pair_q, b.pair_q)
+        assert np.array_equal(a.scales.view(np.uint32), b.scales.view(np.uint32))
+        assert np.array_equal(a.raw, b.raw)
+        assert np.array_equal(pcm_auto.view(np.uint32), pcm_cut.view(np.uint32))
