@@ -297,6 +297,26 @@ class Encoder:
                     self._lib.glc_encoded_free(self.ctx.handle, outs[i])
         return res
 
+    def encode_batch_i16(self, files: Sequence, channels: Sequence[int]) -> List[EncodedAudio]:
+        """`encode_batch` over 16-bit PCM (glc_encode_batch_i16): the loaders' division by 32768
+        (src/audio.rs:51-59) runs on the device, 16-bit samples cross PCIe."""
+        n = len(files)
+        arrs = [np.ascontiguousarray(f, np.int16).reshape(-1) for f in files]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        ns = (C.c_uint64 * n)(*[a.size for a in arrs])
+        chs = (C.c_uint16 * n)(*[int(c) for c in channels])
+        outs = (C.POINTER(_ffi.Encoded) * n)()
+        check(self._lib.glc_encode_batch_i16(self.handle, n, ptrs, ns, chs, outs))
+        res = []
+        try:
+            for i in range(n):
+                res.append(EncodedAudio._from_struct(outs[i].contents))
+        finally:
+            for i in range(n):
+                if outs[i]:
+                    self._lib.glc_encoded_free(self.ctx.handle, outs[i])
+        return res
+
 
 # ------------------------------------------------------------------ Decoder
 

@@ -245,6 +245,38 @@ def test_integer_pcm_ingest_matches_converted_f32(gpu_ctx):
     assert_encoded_equal(got, oracle.encode(x32.astype(np.float32) / np.float32(2147483648.0), 1, 44100), "32-bit ingest")
 
 
+@pytest.mark.parametrize("wave_rows", [0, 24])
+def test_integer_pcm_batch_of_ragged_files(gpu_ctx, wave_rows):
+    """glc_encode_batch_i16 over many short files of ragged lengths (every file starts 0-3 elements after the
+    previous one ends in the staging area, and the conversion of a run of files is ONE launch): each stream equals
+    the single-file encode of the converted f32 (oracle on a sample of the files, the f32 batch path on all),
+    also when waves cut the files in pieces."""
+    from gapless_lossy_codec_b200 import Encoder
+
+    rng = np.random.default_rng(11)
+    files, chs = [], []
+    base = {1: signals.music_like(44100, 1, 1.5, seed=21), 2: signals.music_like(44100, 2, 1.5, seed=22),
+            3: signals.music_like(44100, 3, 1.5, seed=23)}
+    for i in range(40):
+        ch = (1, 2, 3, 1)[i % 4]
+        n = int(rng.integers(600, 60000))  # sample frames; mono lengths of every residue mod 4
+        x = base[ch][: n * ch]
+        files.append(np.clip(np.round(x * 20000.0), -32768, 32767).astype(np.int16))
+        chs.append(ch)
+    enc = Encoder(44100, gpu_ctx)
+    try:
+        gpu_ctx.set_tuning(0, wave_rows)
+        got = enc.encode_batch_i16(files, chs)
+        want = enc.encode_batch([f.astype(np.float32) / np.float32(32768.0) for f in files], chs)
+    finally:
+        gpu_ctx.set_tuning(0, 0)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_encoded_equal(g, to_oracle(w), f"file {i} ({chs[i]} ch, {len(files[i])} samples): i16 batch vs f32 batch")
+    for i in (0, 7, 18, 39):
+        ref = oracle.encode(files[i].astype(np.float32) / np.float32(32768.0), chs[i], 44100)
+        assert_encoded_equal(got[i], ref, f"file {i}: i16 batch vs oracle")
+
+
 def test_decode_to_flac_equals_two_step_path(gpu_ctx):
     """"next" row 2 of SURVEY 8(f): `glc -d x.glc --flac-level N` = decode, then FLAC-encode the decoded
     samples (src/main.rs:55-113).  The fused call keeps the PCM in HBM; bytes must equal the oracle chain."""
