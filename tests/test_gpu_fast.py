@@ -51,6 +51,10 @@ CASES = [
     ("ten_channels_raw_frames", lambda: signals.music_like(44100, 10, 1.2, seed=5), 10, 44100),
     ("seventeen_channels_raw_frames", lambda: signals.music_like(44100, 17, 0.9, seed=3), 17, 44100),
 ]
+# every group geometry of the fused kernel (frames per group = max(1, 8 / ch); ch > 8: COUNT / EMIT rounds), each
+# with tonal AND raw frames
+CASES += [(f"{ch}_channels_raw_and_sparse", (lambda ch=ch: signals.music_like(44100, ch, 0.85, seed=40 + ch)), ch, 44100)
+          for ch in (4, 5, 7, 8, 9, 16)]
 
 
 @pytest.mark.parametrize("name,gen,ch,sr", CASES, ids=[c[0] for c in CASES])
