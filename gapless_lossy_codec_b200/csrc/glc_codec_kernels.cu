@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const DequantLaunch p)
 // which no row of the tile has a pair are neither written nor listed in stage_list.
 __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p)
 {
-    __shared__ uint32_t s_gbits[kImdctWarps][kHop / 32]; // index sets per 8-row group
+    __shared__ uint32_t s_gbits[kImdctMasks][kHop / 32]; // index sets per mask owner (warp of the IMDCT, or row)
     __shared__ uint32_t s_present[kImdctStages];         // OR of the group masks per stage
     const uint64_t n_active = p.slot_off[p.row_end - p.row_begin];
     const uint64_t tile = blockIdx.x;
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rows_here = (uint32_t)min((uint64_t)kImdctBM, n_active - tile * kImdctBM);
-    for (int e = tid; e < kImdctWarps * (kHop / 32); e += 256)
+    for (int e = tid; e < kImdctMasks * (kHop / 32); e += 256)
         (&s_gbits[0][0])[e] = 0;
     __syncthreads();
 
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         const uint32_t n = (uint32_t)(p.pair_off[row + 1] - b);
         const uint32_t chunk = (n + 31) / 32;
         const uint32_t j0 = min(n, lane * chunk), j1 = min(n, j0 + chunk);
-        uint32_t *gb = s_gbits[r / kImdctRowsPerWarp];
+        uint32_t *gb = s_gbits[GLC_IMDCT_ROWMASK ? r : r / kImdctRowsPerWarp];
         uint32_t cur = 0xffffffffu, mask = 0;
         for (uint32_t j = j0; j < j1; ++j)
         {
@@ -449,9 +449,9 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         const uint32_t st = tid;
         uint32_t any = 0;
         uint32_t *masks = reinterpret_cast<uint32_t *>(a + (size_t)st * kImdctAStageFloats + kImdctKC * kImdctBM);
-        uint32_t mm[kImdctWarps];
+        uint32_t mm[kImdctMasks];
 #pragma unroll
-        for (int g = 0; g < kImdctWarps; ++g)
+        for (int g = 0; g < kImdctMasks; ++g)
         {
             mm[g] = (s_gbits[g][(st * kImdctKC) >> 5] >> ((st * kImdctKC) & 31)) & kStageMask;
             any |= mm[g];
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256) dequant_tile_kernel(const DequantLaunch p
         s_present[st] = any;
         if (any)
 #pragma unroll
-            for (int g = 0; g < kImdctWarps; ++g)
+            for (int g = 0; g < kImdctMasks; ++g)
                 masks[g] = mm[g];
     }
     __syncthreads();

@@ -370,7 +370,14 @@ __global__ void __launch_bounds__(kImdctThreads, GLC_IMDCT_MINB) imdct_sparse_ke
 
         // bit-reversed step mask: the next step in ascending order is clz(rm).  Operand addresses are
         // formed as 32-bit shared-memory addresses (one shift-add each per step).
+#if GLC_IMDCT_ROWMASK
+        static_assert(!GLC_IMDCT_ROWMASK || kImdctRowsPerWarp == 2, "row masks are written for two rows per warp");
+        const uint2 rmw = reinterpret_cast<const uint2 *>(sm.a[slot] + kImdctKC * kImdctBM)[warp];
+        const uint32_t rm0 = __brev(rmw.x), rm1 = __brev(rmw.y);
+        uint32_t rm = rm0 | rm1;
+#else
         uint32_t rm = __brev(reinterpret_cast<const uint32_t *>(sm.a[slot] + kImdctKC * kImdctBM)[warp]);
+#endif
         const uint32_t a_base = smem_addr(sm.a[slot] + warp * RW);
         const uint32_t t_base = smem_addr(sm.t[slot] + lane * 4);
         while (rm)
@@ -392,11 +399,29 @@ __global__ void __launch_bounds__(kImdctThreads, GLC_IMDCT_MINB) imdct_sparse_ke
                 t[4 * q + 2] = v.z;
                 t[4 * q + 3] = v.w;
             }
+#if GLC_IMDCT_ROWMASK
+            // skipping a row at a step where it has no pair is exact: the product would be +-0 and the running
+            // sum, which starts at +0.0, is never -0
+            const uint32_t bit = 0x80000000u >> ii;
+            if (rm0 & bit)
+            {
+#pragma unroll
+                for (int c = 0; c < NO; ++c)
+                    acc[0][c] = __fadd_rn(acc[0][c], __fmul_rn(a[0], t[c]));
+            }
+            if (rm1 & bit)
+            {
+#pragma unroll
+                for (int c = 0; c < NO; ++c)
+                    acc[1][c] = __fadd_rn(acc[1][c], __fmul_rn(a[1], t[c]));
+            }
+#else
 #pragma unroll
             for (int r = 0; r < RW; ++r)
 #pragma unroll
                 for (int c = 0; c < NO; ++c)
                     acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
+#endif
         }
         __syncwarp();
         uint32_t nth = 0;

@@ -47,7 +47,14 @@ constexpr int kImdctStages = kHop / kImdctKC;                          // 32
 constexpr int kImdctRowsPerWarp = GLC_IMDCT_RW;
 constexpr int kImdctWarps = kImdctBM / kImdctRowsPerWarp;              // 16
 constexpr int kImdctThreads = kImdctWarps * 32;                        // 512
-constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctWarps;  // 1024 values + 16 masks = 4 160 B
+// GLC_IMDCT_ROWMASK: one step mask per ROW instead of one per warp; the warp still walks the union of its rows'
+// index sets (one table load per step) but executes a row's multiply-adds only at the steps that row holds
+// (warp-uniform branches)
+#ifndef GLC_IMDCT_ROWMASK
+#define GLC_IMDCT_ROWMASK 0
+#endif
+constexpr int kImdctMasks = GLC_IMDCT_ROWMASK ? kImdctBM : kImdctWarps;
+constexpr int kImdctAStageFloats = kImdctKC * kImdctBM + kImdctMasks;  // 1024 values + 16 masks = 4 160 B
 constexpr size_t kImdctATileFloats = (size_t)kImdctStages * kImdctAStageFloats;
 
 // One input file inside a batched encode (device copy lives in FileTable::d_files).
