@@ -47,6 +47,10 @@ CASES = [
     ("ten_channels", lambda: signals.music_like(44100, 10, 0.4, seed=77), 10, 44100),
     ("seventeen_channels", lambda: signals.sweep(200, 6000, 32000, 17, 0.25), 17, 32000),
 ]
+# every frame-group geometry (max(1, 8 / ch) frames per group) and channel counts beyond the OLA tile, each with
+# tonal AND raw frames (raw bodies are written planar and read interleaved, src/codec.rs:498-502, 626-644)
+CASES += [(f"{ch}_channels_raw_and_sparse", (lambda ch=ch: signals.music_like(44100, ch, 0.85, seed=60 + ch)), ch, 44100)
+          for ch in (3, 4, 5, 7, 8, 9, 10, 17)]
 
 
 @pytest.mark.parametrize("name,gen,ch,sr", CASES, ids=[c[0] for c in CASES])

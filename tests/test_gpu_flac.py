@@ -99,6 +99,15 @@ def test_multichannel_and_odd_rates(gpu_ctx):
     _check(gpu_ctx, signals.sine(300, 44100, 2, 0.2)[:-1], 44100, 2, 5, "length not a multiple of channels")
 
 
+@pytest.mark.parametrize("ch", [3, 4, 5, 7, 8])
+def test_channel_counts_up_to_eight(gpu_ctx, ch):
+    """every channel count the frame header can carry (src/flac.rs:806-812), at the largest block size (level 8:
+    the bit buffer of wide frames leaves shared memory) and at level 2 (1 152-sample blocks), ragged tails"""
+    x = signals.music_like(48000, ch, 0.35, seed=70 + ch)[: (16000 + ch) * ch]
+    _check(gpu_ctx, x, 48000, ch, 8, f"{ch} channels level 8")
+    _check(gpu_ctx, x[: 5000 * ch], 48000, ch, 2, f"{ch} channels level 2")
+
+
 def test_extreme_residuals_long_unary_runs(gpu_ctx):
     """alternating full-scale samples: |r| near 2^19, unary runs of hundreds of zeros"""
     x = np.tile(np.array([1.0, -1.0], np.float32), 5000)
