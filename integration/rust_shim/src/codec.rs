@@ -288,21 +288,27 @@ impl Flat
     }
 }
 
+/// `slice::from_raw_parts` must not see a null pointer, not even for an empty slice.
+unsafe fn view<'a, T>(p: *const T, n: usize) -> &'a [T]
+{
+    if n == 0 || p.is_null() { &[] } else { unsafe { slice::from_raw_parts(p, n) } }
+}
+
 /// struct glc_encoded -> EncodedAudio, frame by frame as Encoder::encode builds them
 /// (reference src/codec.rs:521-564).
 unsafe fn nested_from_flat(e: &GlcEncoded) -> EncodedAudio
 {
     let frames = e.n_frames as usize;
     let ch = e.channels as usize;
-    let (raw_flag, po, ro, scales) = unsafe
+    let (raw_flag, po, ro, scales): (&[u8], &[u64], &[u64], &[f32]) = unsafe
     {
-        (slice::from_raw_parts(e.frame_is_raw, frames), slice::from_raw_parts(e.pair_offset, frames * ch + 1),
-         slice::from_raw_parts(e.raw_offset, frames + 1), slice::from_raw_parts(e.scales, frames * ch))
+        (view(e.frame_is_raw, frames), view(e.pair_offset, frames * ch + 1), view(e.raw_offset, frames + 1),
+         view(e.scales, frames * ch))
     };
     let n_pairs = po[frames * ch] as usize;
     let n_raw = ro[frames] as usize;
-    let pairs: &[GlcPair] = if n_pairs == 0 { &[] } else { unsafe { slice::from_raw_parts(e.pairs, n_pairs) } };
-    let raw: &[i16] = if n_raw == 0 { &[] } else { unsafe { slice::from_raw_parts(e.raw, n_raw) } };
+    let pairs: &[GlcPair] = unsafe { view(e.pairs, n_pairs) };
+    let raw: &[i16] = unsafe { view(e.raw, n_raw) };
     let mut out = Vec::with_capacity(frames);
     for f in 0..frames
     {
@@ -467,7 +473,7 @@ impl Decoder
                         break;
                     }
                     // the chunk memory belongs to the stream until the next call: copy it out under the lock
-                    AudioChunk { samples: unsafe { slice::from_raw_parts(p, n as usize) }.to_vec(), is_last: last != 0 }
+                    AudioChunk { samples: unsafe { view(p, n as usize) }.to_vec(), is_last: last != 0 }
                 };
                 if last == 0
                 {
@@ -509,7 +515,7 @@ impl Decoder
         let mut p: *mut f32 = ptr::null_mut();
         let mut n: u64 = 0;
         check(unsafe { glc_decode(self.h.0, &flat.view, &mut p, &mut n) })?;
-        let all = if n == 0 { Vec::new() } else { unsafe { slice::from_raw_parts(p, n as usize) }.to_vec() };
+        let all = unsafe { view(p as *const f32, n as usize) }.to_vec();
         unsafe { glc_free(c.0, p as *mut std::os::raw::c_void) };
         drop(c);
         if let Some(ref s) = progress_sender

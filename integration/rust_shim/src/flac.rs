@@ -20,7 +20,7 @@ pub fn encode_flac_with_level(samples: &[f32], sample_rate: u32, channels: u16, 
     {
         glc_flac_encode(c.0, samples.as_ptr(), samples.len() as u64, sample_rate, channels, compression_level, &mut p, &mut n)
     })?;
-    let bytes = unsafe { slice::from_raw_parts(p, n as usize) }.to_vec();
+    let bytes = if n == 0 || p.is_null() { Vec::new() } else { unsafe { slice::from_raw_parts(p, n as usize) }.to_vec() };
     unsafe { glc_free(c.0, p as *mut std::os::raw::c_void) };
     Ok(bytes)
 }
