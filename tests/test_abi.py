@@ -73,3 +73,30 @@ def test_product_package_never_uses_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 for needle in ("import oracle", "from oracle", "libglc_oracle", "oracle/", "orc_"):
                     assert needle not in text, f"{f} references the oracle ({needle})"
+
+
+def test_rust_shim_binds_only_exported_symbols_and_matches_integration_md():
+    """The Rust shim cannot be compiled in this image (no cargo), so what can be checked is checked: every
+    function its `extern "C"` block declares is exported by the library with the same number of parameters as
+    include/glc.h declares, and the copies embedded in INTEGRATION.md are the files of integration/rust_shim/."""
+    from gapless_lossy_codec_b200 import _ffi
+
+    lib = _ffi.load()
+    shim = os.path.join(ROOT, "integration", "rust_shim")
+    codec = open(os.path.join(shim, "src", "codec.rs")).read()
+    block = re.search(r'unsafe extern "C" \{(.*?)\n    \}', codec, flags=re.S).group(1)
+    block = re.sub(r"//[^\n]*", "", block)
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "glc.h")).read(), flags=re.S)
+    fns = re.findall(r"pub fn (glc_[a-z0-9_]+)\s*\((.*?)\)", block, flags=re.S)
+    assert len(fns) >= 14
+    for name, params in fns:
+        assert hasattr(lib, name), f"{name}: bound by the shim, not exported"
+        c_params = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, header, flags=re.S).group(1)
+        n_c = 0 if c_params.strip() in ("", "void") else c_params.count(",") + 1
+        n_rs = 0 if not params.strip() else params.count(",") + 1
+        assert n_c == n_rs, f"{name}: {n_rs} parameters in the shim, {n_c} in include/glc.h"
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```rust\n(.*?)\n```", md, flags=re.S)
+    for rel in ("build.rs", os.path.join("src", "codec.rs"), os.path.join("src", "flac.rs")):
+        body = open(os.path.join(shim, rel)).read().rstrip("\n")
+        assert any(b.rstrip("\n") == body for b in blocks), f"INTEGRATION.md does not embed {rel} as it is on disk"
