@@ -1735,7 +1735,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
 
 static void block_unref(EncodedBlock *b)
 {
-    if (--b->refs > 0)
+    if (b->refs.fetch_sub(1, std::memory_order_acq_rel) > 1)
         return;
     for (void *p : b->pinned)
         b->ctx->pool.release(p);

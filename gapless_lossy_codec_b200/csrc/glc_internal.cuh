@@ -372,7 +372,7 @@ void ctx_time_end(glc_ctx *ctx, void *token);
 struct EncodedBlock
 {
     glc_ctx *ctx;
-    int refs;
+    std::atomic<int> refs; // the outputs of one batch call share a block and may be freed from different threads
     std::vector<void *> pinned;
     std::vector<void *> heap;
 };
