@@ -861,12 +861,19 @@ static cudaError_t h2d_async(glc_ctx *c, void *dst, const void *src, size_t byte
     {
         for (int i = 0; i < HostStager::kSlots; ++i)
         {
-            cudaError_t e = cudaHostAlloc(&st.slot[i], HostStager::kChunk, cudaHostAllocDefault);
+            if (st.slot[i]) // a previous attempt got this far before it ran out of memory
+                continue;
+            void *p = nullptr;
+            cudaError_t e = cudaHostAlloc(&p, HostStager::kChunk, cudaHostAllocDefault);
             if (e != cudaSuccess)
                 return e;
             e = cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming);
             if (e != cudaSuccess)
+            {
+                cudaFreeHost(p);
                 return e;
+            }
+            st.slot[i] = p; // slot and event exist together (the context's teardown relies on it)
         }
         int n = 3; // + the calling thread
         if (const char *v = getenv("GLC_COPY_THREADS"))
