@@ -32,13 +32,6 @@ using namespace glc;
 
 static thread_local std::string g_last_error;
 
-static double PhaseTraceNow()
-{
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-}
-
 static glc_status fail(glc_status st, const char *fmt, ...)
 {
     char buf[512];
@@ -1143,24 +1136,41 @@ extern "C" glc_status glc_dma_probe(glc_ctx *c, uint64_t h2d_bytes, uint64_t d2h
     }
     memset(h_up, 1, (size_t)std::max<uint64_t>(h2d_bytes, 16)); // touch: the pages exist before the clock starts
     memset(h_down, 1, (size_t)std::max<uint64_t>(d2h_bytes, 16));
+    // timed on the device: one start event, one end event per direction; the call's figure is the later end
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     cudaError_t e = cudaStreamSynchronize(c->compute);
-    const double t0 = PhaseTraceNow();
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+        e = cudaEventCreate(&ev[i]);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(ev[0], c->copy);
     if (e == cudaSuccess && h2d_bytes)
         e = cudaMemcpyAsync(d_up, h_up, h2d_bytes, cudaMemcpyHostToDevice, c->copy);
-    if (e == cudaSuccess && !concurrent)
-        e = cudaStreamSynchronize(c->copy);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(ev[1], c->copy);
+    // concurrent: the other direction starts together with the first; otherwise after it
+    if (e == cudaSuccess)
+        e = cudaStreamWaitEvent(c->d2h, concurrent ? ev[0] : ev[1], 0);
     if (e == cudaSuccess && d2h_bytes)
         e = cudaMemcpyAsync(h_down, d_down, d2h_bytes, cudaMemcpyDeviceToHost, c->d2h);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(ev[2], c->d2h);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(c->copy);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(c->d2h);
-    const double t1 = PhaseTraceNow();
+    float up_ms = 0.0f, down_ms = 0.0f;
+    if (e == cudaSuccess)
+        e = cudaEventElapsedTime(&up_ms, ev[0], ev[1]);
+    if (e == cudaSuccess)
+        e = cudaEventElapsedTime(&down_ms, ev[0], ev[2]);
+    for (cudaEvent_t x : ev)
+        if (x)
+            cudaEventDestroy(x);
     c->pool.release(h_up);
     c->pool.release(h_down);
     if (e != cudaSuccess)
         return fail(GLC_ERR_CUDA, "DMA probe failed: %s", cudaGetErrorString(e));
-    *elapsed_ms = (float)(t1 - t0);
+    *elapsed_ms = std::max(up_ms, down_ms);
     return GLC_OK;
 }
 

@@ -291,7 +291,8 @@ glc_status glc_ctx_sync(glc_ctx *ctx);
 glc_status glc_flush_l2(glc_ctx *ctx);
 /* Pure-DMA probe: moves h2d_bytes host -> device and d2h_bytes device -> host between pinned host memory and
  * HBM, both directions at once (on two streams) when `concurrent` is non-zero, one after the other otherwise,
- * with no kernel in between; *elapsed_ms is the host-clock time until both are done.  The floor any end-to-end
+ * with no kernel in between; *elapsed_ms is measured with CUDA events on the copy streams (from the common start
+ * to the later of the two ends).  The floor any end-to-end
  * figure of this path can reach on this box: bench.py runs it on every rank at the same time. */
 glc_status glc_dma_probe(glc_ctx *ctx, uint64_t h2d_bytes, uint64_t d2h_bytes, int concurrent, float *elapsed_ms);
 /* FP32 non-FMA issue micro-benchmark (FMUL+FADD chains on every SM): returns achieved
