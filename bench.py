@@ -505,7 +505,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         roofline = {
             "kernel": "fast_encode_kernel (fused window + fold + 512-point FFT DCT-IV + thresholds + quantise + ordered pack)",
             "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fe_gbs / hbm_peak,
-            "peak_source": peak_src, "traffic": None, "launches_per_step": k_n["fast_encode"] / args.steps,
+            "peak_source": peak_src,
+            # profiles/r2_ncu_fast_kernels_full_summary.csv: dram read 211.9 MB + write 80.4 MB for a launch of 51 680
+            # rows = 5 655 B per row against 4 792 B algorithmic (1.18x), scaled to the rows of one launch of this run
+            "traffic": 5655.0 * rows / max(k_n["fast_encode"] / args.steps, 1),
+            "traffic_source": "ncu capture of a 51 680-row launch (5 655 B per row), scaled to this run's rows per launch",
+            "launches_per_step": k_n["fast_encode"] / args.steps,
             "ms_per_launch": fe_ms / n_l, "algorithmic_bytes_per_launch": fe_bytes / n_l,
             "kernel_ms_per_step": {k: v / args.steps for k, v in k_ms.items() if v},
         }
@@ -638,6 +643,8 @@ def bench_fast_side(device: int, _unused, args, rows: int, pairs: int, hbm_peak:
                      "peak": hbm_peak, "unit": "GB/s", "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / hbm_peak,
                      "peak_source": peak_src, "launches_per_step": n_l, "ms_per_launch": fe_ms / n_l,
                      "algorithmic_bytes_per_launch": fe_bytes / n_l,
+                     # ncu (profiles/r2_ncu_fast_kernels_full_summary.csv): 5 655 B of DRAM traffic per row
+                     "traffic": 5655.0 * rows / n_l,
                      # executed warp instructions per frame-channel (ncu, profiles/r2_ncu_fast_encode_*): the 512-point
                      # FFT alone is 880, i.e. at a perfect issue rate the FFT alone takes as long as moving the
                      # kernel's bytes at the full HBM rate: the kernel is instruction-bound by construction
@@ -724,7 +731,10 @@ def bench_flac(ctx, args) -> dict:
             "kernel_ms": k_ms, "kernel_audio_s_per_s": args.flac_seconds / (k_ms * 1e-3) if k_ms else None,
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": hbm_peak,
                          "unit": "GB/s", "frac": (alg / (k_ms * 1e-3) / 1e9) / hbm_peak if k_ms else None,
-                         "peak_source": peak_src}}
+                         "peak_source": peak_src,
+                         # ncu (profiles/r2_ncu_flac_kernels_full_summary.csv): flac_measure 111.4 MB + flac_emit
+                         # 49.2 MB of DRAM traffic for 23.04 M samples = 6.97 B per sample
+                         "traffic": 6.97 * xp.size, "algorithmic_bytes": alg}}
 
 
 def cpu_baseline(args) -> dict:
