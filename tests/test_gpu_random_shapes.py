@@ -163,3 +163,50 @@ def test_random_streams_through_the_other_decode_entry_points(gpu_ctx):
         assert np.array_equal(dec.decode_pcm16(enc), want16), f"stream {k}: 16-bit output"
         level = int(rng.integers(0, 9))
         assert dec.decode_to_flac(enc, level) == oracle.flac_encode(pcm_ref, sr, ch, level), f"stream {k}: decode -> FLAC level {level}"
+
+
+def test_mutated_containers_are_rejected_or_decoded_like_the_reference(gpu_ctx):
+    """.glc images are untrusted input (load_encoded, src/codec.rs:781-786): 600 seeded mutations of valid images
+    -- truncations, byte flips, length fields overwritten with small / huge values -- must either be refused with
+    an error or parse into a stream whose decode equals the oracle's decode of the same parsed arrays (the
+    reference's rules for duplicate / out-of-range indices and short raw bodies, src/codec.rs:626-665).  Never a
+    crash, never a huge allocation."""
+    from gapless_lossy_codec_b200 import Decoder, Encoder, GlcError, encoded_from_bytes, encoded_to_bytes
+
+    rng = np.random.default_rng(8086)
+    images = []
+    for ch, n in ((1, 3000), (2, 5000), (5, 2100)):
+        x = _signal(rng, n, ch)
+        images.append(encoded_to_bytes(Encoder(44100, gpu_ctx).encode(x, ch), gpu_ctx))
+    accepted = refused = 0
+    for it in range(600):
+        img = bytearray(images[it % len(images)])
+        kind = it % 4
+        if kind == 0:
+            img = img[: int(rng.integers(0, len(img)))]
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 5))):
+                img[int(rng.integers(0, len(img)))] ^= int(rng.integers(1, 256))
+        elif kind == 2:
+            pos = int(rng.integers(0, max(1, len(img) - 8)))
+            vals = [0, 1, 2, 7, 255, 65536, 2 ** 31, 2 ** 40, 2 ** 63 - 1, 2 ** 64 - 1]
+            val = vals[int(rng.integers(0, len(vals)))]
+            img[pos:pos + 8] = val.to_bytes(8, "little")
+        else:
+            pos = int(rng.integers(0, max(1, len(img) - 8)))
+            img[pos:pos + 8] = bytes(rng.integers(0, 256, 8, dtype=np.uint8))
+            img = img[: int(rng.integers(pos, len(img) + 1))]
+        try:
+            parsed = encoded_from_bytes(bytes(img), gpu_ctx)
+        except GlcError:
+            refused += 1
+            continue
+        try:
+            pcm = Decoder(int(parsed.channels), int(parsed.sample_rate), gpu_ctx).decode(parsed)
+        except GlcError:
+            refused += 1
+            continue
+        accepted += 1
+        if parsed.n_frames * max(1, int(parsed.channels)) <= 4096:  # keep the oracle's share of the test small
+            assert_pcm_bits_equal(pcm, oracle.decode(to_oracle(parsed)), f"mutation {it} (kind {kind})")
+    assert accepted >= 20 and refused >= 200, (accepted, refused)
