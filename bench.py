@@ -530,6 +530,17 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         # in L2), scaled to the rows of one launch of this run
         "traffic": 12008.0 * rows / max(k_n["mdct_exact"] / args.steps, 1),
         "traffic_source": "ncu capture of a 51 712-row launch (12 008 B per row), scaled to this run's rows per launch",
+        # DRAM bytes per frame-channel of every kernel of the unfused chains (ncu --set full, one encode + decode of
+        # 600 s, profiles/r2_ncu_codec_kernels_full_summary.csv) next to the algorithmic figures of SURVEY.md 8(d):
+        # the encode chain moves 5.2x and the decode chain 3.8x its algorithmic bytes (windowed A tile, dense coefficient row and IMDCT blocks round-trip
+        # HBM), which costs about 3 ms of the step; the step itself is bound by the FP32 issue rate of the two
+        # contractions, not by these bytes
+        "chain_traffic_bytes_per_frame_channel": {
+            "encode": {"window_tile": 11302, "mdct_exact": 12071, "quant_pack": 5580, "scans": 6, "gather_pairs": 760,
+                       "gather_raw": 2100, "total": 31819, "algorithmic": 4096 + 4 * 258 * 0.67 + 8 + 0.33 * 4096},
+            "decode": {"dequant": 5814 + 4, "imdct_exact": 7339, "ola": 10376, "total": 23533,
+                       "algorithmic": 4 * 258 * 0.67 + 8 + 0.33 * 4096 + 4096},
+            "source": "ncu, profiles/r2_ncu_codec_kernels_full_summary.csv (51 680 rows, raw fraction 0.33, 258 pairs per sparse row)"},
         "launches_per_step": k_n["mdct_exact"] / args.steps,
         "ms_per_launch": k_ms["mdct_exact"] / max(k_n["mdct_exact"], 1),
         "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
