@@ -273,7 +273,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # the measured non-FMA FP32 issue roof of this GPU (same run, same clocks)
     tera = C.c_double()
     chk(L.glc_measure_fp32_issue(ctx.handle, 0, C.byref(tera)))
-    fp32_roof = tera.value  # 1e12 lane-ops / s
+    fp32_roof_scalar = tera.value  # 1e12 lane-ops / s, scalar FMUL -> FADD chains
+    chk(L.glc_measure_fp32_issue(ctx.handle, 1, C.byref(tera)))
+    fp32_roof_packed = tera.value  # the same chains as packed f32x2 instructions (what the kernels issue)
+    fp32_roof = max(fp32_roof_scalar, fp32_roof_packed)
 
     def dev_step():
         de, dq = C.c_void_p(), C.c_void_p()
@@ -516,14 +519,16 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         }
     else:
       roofline = {
-        "kernel": "exact_gemm_kernel<MDCT> (direct-form MDCT contraction, EXACT mode; operands by TMA bulk copy)",
+        "kernel": "exact_gemm_kernel<MDCT> (direct-form MDCT contraction, EXACT mode; operands by TMA bulk copy, packed f32x2 multiply-then-add)",
         "bound": "fp32_issue", "achieved": achieved_tops, "peak": fp32_roof, "unit": "TFLOP/s",
         "frac": achieved_tops / fp32_roof if fp32_roof else None,
         # nominal: 148 SMs x 128 FP32 lanes x the maximum SM clock, one non-FMA operation per lane and cycle
         "peak_nominal": 148 * 128 * (clocks["sm_max_mhz"] if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e6 / 1e12,
         "frac_of_nominal": achieved_tops / (148 * 128 * (clocks["sm_max_mhz"] if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e6 / 1e12),
-        "peak_source": "FMUL+FADD issue micro-benchmark on this GPU in this run (glc_measure_fp32_issue); "
-                       "non-FMA FP32 lane-ops: tensor cores / FMA / reordering break bit-exact parity",
+        "peak_scalar": fp32_roof_scalar, "peak_packed": fp32_roof_packed,
+        "peak_source": "separate multiply-then-add issue micro-benchmarks on this GPU in this run (glc_measure_fp32_issue, "
+                       "scalar FMUL+FADD and packed f32x2; the higher of the two); non-contracted FP32 lane-ops: tensor "
+                       "cores / fused multiply-add / reordering break bit-exact parity",
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
         # profiles/r1_ncu_exact_gemm_tma_full_summary.csv: 620 965 888 B for a launch of 51 712 rows
         # (12 008 B/row = the 8 KiB A tile it reads + the 4 KiB coefficient row it writes; the table stays

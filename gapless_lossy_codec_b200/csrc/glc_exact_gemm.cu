@@ -84,12 +84,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!done);
 }
 
+#pragma nv_diag_suppress 177 // which of the helpers below are used depends on the compile-time variant
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+
+// Packed pairs of f32 (sm_100: mul/add.rn.f32x2 work on two lanes of a 64-bit register, each lane rounded to nearest
+// exactly like the scalar instruction, and an explicit .rn is never contracted into an fma): half the issue slots
+// for the same arithmetic, which matters where the kernel is bound by issue slots and not by the FMA pipe.
+__device__ __forceinline__ void lds128_x2(uint32_t addr, unsigned long long &lo, unsigned long long &hi)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
+__device__ __forceinline__ unsigned long long pack_x2(float a, float b)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_x2(unsigned long long v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul_then_add_x2(unsigned long long acc, unsigned long long a, unsigned long long t,
+                                                           unsigned long long one2, unsigned long long neg_zero2)
+{
+    // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad false (seen in the SASS), which
+    // rounds once instead of twice, and it does the same to fma(a, t, -0.0) followed by fma(p, 1.0, acc) when it can
+    // see the constants.  With the constants arriving as kernel parameters the two FMAs stay, and they are exact
+    // restatements:  a * t + (-0.0) == RN(a * t) with the sign of a zero product kept;  p * 1.0 + acc == RN(acc + p)
+    unsigned long long p, r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(a), "l"(t), "l"(neg_zero2));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p), "l"(one2), "l"(acc));
+    return r;
+}
+
+#pragma nv_diag_default 177
 
 // One TMA-engine bulk copy global -> shared, completing `bytes` on the mbarrier.
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
@@ -112,6 +145,9 @@ struct GemmParams
     uint64_t n_rows;         // rows (MDCT: frame-channels; IMDCT: compacted slots) that exist; stores are clipped
     float norm;
     float *out;              // MDCT: coefs[row][1024]; IMDCT: blocks[slot][2048]
+    // packed (f32x2) constants handed over as PARAMETERS so that ptxas cannot see their values: {1.0f, 1.0f} and
+    // {-0.0f, -0.0f} (see mul_then_add_x2)
+    unsigned long long x2_one, x2_neg_zero;
 };
 
 struct Smem
@@ -177,12 +213,22 @@ __global__ void __launch_bounds__(kGemmThreads * 8 / NC, 2) exact_gemm_kernel(co
         for (int s = 0; s < kRing; ++s)
             issue(s);
 
+#if GLC_MDCT_X2
+    static_assert(!GLC_MDCT_X2 || NC == 8, "packed variant: 8 x 8 outputs per thread");
+    unsigned long long acc2[8][NC / 2]; // pairs of adjacent outputs, +0.0 in both lanes
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c)
+            acc2[r][c] = 0ull;
+#else
     float acc[8][NC];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c < NC; ++c)
             acc[r][c] = 0.0f;
+#endif
 
     for (int s = 0; s < n_stages; ++s)
     {
@@ -191,6 +237,26 @@ __global__ void __launch_bounds__(kGemmThreads * 8 / NC, 2) exact_gemm_kernel(co
 
         const float *As = sm.a[slot] + ty * 8;
         const float *Ts = sm.t[slot] + tx * 4;
+#if GLC_MDCT_X2
+#pragma unroll 4
+        for (int ii = 0; ii < kKC; ++ii)
+        {
+            const float4 a_lo = *reinterpret_cast<const float4 *>(As + ii * kBM);
+            const float4 a_hi = *reinterpret_cast<const float4 *>(As + ii * kBM + 4);
+            const ulonglong2 t_lo = *reinterpret_cast<const ulonglong2 *>(Ts + ii * kBN);
+            const ulonglong2 t_hi = *reinterpret_cast<const ulonglong2 *>(Ts + ii * kBN + 64);
+            const float a[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+            const unsigned long long t2[4] = {t_lo.x, t_lo.y, t_hi.x, t_hi.y};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+            {
+                const unsigned long long ar = pack_x2(a[r], a[r]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    acc2[r][c] = mul_then_add_x2(acc2[r][c], ar, t2[c], p.x2_one, p.x2_neg_zero);
+            }
+        }
+#else
 #pragma unroll 4
         for (int ii = 0; ii < kKC; ++ii)
         {
@@ -208,6 +274,7 @@ __global__ void __launch_bounds__(kGemmThreads * 8 / NC, 2) exact_gemm_kernel(co
                 for (int c = 0; c < NC; ++c)
                     acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
         }
+#endif
         __syncwarp();
         uint32_t nth = 0;
         if (lane == 0)
@@ -226,6 +293,14 @@ __global__ void __launch_bounds__(kGemmThreads * 8 / NC, 2) exact_gemm_kernel(co
     }
 
     // ---- epilogue: * norm, two float4 stores per row ----
+#if GLC_MDCT_X2
+    float acc[8][NC];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c)
+            unpack_x2(acc2[r][c], acc[r][2 * c], acc[r][2 * c + 1]);
+#endif
     const int n_lo = n_block * kBN + tx * 4;
     const int n_hi = n_lo + 64;
     const uint64_t row0 = m_tile * kBM + ty * 8;
@@ -356,12 +431,22 @@ __global__ void __launch_bounds__(kImdctThreads, GLC_IMDCT_MINB) imdct_sparse_ke
 
     constexpr int RW = kImdctRowsPerWarp;
     constexpr int NO = 4 * kImdctNQ; // outputs per thread and row
+#if GLC_IMDCT_X2
+    static_assert(!GLC_IMDCT_X2 || (kImdctRowsPerWarp == 2 && !GLC_IMDCT_ROWMASK), "packed variant: two rows per warp, union masks");
+    unsigned long long acc2[RW][NO / 2]; // pairs of adjacent outputs; +0.0 in both lanes
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int c = 0; c < NO / 2; ++c)
+            acc2[r][c] = 0ull;
+#else
     float acc[RW][NO];
 #pragma unroll
     for (int r = 0; r < RW; ++r)
 #pragma unroll
         for (int c = 0; c < NO; ++c)
             acc[r][c] = 0.0f;
+#endif
 
     for (int s = 0; s < n_stages; ++s)
     {
@@ -389,6 +474,21 @@ __global__ void __launch_bounds__(kImdctThreads, GLC_IMDCT_MINB) imdct_sparse_ke
                 asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[0]), "=f"(a[1]) : "r"(a_base + ii * (kImdctBM * 4)));
             else
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[0]) : "r"(a_base + ii * (kImdctBM * 4)));
+#if GLC_IMDCT_X2
+            {
+                const unsigned long long a0 = pack_x2(a[0], a[0]), a1 = pack_x2(a[1], a[1]);
+#pragma unroll
+                for (int q = 0; q < kImdctNQ; ++q)
+                {
+                    unsigned long long t0, t1;
+                    lds128_x2(t_base + ii * (kImdctBN * 4) + q * 512, t0, t1);
+                    acc2[0][2 * q + 0] = mul_then_add_x2(acc2[0][2 * q + 0], a0, t0, p.x2_one, p.x2_neg_zero);
+                    acc2[0][2 * q + 1] = mul_then_add_x2(acc2[0][2 * q + 1], a0, t1, p.x2_one, p.x2_neg_zero);
+                    acc2[1][2 * q + 0] = mul_then_add_x2(acc2[1][2 * q + 0], a1, t0, p.x2_one, p.x2_neg_zero);
+                    acc2[1][2 * q + 1] = mul_then_add_x2(acc2[1][2 * q + 1], a1, t1, p.x2_one, p.x2_neg_zero);
+                }
+            }
+#else
             float t[NO];
 #pragma unroll
             for (int q = 0; q < kImdctNQ; ++q)
@@ -422,6 +522,7 @@ __global__ void __launch_bounds__(kImdctThreads, GLC_IMDCT_MINB) imdct_sparse_ke
                 for (int c = 0; c < NO; ++c)
                     acc[r][c] = __fadd_rn(acc[r][c], __fmul_rn(a[r], t[c]));
 #endif
+#endif // GLC_IMDCT_X2
         }
         __syncwarp();
         uint32_t nth = 0;
@@ -441,6 +542,14 @@ __global__ void __launch_bounds__(kImdctThreads, GLC_IMDCT_MINB) imdct_sparse_ke
     }
 
     // ---- epilogue: * norm, * window, float4 per 128 outputs (a warp writes contiguous 512-byte runs) ----
+#if GLC_IMDCT_X2
+    float acc[RW][NO];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int c = 0; c < NO / 2; ++c)
+            unpack_x2(acc2[r][c], acc[r][2 * c], acc[r][2 * c + 1]);
+#endif
     const uint64_t row0 = m_tile * kImdctBM + warp * RW;
 #pragma unroll
     for (int q = 0; q < kImdctNQ; ++q)
@@ -574,6 +683,8 @@ cudaError_t launch_mdct_exact(const MdctLaunch &l, cudaStream_t s)
     p.n_rows = l.row_end - l.row_begin;
     p.norm = l.norm;
     p.out = l.coefs + l.row_begin * kHop; // rows of this launch are numbered from 0 inside the kernel
+    p.x2_one = 0x3f8000003f800000ull;
+    p.x2_neg_zero = 0x8000000080000000ull;
     return launch_gemm(p, m_tiles, s);
 }
 
@@ -590,6 +701,8 @@ cudaError_t launch_imdct_exact(const ImdctLaunch &l, cudaStream_t s)
     p.n_rows = l.max_slots;
     p.norm = l.norm;
     p.out = l.blocks;
+    p.x2_one = 0x3f8000003f800000ull;
+    p.x2_neg_zero = 0x8000000080000000ull;
     GLC_SET_MAX_DYN_SMEM_ONCE(imdct_sparse_kernel, sizeof(ImdctSmem));
     const uint64_t m_tiles = (l.max_slots + kImdctBM - 1) / kImdctBM;
     if (m_tiles == 0)

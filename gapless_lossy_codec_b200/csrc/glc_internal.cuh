@@ -50,6 +50,14 @@ constexpr int kImdctThreads = kImdctWarps * 32;                        // 512
 // GLC_IMDCT_ROWMASK: one step mask per ROW instead of one per warp; the warp still walks the union of its rows'
 // index sets (one table load per step) but executes a row's multiply-adds only at the steps that row holds
 // (warp-uniform branches)
+// GLC_MDCT_X2 / GLC_IMDCT_X2: the multiply-adds of the contraction as packed f32x2 instructions (two lanes per
+// issue slot, each lane rounded exactly like the scalar FMUL / FADD pair; see mul_then_add_x2 in glc_exact_gemm.cu)
+#ifndef GLC_MDCT_X2
+#define GLC_MDCT_X2 1
+#endif
+#ifndef GLC_IMDCT_X2
+#define GLC_IMDCT_X2 1
+#endif
 #ifndef GLC_IMDCT_ROWMASK
 #define GLC_IMDCT_ROWMASK 0
 #endif

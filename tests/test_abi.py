@@ -100,3 +100,29 @@ def test_rust_shim_binds_only_exported_symbols_and_matches_integration_md():
     for rel in ("build.rs", os.path.join("src", "codec.rs"), os.path.join("src", "flac.rs")):
         body = open(os.path.join(shim, rel)).read().rstrip("\n")
         assert any(b.rstrip("\n") == body for b in blocks), f"INTEGRATION.md does not embed {rel} as it is on disk"
+
+
+def test_exact_kernels_never_contract_a_multiply_add():
+    """Bit-exact parity rests on two roundings per multiply-add.  Read it off the SASS of
+    the built library: the EXACT contractions hold no scalar FFMA, and every packed FFMA2 is one of the two exact
+    forms (product + (-0.0), or addend + p * 1.0, the constant in a uniform register) in equal numbers -- ptxas has
+    been seen to contract a packed multiply / add pair into one fused FFMA2, which this test would catch on a
+    machine without a GPU."""
+    import shutil
+    import sys
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_histogram
+
+    hist = sass_histogram.histogram()
+    for kernel in ("exact_gemm_kernel<8>", "imdct_sparse_kernel"):
+        h = hist[kernel]
+        assert h["FFMA"] == 0, (kernel, "scalar fused multiply-add in an EXACT kernel")
+        assert h["x2fused"] == 0, (kernel, "a packed multiply / add pair was contracted")
+        if h["FFMA2"]:
+            assert h["x2mul"] == h["x2add"] == h["FFMA2"] // 2, (kernel, dict(h))
+        else:
+            assert h["FMUL"] >= h["FADD"] > 0, (kernel, dict(h))  # the scalar build: FMUL + FADD pairs
+        assert h["UBLKCP"] > 0 and h["SYNCS"] > 0, (kernel, "operands must arrive by TMA bulk copies on mbarriers")
