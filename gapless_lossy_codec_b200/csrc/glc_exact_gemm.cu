@@ -6,9 +6,13 @@
 // with `s` starting at +0.0, strictly ascending reduction index, the product rounded to f32 and
 // then the sum rounded to f32 (no FMA).  Bit-exact parity needs exactly that chain per output, so
 // this is a dense contraction  C[row][n] = sum_j A[j][row] * T[k(j)][n]  whose reduction order is
-// fixed and whose inner operation is FMUL followed by FADD.  Tensor cores, FMA contraction and
-// split-K are all ruled out; the binding roof is FP32 issue, not HBM,
-// so the design goal is: every issue slot an FMUL or FADD.
+// fixed and whose inner operation is a rounded multiply followed by a rounded add.  Tensor cores, FMA
+// contraction and split-K are all ruled out; the binding roof is the FP32 pipe
+// at two instructions per multiply-add, not HBM.  Since round 2 both kernels issue those two instructions
+// as PACKED pairs (f32x2: two outputs per issue slot, the FMA pipe busy for two cycles), which takes the
+// operand loads and bookkeeping off the critical issue port: see mul_then_add_x2 below for the exact forms
+// and for why their constants are kernel parameters.  GLC_MDCT_X2=0 / GLC_IMDCT_X2=0 build the scalar
+// FMUL + FADD loops (bit-identical, 39.7 instead of 37.9 ms and 13.8 instead of 12.6 ms per hour of stereo).
 //
 // Mapping:
 //   * CTA tile = 128 rows (frame-channels) x 128 outputs, 256 threads, 8x8 outputs per thread,
@@ -38,7 +42,7 @@ constexpr int kStageFloats = kKC * kBN;        // 4096 floats = 16 KiB per opera
 constexpr int kStageBytes = kStageFloats * 4;
 constexpr int kRing = 3;
 // Outputs per thread of the MDCT contraction.  Measured on the hour-long bench signal: 8 (256 threads,
-// 126 registers, 16 warps/SM) 39.6 ms; 4 (512 threads, 64 registers, 32 warps/SM) 41.7 ms -- twice the
+// 126 registers, 16 warps/SM) 39.6 ms (scalar build); 4 (512 threads, 64 registers, 32 warps/SM) 41.7 ms -- twice the
 // warps do not make up for 3 instead of 4 operand loads per 64 instead of 128 arithmetic instructions.
 #ifndef GLC_MDCT_NC
 #define GLC_MDCT_NC 8

@@ -111,8 +111,8 @@ glc_status glc_device_count(int *count);
  * host libm (MdctTables::new, src/codec.rs:326-356) and uploads them. */
 glc_status glc_ctx_create(int device, glc_mode mode, glc_ctx **out);
 void glc_ctx_destroy(glc_ctx *ctx);
-/* Tuning knobs: `reserved` is ignored (it selected packed f32x2 kernel variants that measured no
- * faster than scalar FMUL+FADD and were removed); wave_rows = frame-channel rows per encode
+/* Tuning knobs: `reserved` is ignored (it once selected kernel variants at run time; variants are
+ * compile-time choices now); wave_rows = frame-channel rows per encode
  * pipeline wave, 0 = automatic (multiples of 37 row tiles). */
 glc_status glc_ctx_set_tuning(glc_ctx *ctx, int reserved, uint64_t wave_rows);
 /* Pinned host memory for callers that want zero-staging transfers (optional). */
@@ -295,7 +295,8 @@ glc_status glc_flush_l2(glc_ctx *ctx);
  * to the later of the two ends).  The floor any end-to-end
  * figure of this path can reach on this box: bench.py runs it on every rank at the same time. */
 glc_status glc_dma_probe(glc_ctx *ctx, uint64_t h2d_bytes, uint64_t d2h_bytes, int concurrent, float *elapsed_ms);
-/* FP32 non-FMA issue micro-benchmark (FMUL+FADD chains on every SM): returns achieved
+/* FP32 multiply-then-add micro-benchmark (independent chains on every SM; packed = 0: scalar FMUL + FADD,
+ * packed != 0: the same chains as f32x2 instructions, what the EXACT contractions issue): returns achieved
  * 1e12 lane-operations per second; the measured roof for the EXACT transform kernels. */
 glc_status glc_measure_fp32_issue(glc_ctx *ctx, int packed, double *tera_ops_per_s);
 
