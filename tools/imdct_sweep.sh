@@ -1,6 +1,9 @@
 #!/bin/bash
 # Builds imdct_sparse_kernel variants ON THE GPU BOX and times the decode of the hour-long bench signal.
 # usage (under gpurun): bash tools/imdct_sweep.sh "<flags variant 1>" "<flags variant 2>" ...
+# flags: -DGLC_IMDCT_BN=256|512 -DGLC_IMDCT_RW=1|2 -DGLC_IMDCT_KC=16|32 -DGLC_IMDCT_RING=2..6 -DGLC_IMDCT_MINB=1..3
+#        -DGLC_IMDCT_ROWMASK=1 -DGLC_IMDCT_X2=0|1 (packed multiply-adds, default 1; the shapes other than 2 rows per warp and
+#        ROWMASK need -DGLC_IMDCT_X2=0) -DGLC_MDCT_X2=0|1
 cd "$(dirname "$0")/../gapless_lossy_codec_b200/csrc" || exit 1
 unset CC CXX
 for v in "$@"; do
