@@ -445,6 +445,28 @@ static cudaEvent_t get_event(glc_ctx *c)
     return e;
 }
 
+// Events of one call: they go back to the context's free list on every exit path (an error return used to
+// drop them).
+struct EventScope
+{
+    glc_ctx *c;
+    std::vector<cudaEvent_t> held;
+    explicit EventScope(glc_ctx *ctx) : c(ctx) {}
+    EventScope(const EventScope &) = delete;
+    EventScope &operator=(const EventScope &) = delete;
+    cudaEvent_t get()
+    {
+        cudaEvent_t e = get_event(c);
+        held.push_back(e);
+        return e;
+    }
+    ~EventScope()
+    {
+        for (cudaEvent_t e : held)
+            c->ev_free.push_back(e);
+    }
+};
+
 // Brackets one kernel launch for the per-kernel statistics.
 struct LaunchScope
 {
@@ -1469,15 +1491,27 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
 
     // H2D plan: file i is needed by the first wave that touches it; copy whole files in order,
     // splitting big files at wave boundaries so that copy and compute overlap.
+    EventScope events(c);
     cudaEvent_t ev_copy = nullptr;
     if (host_pcm)
-        ev_copy = get_event(c);
+        ev_copy = events.get();
     // host output: per-wave D2H of the compacted pairs / raw bodies on the d2h stream
+    struct PinnedGuard // releases the block on every exit path
+    {
+        PinnedPool &pool;
+        void *p;
+        ~PinnedGuard()
+        {
+            if (p)
+                pool.release(p);
+        }
+    } tot_guard{c->pool, nullptr};
     uint64_t *h_tot = nullptr; // [2 * waves] running totals after each wave (pinned)
     std::vector<cudaEvent_t> wave_done;
     if (ho)
     {
         h_tot = (uint64_t *)c->pool.alloc(16 * waves.size());
+        tot_guard.p = h_tot;
         if (!h_tot)
             return fail(GLC_ERR_NO_MEMORY, "pinned host allocation failed");
     }
@@ -1520,7 +1554,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         c->stats.d2h_bytes += (p1 - p0) * sizeof(glc_pair) + (q1 - q0) * sizeof(int16_t);
         // wave w + 2 writes the same half of the ring: it waits for these copies
         if (!ev_ring[w & 1])
-            ev_ring[w & 1] = get_event(c);
+            ev_ring[w & 1] = events.get();
         CUDA_TRY(cudaEventRecord(ev_ring[w & 1], c->d2h));
         return GLC_OK;
     };
@@ -1715,7 +1749,7 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         {
             CUDA_TRY(cudaMemcpyAsync(h_tot + 2 * wi, de->d_pair_off + w.r1, 8, cudaMemcpyDeviceToHost, cs));
             CUDA_TRY(cudaMemcpyAsync(h_tot + 2 * wi + 1, de->d_raw_off + w.f1, 8, cudaMemcpyDeviceToHost, cs));
-            cudaEvent_t ev = get_event(c);
+            cudaEvent_t ev = events.get();
             wave_done.push_back(ev);
             CUDA_TRY(cudaEventRecord(ev, cs));
             if (wi >= 1)
@@ -1733,19 +1767,11 @@ static glc_status encode_core(glc_encoder *enc, const std::vector<FileDesc> &fil
         c->hwm_pairs_per_row = std::max(c->hwm_pairs_per_row, (double)ho->n_pairs / (double)tot_rows);
         c->hwm_raw_per_row = std::max(c->hwm_raw_per_row, (double)ho->n_raw / (double)tot_rows);
         c->stats.d2h_bytes += 16 * waves.size();
-        c->pool.release(h_tot);
-        for (cudaEvent_t e : wave_done)
-            c->ev_free.push_back(e);
         // the ring goes back to the pool in compute-stream order: the last copies out of it come first
         for (cudaEvent_t e : ev_ring)
             if (e)
-            {
                 CUDA_TRY(cudaStreamWaitEvent(cs, e, 0));
-                c->ev_free.push_back(e);
-            }
     }
-    if (ev_copy)
-        c->ev_free.push_back(ev_copy);
     tr.mark("waves");
     return GLC_OK;
 }
@@ -2186,12 +2212,11 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
     for (const DecFileDesc &f : files)
         if (f.channels >= 3 && f.channels <= 8)
             ola_tile_channels = std::max(ola_tile_channels, f.channels);
-    std::vector<cudaEvent_t> used_events;
+    EventScope events(c);
     if (io)
     {
         // the copy stream writes buffers that were handed out in compute-stream order
-        cudaEvent_t ev = get_event(c);
-        used_events.push_back(ev);
+        cudaEvent_t ev = events.get();
         CUDA_TRY(cudaEventRecord(ev, cs));
         CUDA_TRY(cudaStreamWaitEvent(c->copy, ev, 0));
     }
@@ -2234,8 +2259,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
             }
             if (any || wi == 0)
             {
-                cudaEvent_t ev = get_event(c);
-                used_events.push_back(ev);
+                cudaEvent_t ev = events.get();
                 CUDA_TRY(cudaEventRecord(ev, c->copy));
                 CUDA_TRY(cudaStreamWaitEvent(cs, ev, 0));
             }
@@ -2323,8 +2347,7 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         if (io && io->h_out)
         {
             // D2H of the finished range, clipped to every file's gapless window
-            cudaEvent_t ev = get_event(c);
-            used_events.push_back(ev);
+            cudaEvent_t ev = events.get();
             CUDA_TRY(cudaEventRecord(ev, cs));
             CUDA_TRY(cudaStreamWaitEvent(c->d2h, ev, 0));
             for (uint32_t i = 0; i < n_files; ++i)
@@ -2352,8 +2375,6 @@ static glc_status decode_core(glc_ctx *c, const std::vector<DecFileDesc> &files,
         CUDA_TRY(cudaStreamSynchronize(c->d2h));
         CUDA_TRY(cudaStreamSynchronize(cs));
     }
-    for (cudaEvent_t e : used_events)
-        c->ev_free.push_back(e);
     ds.keep(d_out); // the caller owns the output; the scratch blocks are released by `ds`
     tr.mark("free");
     *d_out_ret = d_out;
